@@ -1,0 +1,79 @@
+"""Deterministic integer-only synthetic RGBA frames.
+
+One implementation on torch integer ops, so the same code produces the host frames the CPU oracle
+is fed in tests and the device-resident frame streams bench.py times.  Pinned by a CRC in
+tests/test_synth.py.  Kinds:
+  video  smooth triangle-wave gradients + small hash noise + letterbox bars (partly compressible)
+  flat   constant 0x336699FF (maximum compressibility, exercises the RLE paths)
+  noise  hash bytes (incompressible, exercises both raw fallbacks of hap.c:460 and :478)
+"""
+from __future__ import annotations
+
+import torch
+
+SEED = 20260923
+_M32 = 0xFFFFFFFF
+
+
+def pcg_hash(v: torch.Tensor) -> torch.Tensor:
+    """PCG-RXS-M-XS 32-bit output hash on int64 tensors holding uint32 values."""
+    state = (v * 747796405 + 2891336453) & _M32
+    shift = (state >> 28) + 4
+    word = (((state >> shift) ^ state) * 277803737) & _M32
+    return ((word >> 22) ^ word) & _M32
+
+
+def _tri8(t: torch.Tensor) -> torch.Tensor:
+    u = t & 511
+    return torch.where(u < 256, u, 511 - u)
+
+
+def frame(width: int, height: int, index: int = 0, kind: str = "video", alpha: str = "opaque",
+          seed: int = SEED, noise_bits: int = 3, device="cpu") -> torch.Tensor:
+    """(height, width, 4) uint8 RGBA frame number `index`."""
+    dev = torch.device(device)
+    if kind == "flat":
+        px = torch.tensor([0x33, 0x66, 0x99, 0xFF], dtype=torch.uint8, device=dev)
+        return px.expand(height, width, 4).contiguous()
+    y = torch.arange(height, dtype=torch.int64, device=dev).view(height, 1, 1)
+    x = torch.arange(width, dtype=torch.int64, device=dev).view(1, width, 1)
+    c = torch.arange(4, dtype=torch.int64, device=dev).view(1, 1, 4)
+    lin = (((index * height + y) * width + x) * 4 + c) & _M32
+    h = pcg_hash(lin ^ (seed & _M32))
+    if kind == "noise":
+        out = (h >> 24).to(torch.uint8)
+        out[..., 3] = 255
+        return out
+    if kind != "video":
+        raise ValueError(kind)
+    k1 = torch.tensor([1, 2, 3, 1], dtype=torch.int64, device=dev).view(1, 1, 4)
+    k2 = torch.tensor([2, 1, 3, 1], dtype=torch.int64, device=dev).view(1, 1, 4)
+    px = (3 * x * k1 * 512) // width + 8 * index
+    py = (5 * y * k2 * 512) // height
+    half = 1 << (noise_bits - 1) if noise_bits > 0 else 0
+    nz = (h >> (32 - noise_bits)) - half if noise_bits > 0 else torch.zeros_like(h)
+    v = 43 + _tri8(px) // 3 + _tri8(py) // 3 + nz
+    v = v.clamp(0, 255)
+    bar = height // 10
+    letter = (y < bar) | (y >= height - bar)
+    v = torch.where(letter, torch.full_like(v, 16), v)
+    out = v.to(torch.uint8)
+    if alpha == "opaque":
+        out[..., 3] = 255
+    elif alpha == "ramp":
+        # horizontal ramp blended with a soft disc (Hap Q Alpha / Hap Alpha configs)
+        ramp = (255 * x) // max(width - 1, 1)
+        cx, cy = width // 2, height // 2
+        r2 = (x - cx) * (x - cx) + (y - cy) * (y - cy)
+        rad2 = (min(width, height) // 3) ** 2
+        disc = (255 - (255 * r2) // max(rad2, 1)).clamp(0, 255)
+        a = torch.maximum(ramp.expand(height, width, 1), disc)
+        out[..., 3] = a[..., 0].to(torch.uint8)
+    else:
+        raise ValueError(alpha)
+    return out
+
+
+def frames(width: int, height: int, count: int, start: int = 0, **kw) -> torch.Tensor:
+    """(count, height, width, 4) uint8"""
+    return torch.stack([frame(width, height, start + i, **kw) for i in range(count)])
