@@ -1,0 +1,393 @@
+// hap_b200/csrc/bc_block.cuh -- K1-K4 block math: one 4x4 RGBA block -> one 8/16-byte S3TC/RGTC block.
+//
+// The block compressors sit UPSTREAM of the reference (which takes already-compressed DXT bytes,
+// /root/reference/source/hap.h:82-104; formats per documentation/HapVideoDRAFT.md:22-27); the
+// north star makes them the encode hot kernel.  Quality bar: PSNR within 0.1 dB of a squish-HIGH
+// (iterative cluster fit) encode, which oracle/bc_oracle.c restates.
+//
+// Work decomposition: ONE THREAD PER BLOCK.  SURVEY.md H1: at the bandwidth target a 4x4 block has
+// ~13 warp-instructions if a warp owns it but ~420 thread-instructions if a thread owns it; all 16
+// texels live in registers, every reduction is a private serial sum (no shuffles, no idle lanes),
+// and coalescing is restored by staging tiles through shared memory in the kernels (bc_encode.cuh).
+//
+// Colour fit: principal axis of the block's covariance (power iteration), then REFINE rounds of
+// [project texels onto the current segment -> 4 clusters] + [2x2 least squares for the endpoints
+// given those clusters] -- the same normal equations cluster fit solves, for the partition the
+// current endpoints imply instead of all 969 -- then 5:6:5 rounding and a final nearest-index pass
+// against the decoder's integer palette.
+//
+// Floating point is written with explicit fused multiply-adds (hap_fma) and the translation unit is
+// built with -fmad=false, so the CPU twin used by the tests (tests/emu/bc_twin.cc) reproduces the
+// GPU result bit for bit: IEEE add/mul/div/sqrt and fma are exact on both sides.
+#pragma once
+#include "simt.h"
+#include <math.h>
+
+namespace hapb200 {
+
+#ifdef HAPB200_EMU
+#define HAP_HD inline
+static inline float hap_fma(float a, float b, float c) { return fmaf(a, b, c); }
+#else
+#define HAP_HD __host__ __device__ __forceinline__
+HAP_HD float hap_fma(float a, float b, float c) { return fmaf(a, b, c); }
+#endif
+
+
+struct Block8 { uint32_t lo, hi; };
+
+HAP_HD int hap_clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+
+// ---- BC4 / RGTC1: 16 values -> 8 bytes ------------------------------------------------------------
+// 8-value mode (a0 > a1): palette a0, a1, then 6 interpolants (decoder: ((8-i)a0 + (i-1)a1)/7).
+// Endpoints start at max/min; one least-squares refinement of the endpoints is kept if it lowers the
+// error against the decoder's truncating palette.
+HAP_HD int bc4_error_and_indices(const int v[16], int a0, int a1, uint32_t &bits_lo, uint32_t &bits_hi)
+{
+    // a0 > a1.  level L in 0..7 counted from a1 (min) upwards: value = ((7-L)*a1 + L*a0)/7
+    int pal[8];
+#pragma unroll
+    for (int L = 0; L < 8; L++) pal[L] = ((7 - L) * a1 + L * a0) / 7;
+    const int range = a0 - a1;
+    uint64_t bits = 0;
+    int err = 0;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        int L = hap_clampi(((v[t] - a1) * 14 + range) / (2 * range), 0, 7);  // round((v-a1)*7/range)
+        // the truncating palette is not exactly uniform: check the neighbour below/above
+        int d = v[t] - pal[L];
+        int best = d * d, bl = L;
+        if (L > 0) { int e = v[t] - pal[L - 1]; if (e * e < best) { best = e * e; bl = L - 1; } }
+        if (L < 7) { int e = v[t] - pal[L + 1]; if (e * e < best) { best = e * e; bl = L + 1; } }
+        err += best;
+        // DXT index: 0 = a0, 1 = a1, 2..7 = interpolants from a0 towards a1
+        uint32_t idx = bl == 7 ? 0u : bl == 0 ? 1u : (uint32_t)(8 - bl);
+        bits |= (uint64_t)idx << (3 * t);
+    }
+    bits_lo = (uint32_t)bits;
+    bits_hi = (uint32_t)(bits >> 32);
+    return err;
+}
+
+HAP_HD Block8 encode_bc4_block(const int v[16])
+{
+    int mn = 255, mx = 0;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        mn = v[t] < mn ? v[t] : mn;
+        mx = v[t] > mx ? v[t] : mx;
+    }
+    Block8 out;
+    if (mx == mn) {
+        // a0 == a1 selects the 6-value mode; index 0 decodes to a0 in both modes
+        out.lo = (uint32_t)mx | ((uint32_t)mn << 8);
+        out.hi = 0;
+        return out;
+    }
+    uint32_t lo, hi;
+    int a0 = mx, a1 = mn;
+    int err = bc4_error_and_indices(v, a0, a1, lo, hi);
+    if (err != 0) {
+        // least squares for (a0, a1) given the levels just chosen: v ~ a1 + (a0-a1)*L/7
+        float sl = 0.f, sll = 0.f, sv = 0.f, slv = 0.f;
+        const int range = a0 - a1;
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            int L = hap_clampi(((v[t] - a1) * 14 + range) / (2 * range), 0, 7);
+            float f = (float)L * (1.0f / 7.0f);
+            sl += f;
+            sll = hap_fma(f, f, sll);
+            sv += (float)v[t];
+            slv = hap_fma(f, (float)v[t], slv);
+        }
+        float det = 16.0f * sll - sl * sl;
+        if (det > 1e-3f) {
+            float slope = (16.0f * slv - sl * sv) / det;
+            float base = (sv - slope * sl) * (1.0f / 16.0f);
+            int n1 = hap_clampi((int)floorf(base + 0.5f), 0, 255);
+            int n0 = hap_clampi((int)floorf(base + slope + 0.5f), 0, 255);
+            if (n0 > n1 && (n0 != a0 || n1 != a1)) {
+                uint32_t lo2, hi2;
+                int err2 = bc4_error_and_indices(v, n0, n1, lo2, hi2);
+                if (err2 < err) { a0 = n0; a1 = n1; lo = lo2; hi = hi2; }
+            }
+        }
+    }
+    out.lo = (uint32_t)a0 | ((uint32_t)a1 << 8) | (lo << 16);
+    out.hi = (lo >> 16) | (hi << 16);
+    return out;
+}
+
+// ---- BC1 colour block: 16 (r,g,b) in 0..255 -> 8 bytes, always 4-colour mode ---------------------
+HAP_HD uint32_t expand5(uint32_t c) { return (c << 3) | (c >> 2); }
+HAP_HD uint32_t expand6(uint32_t c) { return (c << 2) | (c >> 4); }
+
+// Picks, for one channel, the pair of grid values around the float endpoints (a,b) that minimises the
+// cluster-weighted squared error.  levels = 31 or 63; values stay in 0..255 units.
+HAP_HD void snap_channel(float &a, float &b, float a2, float b2, float ab, float ax, float bx, float levels)
+{
+    const float to_grid = levels * (1.0f / 255.0f), from_grid = 255.0f / levels;
+    float a_lo = floorf(a * to_grid), b_lo = floorf(b * to_grid);
+    float best = 1e30f, best_a = a, best_b = b;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float ga = fminf(a_lo + (float)(k & 1), levels), gb = fminf(b_lo + (float)(k >> 1), levels);
+        // the decoder expands by bit replication, which equals round(g*255/levels) for 5 and 6 bits
+        float ca = floorf(hap_fma(ga, from_grid, 0.5f)), cb = floorf(hap_fma(gb, from_grid, 0.5f));
+        float e = hap_fma(ca * ca, a2, hap_fma(cb * cb, b2, 2.0f * (ca * cb * ab - ca * ax - cb * bx)));
+        if (e < best) { best = e; best_a = ca; best_b = cb; }
+    }
+    a = best_a;
+    b = best_b;
+}
+
+// REFINE: least-squares rounds; RESNAP: extra rounds of Lloyd on the snapped endpoints; EXACT: final
+// indices by true nearest palette colour (else by projection onto the palette segment).
+template <int REFINE, int RESNAP, bool EXACT>
+HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const float b[16])
+{
+    // mean and covariance
+    float mr = 0.f, mg = 0.f, mb = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; t++) { mr += r[t]; mg += g[t]; mb += b[t]; }
+    mr *= 0.0625f; mg *= 0.0625f; mb *= 0.0625f;
+    float crr = 0.f, crg = 0.f, crb = 0.f, cgg = 0.f, cgb = 0.f, cbb = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        float dr = r[t] - mr, dg = g[t] - mg, db = b[t] - mb;
+        crr = hap_fma(dr, dr, crr); crg = hap_fma(dr, dg, crg); crb = hap_fma(dr, db, crb);
+        cgg = hap_fma(dg, dg, cgg); cgb = hap_fma(dg, db, cgb); cbb = hap_fma(db, db, cbb);
+    }
+    float ar, ag, ab_, br, bg, bb;  // float endpoints a (index 0 side) and b
+    const float var = crr + cgg + cbb;
+    if (var < 0.5f) {
+        // (near-)flat block: bracket the mean with its 5:6:5 grid neighbours so the 4 palette entries
+        // straddle it; the final nearest-index pass picks the closest
+        ar = floorf(mr * (31.0f / 255.0f)) * (255.0f / 31.0f); br = ceilf(mr * (31.0f / 255.0f)) * (255.0f / 31.0f);
+        ag = floorf(mg * (63.0f / 255.0f)) * (255.0f / 63.0f); bg = ceilf(mg * (63.0f / 255.0f)) * (255.0f / 63.0f);
+        ab_ = floorf(mb * (31.0f / 255.0f)) * (255.0f / 31.0f); bb = ceilf(mb * (31.0f / 255.0f)) * (255.0f / 31.0f);
+    } else {
+        // principal axis: power iteration from the covariance row with the largest diagonal
+        float vr, vg, vb;
+        if (crr >= cgg && crr >= cbb) { vr = crr; vg = crg; vb = crb; }
+        else if (cgg >= cbb) { vr = crg; vg = cgg; vb = cgb; }
+        else { vr = crb; vg = cgb; vb = cbb; }
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            float nr = hap_fma(crr, vr, hap_fma(crg, vg, crb * vb));
+            float ng = hap_fma(crg, vr, hap_fma(cgg, vg, cgb * vb));
+            float nb = hap_fma(crb, vr, hap_fma(cgb, vg, cbb * vb));
+            float m = fmaxf(fabsf(nr), fmaxf(fabsf(ng), fabsf(nb)));
+            float inv = 1.0f / m;
+            vr = nr * inv; vg = ng * inv; vb = nb * inv;
+        }
+        // extent along the axis
+        float tmin = 1e30f, tmax = -1e30f;
+        const float vv = hap_fma(vr, vr, hap_fma(vg, vg, vb * vb));
+        const float ivv = 1.0f / vv;
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            float d = hap_fma(r[t] - mr, vr, hap_fma(g[t] - mg, vg, (b[t] - mb) * vb)) * ivv;
+            tmin = fminf(tmin, d);
+            tmax = fmaxf(tmax, d);
+        }
+        ar = hap_fma(vr, tmin, mr); ag = hap_fma(vg, tmin, mg); ab_ = hap_fma(vb, tmin, mb);
+        br = hap_fma(vr, tmax, mr); bg = hap_fma(vg, tmax, mg); bb = hap_fma(vb, tmax, mb);
+        // refinement: clusters implied by the current segment, then least squares for the endpoints
+        float a2 = 0.f, b2 = 0.f, ab = 0.f;
+        float axr = 0.f, axg = 0.f, axb = 0.f, bxr = 0.f, bxg = 0.f, bxb = 0.f;
+#pragma unroll 1
+        for (int it = 0; it < REFINE; it++) {
+            float dr = br - ar, dg = bg - ag, db = bb - ab_;
+            float dd = hap_fma(dr, dr, hap_fma(dg, dg, db * db));
+            if (dd < 1e-6f) break;
+            float scale = 3.0f / dd;
+            float na2 = 0.f, nb2 = 0.f, nab = 0.f;
+            float naxr = 0.f, naxg = 0.f, naxb = 0.f, nbxr = 0.f, nbxg = 0.f, nbxb = 0.f;
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+                float s = hap_fma(r[t] - ar, dr, hap_fma(g[t] - ag, dg, (b[t] - ab_) * db)) * scale;
+                float q = floorf(s + 0.5f);
+                q = fminf(fmaxf(q, 0.0f), 3.0f);
+                float be = q * (1.0f / 3.0f), al = 1.0f - be;
+                na2 = hap_fma(al, al, na2); nb2 = hap_fma(be, be, nb2); nab = hap_fma(al, be, nab);
+                naxr = hap_fma(al, r[t], naxr); naxg = hap_fma(al, g[t], naxg); naxb = hap_fma(al, b[t], naxb);
+                nbxr = hap_fma(be, r[t], nbxr); nbxg = hap_fma(be, g[t], nbxg); nbxb = hap_fma(be, b[t], nbxb);
+            }
+            float det = na2 * nb2 - nab * nab;
+            if (det < 1e-4f) break;
+            a2 = na2; b2 = nb2; ab = nab;
+            axr = naxr; axg = naxg; axb = naxb; bxr = nbxr; bxg = nbxg; bxb = nbxb;
+            float idet = 1.0f / det;
+            ar = fminf(fmaxf((axr * b2 - bxr * ab) * idet, 0.f), 255.f);
+            ag = fminf(fmaxf((axg * b2 - bxg * ab) * idet, 0.f), 255.f);
+            ab_ = fminf(fmaxf((axb * b2 - bxb * ab) * idet, 0.f), 255.f);
+            br = fminf(fmaxf((bxr * a2 - axr * ab) * idet, 0.f), 255.f);
+            bg = fminf(fmaxf((bxg * a2 - axg * ab) * idet, 0.f), 255.f);
+            bb = fminf(fmaxf((bxb * a2 - axb * ab) * idet, 0.f), 255.f);
+        }
+        // Grid snapping: for fixed clusters the squared error is separable per channel,
+        //   E(a,b) = a^2 A2 + b^2 B2 + 2ab AB - 2a AX - 2b BX,
+        // so each channel tries floor/ceil of both endpoints on its 5- or 6-bit grid (4 candidates).
+        if (a2 + b2 > 0.f) {
+            snap_channel(ar, br, a2, b2, ab, axr, bxr, 31.0f);
+            snap_channel(ag, bg, a2, b2, ab, axg, bxg, 63.0f);
+            snap_channel(ab_, bb, a2, b2, ab, axb, bxb, 31.0f);
+#pragma unroll 1
+            for (int it = 0; it < RESNAP; it++) {
+                // Lloyd on the quantised problem: re-cluster against the snapped segment, re-solve, re-snap
+                float dr = br - ar, dg = bg - ag, db = bb - ab_;
+                float dd = hap_fma(dr, dr, hap_fma(dg, dg, db * db));
+                if (dd < 1e-6f) break;
+                float scale = 3.0f / dd;
+                float na2 = 0.f, nb2 = 0.f, nab = 0.f;
+                float naxr = 0.f, naxg = 0.f, naxb = 0.f, nbxr = 0.f, nbxg = 0.f, nbxb = 0.f;
+#pragma unroll
+                for (int t = 0; t < 16; t++) {
+                    float s2 = hap_fma(r[t] - ar, dr, hap_fma(g[t] - ag, dg, (b[t] - ab_) * db)) * scale;
+                    float q = fminf(fmaxf(floorf(s2 + 0.5f), 0.0f), 3.0f);
+                    float be = q * (1.0f / 3.0f), al = 1.0f - be;
+                    na2 = hap_fma(al, al, na2); nb2 = hap_fma(be, be, nb2); nab = hap_fma(al, be, nab);
+                    naxr = hap_fma(al, r[t], naxr); naxg = hap_fma(al, g[t], naxg); naxb = hap_fma(al, b[t], naxb);
+                    nbxr = hap_fma(be, r[t], nbxr); nbxg = hap_fma(be, g[t], nbxg); nbxb = hap_fma(be, b[t], nbxb);
+                }
+                float det = na2 * nb2 - nab * nab;
+                if (det < 1e-4f) break;
+                float idet = 1.0f / det;
+                float car = fminf(fmaxf((naxr * nb2 - nbxr * nab) * idet, 0.f), 255.f), cbr = fminf(fmaxf((nbxr * na2 - naxr * nab) * idet, 0.f), 255.f);
+                float cag = fminf(fmaxf((naxg * nb2 - nbxg * nab) * idet, 0.f), 255.f), cbg = fminf(fmaxf((nbxg * na2 - naxg * nab) * idet, 0.f), 255.f);
+                float cab = fminf(fmaxf((naxb * nb2 - nbxb * nab) * idet, 0.f), 255.f), cbb2 = fminf(fmaxf((nbxb * na2 - naxb * nab) * idet, 0.f), 255.f);
+                snap_channel(car, cbr, na2, nb2, nab, naxr, nbxr, 31.0f);
+                snap_channel(cag, cbg, na2, nb2, nab, naxg, nbxg, 63.0f);
+                snap_channel(cab, cbb2, na2, nb2, nab, naxb, nbxb, 31.0f);
+                ar = car; br = cbr; ag = cag; bg = cbg; ab_ = cab; bb = cbb2;
+            }
+        }
+    }
+    // 5:6:5
+    uint32_t a5r = (uint32_t)hap_clampi((int)floorf(hap_fma(ar, 31.0f / 255.0f, 0.5f)), 0, 31);
+    uint32_t a6g = (uint32_t)hap_clampi((int)floorf(hap_fma(ag, 63.0f / 255.0f, 0.5f)), 0, 63);
+    uint32_t a5b = (uint32_t)hap_clampi((int)floorf(hap_fma(ab_, 31.0f / 255.0f, 0.5f)), 0, 31);
+    uint32_t b5r = (uint32_t)hap_clampi((int)floorf(hap_fma(br, 31.0f / 255.0f, 0.5f)), 0, 31);
+    uint32_t b6g = (uint32_t)hap_clampi((int)floorf(hap_fma(bg, 63.0f / 255.0f, 0.5f)), 0, 63);
+    uint32_t b5b = (uint32_t)hap_clampi((int)floorf(hap_fma(bb, 31.0f / 255.0f, 0.5f)), 0, 31);
+    uint32_t c0 = (a5r << 11) | (a6g << 5) | a5b, c1 = (b5r << 11) | (b6g << 5) | b5b;
+    Block8 out;
+    if (c0 == c1) {
+        out.lo = c0 | (c1 << 16);
+        out.hi = 0;  // index 0 = c0 in either mode
+        return out;
+    }
+    if (c0 < c1) {
+        uint32_t tmp;
+        tmp = c0; c0 = c1; c1 = tmp;
+        tmp = a5r; a5r = b5r; b5r = tmp;
+        tmp = a6g; a6g = b6g; b6g = tmp;
+        tmp = a5b; a5b = b5b; b5b = tmp;
+    }
+    // decoder palette ends (c0 = first endpoint), float for the projection
+    const float p0r = (float)expand5(a5r), p0g = (float)expand6(a6g), p0b = (float)expand5(a5b);
+    const float p1r = (float)expand5(b5r), p1g = (float)expand6(b6g), p1b = (float)expand5(b5b);
+    const float er = p1r - p0r, eg = p1g - p0g, eb = p1b - p0b;
+    const float ee = hap_fma(er, er, hap_fma(eg, eg, eb * eb));
+    const float sc = 3.0f / ee;
+    uint32_t bits = 0;
+    if (EXACT) {
+        // decoder palette (truncating thirds), DXT numbering 0 = c0, 1 = c1, 2, 3
+        const float q2r = floorf((2.0f * p0r + p1r) * (1.0f / 3.0f) + 0.01f), q3r = floorf((p0r + 2.0f * p1r) * (1.0f / 3.0f) + 0.01f);
+        const float q2g = floorf((2.0f * p0g + p1g) * (1.0f / 3.0f) + 0.01f), q3g = floorf((p0g + 2.0f * p1g) * (1.0f / 3.0f) + 0.01f);
+        const float q2b = floorf((2.0f * p0b + p1b) * (1.0f / 3.0f) + 0.01f), q3b = floorf((p0b + 2.0f * p1b) * (1.0f / 3.0f) + 0.01f);
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            float d0 = hap_fma(r[t] - p0r, r[t] - p0r, hap_fma(g[t] - p0g, g[t] - p0g, (b[t] - p0b) * (b[t] - p0b)));
+            float d1 = hap_fma(r[t] - p1r, r[t] - p1r, hap_fma(g[t] - p1g, g[t] - p1g, (b[t] - p1b) * (b[t] - p1b)));
+            float d2 = hap_fma(r[t] - q2r, r[t] - q2r, hap_fma(g[t] - q2g, g[t] - q2g, (b[t] - q2b) * (b[t] - q2b)));
+            float d3 = hap_fma(r[t] - q3r, r[t] - q3r, hap_fma(g[t] - q3g, g[t] - q3g, (b[t] - q3b) * (b[t] - q3b)));
+            uint32_t i01 = d1 < d0 ? 1u : 0u, i23 = d3 < d2 ? 3u : 2u;
+            uint32_t idx = fminf(d2, d3) < fminf(d0, d1) ? i23 : i01;
+            bits |= idx << (2 * t);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            float s = hap_fma(r[t] - p0r, er, hap_fma(g[t] - p0g, eg, (b[t] - p0b) * eb)) * sc;
+            int q = hap_clampi((int)floorf(s + 0.5f), 0, 3);  // 0 = c0 ... 3 = c1 along the segment
+            // DXT numbering: 0 = c0, 1 = c1, 2 = (2c0+c1)/3, 3 = (c0+2c1)/3
+            uint32_t idx = q == 0 ? 0u : q == 3 ? 1u : (uint32_t)(q + 1);
+            bits |= idx << (2 * t);
+        }
+    }
+    out.lo = c0 | (c1 << 16);
+    out.hi = bits;
+    return out;
+}
+
+// ---- scaled YCoCg (van Waveren & Castano 2007) ----------------------------------------------------
+// Per block: co = (R-B)/2, cg = (-R+2G-B)/4 kept as exact half/quarter integers; scale = largest of
+// {4,2,1} with |co*scale|,|cg*scale| <= 127; stored texel (Co', Cg', (scale-1)*8, Y).
+HAP_HD void ycocg_block(const uint32_t px[16], float cr[16], float cg_[16], float cb[16], int yv[16])
+{
+    int m2 = 0, m4 = 0;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        int R = px[t] & 0xFF, G = (px[t] >> 8) & 0xFF, B = (px[t] >> 16) & 0xFF;
+        int co2 = R - B, cg4 = -R + 2 * G - B;
+        int a2 = co2 < 0 ? -co2 : co2, a4 = cg4 < 0 ? -cg4 : cg4;
+        m2 = a2 > m2 ? a2 : m2;
+        m4 = a4 > m4 ? a4 : m4;
+    }
+    int scale = 1;
+    if (m2 * 4 <= 254 && m4 * 4 <= 508) scale = 4;
+    else if (m2 * 2 <= 254 && m4 * 2 <= 508) scale = 2;
+    const float sb = (float)((scale - 1) << 3);
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        int R = px[t] & 0xFF, G = (px[t] >> 8) & 0xFF, B = (px[t] >> 16) & 0xFF;
+        // round half up of co2*scale/2 and cg4*scale/4 (arithmetic shift floors)
+        int co = ((R - B) * scale + 1) >> 1;
+        int cg = ((-R + 2 * G - B) * scale + 2) >> 2;
+        cr[t] = (float)hap_clampi(co + 128, 0, 255);
+        cg_[t] = (float)hap_clampi(cg + 128, 0, 255);
+        cb[t] = sb;
+        yv[t] = (R + 2 * G + B + 2) >> 2;
+    }
+}
+
+// ---- whole-block encoders: px = 16 RGBA8 texels, row-major inside the block, little-endian ------
+HAP_HD Block8 encode_dxt1(const uint32_t px[16])
+{
+    float r[16], g[16], b[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        r[t] = (float)(px[t] & 0xFF); g[t] = (float)((px[t] >> 8) & 0xFF); b[t] = (float)((px[t] >> 16) & 0xFF);
+    }
+    return encode_colour_block<2, 1, true>(r, g, b);
+}
+
+HAP_HD void encode_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colour)
+{
+    int a[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) a[t] = (int)(px[t] >> 24);
+    alpha = encode_bc4_block(a);
+    colour = encode_dxt1(px);
+}
+
+HAP_HD void encode_ycocg_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colour)
+{
+    float r[16], g[16], b[16];
+    int y[16];
+    ycocg_block(px, r, g, b, y);
+    alpha = encode_bc4_block(y);
+    colour = encode_colour_block<2, 0, false>(r, g, b);
+}
+
+HAP_HD Block8 encode_rgtc1_alpha(const uint32_t px[16])
+{
+    int a[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) a[t] = (int)(px[t] >> 24);
+    return encode_bc4_block(a);
+}
+
+}  // namespace hapb200

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
     const uint32_t in_end = job.src_bytes;
     const uint32_t expected = job.dst_bytes;
 
+    if (job.compressor == 0) return;  // unused slot of a batched frame (hap_parse.cuh)
     if (job.compressor == kHapChunkRaw) {
         // hap.c:630-636: verbatim chunk
         if (in_end != expected) {

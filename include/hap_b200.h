@@ -1,0 +1,91 @@
+/*
+ * include/hap_b200.h -- extensions of libhap_b200.so beyond the reference's hap.h.
+ *
+ * The reference API starts at DXT bytes and moves one frame per call through host memory
+ * (/root/reference/source/hap.h:98-137).  A B200 is only busy when whole streams of frames stay in
+ * HBM, so these entry points add (a) the RGBA side of the path -- the block compressors that sit
+ * upstream of HapEncode and the block decoder downstream of HapDecode -- and (b) batched,
+ * device-resident, stream-ordered variants.  Plain C ABI: pointers, sizes, no CUDA types (a stream is
+ * passed as void*, NULL = the library's own stream; the call then returns after the work finished).
+ * Results are HapResult values (hap.h).
+ */
+#ifndef hap_b200_h
+#define hap_b200_h
+#include "hap.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Hap flavours by FourCC (reference documentation/HapVideoDRAFT.md:132-142) */
+enum HapB200Codec {
+    HapB200Codec_Hap1 = 0, /* RGB DXT1                         "Hap"            */
+    HapB200Codec_Hap5 = 1, /* RGBA DXT5                        "Hap Alpha"      */
+    HapB200Codec_HapY = 2, /* scaled YCoCg DXT5                "Hap Q"          */
+    HapB200Codec_HapM = 3, /* scaled YCoCg DXT5 + alpha RGTC1  "Hap Q Alpha"    */
+    HapB200Codec_HapA = 4  /* alpha RGTC1                      "Hap Alpha-Only" */
+};
+
+const char *HapB200Version(void);
+/* kernels launched by this library in this process so far (bench.py reports the delta) */
+unsigned long long HapB200KernelLaunchCount(void);
+
+/* worst-case frame size for a width x height frame of `codec` (HapMaxEncodedLength on its textures) */
+unsigned long HapB200MaxEncodedLengthRGBA(unsigned int width, unsigned int height, unsigned int codec,
+                                          unsigned int chunkCount);
+/* bytes of texture `index` (0 or 1) of a width x height frame of `codec`; 0 when absent */
+unsigned long HapB200TextureBytes(unsigned int width, unsigned int height, unsigned int codec, unsigned int index);
+
+/* One RGBA8 frame (row-major, rowBytes stride, width/height multiples of 4) -> one Hap frame.
+ * Host or device pointers.  Fuses block compression, Snappy and frame assembly on the GPU. */
+unsigned int HapB200EncodeRGBA(const void *rgba, unsigned int width, unsigned int height, unsigned long rowBytes,
+                               unsigned int codec, unsigned int compressor, unsigned int chunkCount,
+                               void *outputBuffer, unsigned long outputBufferBytes,
+                               unsigned long *outputBufferBytesUsed);
+
+/* One Hap frame -> RGBA8 (all textures of the frame combined; YCoCg converted, alpha merged). */
+unsigned int HapB200DecodeRGBA(const void *inputBuffer, unsigned long inputBufferBytes, unsigned int width,
+                               unsigned int height, void *rgba, unsigned long rowBytes);
+
+/* ---- device-resident batches: every pointer below is a DEVICE pointer, 16-byte aligned ---------- */
+
+/* frames x RGBA8 -> frames x Hap frame at out + f*outStride, encoded length in used[f] (device). */
+unsigned int HapB200EncodeRGBABatch(const void *rgba, unsigned int frames, unsigned long frameStride,
+                                    unsigned int width, unsigned int height, unsigned long rowBytes,
+                                    unsigned int codec, unsigned int compressor, unsigned int chunkCount,
+                                    void *out, unsigned long outStride, unsigned long long *used, void *stream);
+
+/* HapEncode over a batch: texture t of frame f at textures[t] + f*textureStrides[t]. */
+unsigned int HapB200EncodeBatch(unsigned int count, const void **textures, unsigned long *textureStrides,
+                                unsigned long *textureBytes, unsigned int *textureFormats,
+                                unsigned int *compressors, unsigned int *chunkCounts, unsigned int frames,
+                                void *out, unsigned long outStride, unsigned long long *used, void *stream);
+
+/* HapDecode over a batch: frame f at in + f*inStride with inBytes[f] bytes -> texture `index` at
+ * out + f*outStride; per frame used[f], formats[f], results[f] (HapResult) are device arrays.
+ * maxChunks bounds the chunk count of any frame (frames with more report Bad_Arguments). */
+unsigned int HapB200DecodeBatch(const void *in, unsigned int frames, unsigned long inStride,
+                                const unsigned long long *inBytes, unsigned int index, unsigned int maxChunks,
+                                void *out, unsigned long outStride, unsigned long long *used,
+                                unsigned int *formats, unsigned int *results, void *stream);
+
+/* Decode straight to RGBA8: HapDecode of every texture + block decode (+ YCoCg, + alpha merge). */
+unsigned int HapB200DecodeRGBABatch(const void *in, unsigned int frames, unsigned long inStride,
+                                    const unsigned long long *inBytes, unsigned int maxChunks,
+                                    unsigned int width, unsigned int height, void *rgba,
+                                    unsigned long frameStride, unsigned long rowBytes, unsigned int *results,
+                                    void *stream);
+
+/* Block codecs alone (K1-K4 / K8), batched: kind = HapB200Codec; HapM writes/reads the YCoCg plane at
+ * blocks and the RGTC1 plane at blocks + HapB200TextureBytes(.., 0). */
+unsigned int HapB200BlockEncodeBatch(const void *rgba, unsigned int frames, unsigned long frameStride,
+                                     unsigned int width, unsigned int height, unsigned long rowBytes,
+                                     unsigned int codec, void *blocks, unsigned long blocksStride, void *stream);
+unsigned int HapB200BlockDecodeBatch(const void *blocks, unsigned int frames, unsigned long blocksStride,
+                                     unsigned int width, unsigned int height, unsigned int codec, void *rgba,
+                                     unsigned long frameStride, unsigned long rowBytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,177 @@
+// tests/emu/test_encode_emu.cc -- TEST INFRASTRUCTURE ONLY.
+// Runs the CUDA encode path (K5 fragment compressor, K6 plan + place) under the fiber SIMT emulator
+// and checks the produced frames with the CPU oracle decoder (and the unmodified reference, when
+// oracle/_ref/libhap_ref.so is present): payload bit-exact, container identical where it must be.
+#define HAPB200_EMU
+#include "hap_assemble.cuh"
+#include "hap_host.h"
+#include "snappy_decode.cuh"
+
+extern "C" {
+#include "bc_oracle.h"
+#include "hap_oracle.h"
+#include "snappy_oracle.h"
+}
+#include <dlfcn.h>
+#include <random>
+#include <string>
+
+using namespace hapb200;
+static int g_fail = 0;
+typedef unsigned (*decode_fn)(const void *, unsigned long, unsigned, orc_decode_cb, void *, void *, unsigned long,
+                              unsigned long *, unsigned *);
+static decode_fn g_ref_decode = nullptr;
+
+static void serial_cb(orc_work_fn fn, void *p, unsigned n, void *) { for (unsigned i = 0; i < n; i++) fn(p, i); }
+
+struct Tex { std::vector<uint8_t> data; unsigned fmt, compressor, chunks; };
+
+static std::vector<uint8_t> gpu_encode(const std::vector<Tex> &tex, int mode)
+{
+    TextureArgs ta[2];
+    for (size_t i = 0; i < tex.size(); i++) ta[i] = TextureArgs{tex[i].data.size(), tex[i].fmt, tex[i].compressor, tex[i].chunks};
+    FrameGeom G;
+    if (build_frame_geom((uint32_t)tex.size(), ta, G) != 0) abort();
+    // one device-style input buffer holding both textures, 16-byte aligned offsets, exact size + no slack
+    size_t off1 = (tex[0].data.size() + 15) & ~(size_t)15;
+    std::vector<uint8_t> in(off1 + (tex.size() > 1 ? tex[1].data.size() : 0));
+    memcpy(in.data(), tex[0].data.data(), tex[0].data.size());
+    if (tex.size() > 1) { memcpy(in.data() + off1, tex[1].data.data(), tex[1].data.size()); G.s[1].in_offset = off1; }
+    unsigned long lens[2], cap;
+    unsigned fmts[2], chunks[2];
+    for (size_t i = 0; i < tex.size(); i++) { lens[i] = tex[i].data.size(); fmts[i] = tex[i].fmt; chunks[i] = tex[i].chunks; }
+    cap = orc_HapMaxEncodedLength((unsigned)tex.size(), lens, fmts, chunks);
+    std::vector<uint8_t> scratch((size_t)G.frags_per_frame * kFragCap), out(cap, 0xEE);
+    std::vector<uint32_t> fsize(G.frags_per_frame), fdst(G.frags_per_frame);
+    unsigned long long used = 0;
+    emu::g_order_mode() = mode;
+    HAP_LAUNCH(snappy_encode_fragments_kernel, dim3(G.frags_per_frame), dim3(kEncThreads), sizeof(EncodeSmem), nullptr,
+               in.data(), G, scratch.data(), fsize.data());
+    HAP_LAUNCH(hap_plan_frames_kernel, dim3(1), dim3(kPlanThreads), 0, nullptr, G, in.data(), fsize.data(), fdst.data(),
+               out.data(), (uint64_t)cap, &used);
+    HAP_LAUNCH(hap_place_fragments_kernel, dim3(G.frags_per_frame), dim3(kPlaceThreads), 0, nullptr, G, in.data(),
+               scratch.data(), fsize.data(), fdst.data(), out.data(), (uint64_t)cap);
+    if (used > cap) { fprintf(stderr, "used %llu > cap %lu\n", used, cap); abort(); }
+    out.resize(used);
+    return out;
+}
+
+static void check(const std::string &name, const std::vector<Tex> &tex, int mode, double *ratio = nullptr)
+{
+    std::vector<uint8_t> frame = gpu_encode(tex, mode);
+    bool ok = true;
+    std::string why;
+    unsigned cnt = 0;
+    if (orc_HapGetFrameTextureCount(frame.data(), frame.size(), &cnt) != 0 || cnt != tex.size()) { ok = false; why = "texture count"; }
+    // oracle encode of the same input: container decisions that do not depend on Snappy bytes must agree
+    {
+        const void *ins[2]; unsigned long lens[2]; unsigned fmts[2], comps[2], chunks[2];
+        for (size_t i = 0; i < tex.size(); i++) { ins[i] = tex[i].data.data(); lens[i] = tex[i].data.size(); fmts[i] = tex[i].fmt; comps[i] = tex[i].compressor; chunks[i] = tex[i].chunks; }
+        unsigned long cap = orc_HapMaxEncodedLength((unsigned)tex.size(), lens, fmts, chunks), oused = 0;
+        std::vector<uint8_t> of(cap);
+        unsigned r = orc_HapEncode((unsigned)tex.size(), ins, lens, fmts, comps, chunks, of.data(), cap, &oused);
+        if (r != 0) { ok = false; why = "oracle encode failed"; }
+        bool all_none = true;
+        for (auto &t : tex) all_none = all_none && t.compressor == 0;
+        if (all_none && (oused != frame.size() || memcmp(of.data(), frame.data(), oused) != 0)) { ok = false; why = "None frame differs from oracle"; }
+        for (unsigned i = 0; i < tex.size() && ok; i++) {
+            int kc_o = 0, kc_g = 0;
+            orc_HapGetFrameTextureChunkCount(of.data(), oused, i, &kc_o);
+            orc_HapGetFrameTextureChunkCount(frame.data(), frame.size(), i, &kc_g);
+            // the raw/complex decision may differ when sizes are borderline; chunk counts agree when both are complex
+            if (kc_o != kc_g && kc_o != 1 && kc_g != 1) { ok = false; why = "chunk count differs from oracle"; }
+        }
+        if (ratio) *ratio = (double)frame.size() / (double)oused;
+    }
+    for (unsigned i = 0; i < tex.size() && ok; i++) {
+        for (int which = 0; which < 2; which++) {
+            decode_fn fn = which == 0 ? (decode_fn)orc_HapDecode : g_ref_decode;
+            if (!fn) continue;
+            std::vector<uint8_t> back(tex[i].data.size() + 8, 0x77);
+            unsigned long used = 0; unsigned fmt = 0;
+            unsigned r = fn(frame.data(), frame.size(), i, serial_cb, nullptr, back.data(), tex[i].data.size(), &used, &fmt);
+            size_t expect = tex[i].data.size();
+            if (r != 0 || fmt != tex[i].fmt) { ok = false; why = std::string(which ? "reference" : "oracle") + " decode result " + std::to_string(r); break; }
+            // on the Snappy path bytes/chunks truncates, trailing bytes are not carried
+            if (used != expect) {
+                uint32_t k = limited_chunk_count(expect, tex[i].fmt, tex[i].chunks);
+                if (used != (expect / k) * k) { ok = false; why = "decoded length"; break; }
+            }
+            if (memcmp(back.data(), tex[i].data.data(), used) != 0) { ok = false; why = std::string(which ? "reference" : "oracle") + " payload mismatch"; break; }
+        }
+    }
+    if (!ok) { g_fail++; fprintf(stderr, "FAIL %s mode %d: %s (frame %zu bytes)\n", name.c_str(), mode, why.c_str(), frame.size()); }
+}
+
+int main(int argc, char **argv)
+{
+    int modes = argc > 1 ? atoi(argv[1]) : 3;
+    const char *refso = argc > 2 ? argv[2] : nullptr;
+    if (refso) {
+        void *h = dlopen(refso, RTLD_NOW | RTLD_LOCAL);
+        if (h) g_ref_decode = (decode_fn)dlsym(h, "HapDecode");
+        printf("reference decoder: %s\n", g_ref_decode ? "loaded" : "unavailable");
+    }
+    std::mt19937 rng(777);
+    // a 256x128 picture with gradients + noise + bars, block-compressed by the oracle
+    const int W = 256, H = 128;
+    std::vector<uint8_t> img(W * H * 4);
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            uint8_t *p = &img[4 * (y * W + x)];
+            bool bar = y < 16 || y >= H - 16;
+            for (int c = 0; c < 3; c++) p[c] = bar ? 16 : (uint8_t)(40 + (x * (c + 1)) % 160 + (y * 3) % 40 + (rng() % 4));
+            p[3] = (uint8_t)(x);
+        }
+    auto blocks = [&](int kind) {
+        std::vector<uint8_t> b((W / 4) * (H / 4) * (kind == 0 || kind == 3 ? 8 : 16));
+        if (kind == 0) orc_bc1_encode_clusterfit(img.data(), W, H, b.data(), 1);
+        else if (kind == 1) orc_bc3_encode_clusterfit(img.data(), W, H, b.data(), 1);
+        else if (kind == 2) orc_ycocg_dxt5_encode_clusterfit(img.data(), W, H, b.data(), 1);
+        else orc_bc4_encode_squish(img.data(), W, H, 3, b.data());
+        return b;
+    };
+    std::vector<uint8_t> dxt1 = blocks(0), dxt5 = blocks(1), ycocg = blocks(2), rgtc = blocks(3);
+    std::vector<uint8_t> noise(70000 - 70000 % 16), flat(16 * 5000);
+    for (auto &b : noise) b = (uint8_t)rng();
+    for (size_t i = 0; i < flat.size(); i++) flat[i] = (uint8_t)(0x30 + (i % 16));
+    // bigger than one fragment, so chunk streams are concatenations of fragment streams
+    std::vector<uint8_t> big;
+    for (int r = 0; r < 5; r++) big.insert(big.end(), ycocg.begin(), ycocg.end());
+    for (size_t i = 0; i < big.size(); i += 977) big[i] ^= (uint8_t)rng();
+
+    struct Case { std::string name; std::vector<Tex> tex; };
+    std::vector<Case> cases = {
+        {"dxt1_1chunk", {{dxt1, 0x83F0, 1, 1}}},
+        {"dxt1_3chunks", {{dxt1, 0x83F0, 1, 3}}},
+        {"dxt5_4chunks", {{dxt5, 0x83F3, 1, 4}}},
+        {"ycocg_8chunks", {{ycocg, 0x01, 1, 8}}},
+        {"ycocg_limit_7_to_x", {{ycocg, 0x01, 1, 7}}},
+        {"rgtc_2chunks", {{rgtc, 0x8DBB, 1, 2}}},
+        {"hapm", {{ycocg, 0x01, 1, 4}, {rgtc, 0x8DBB, 1, 2}}},
+        {"hapm_mixed_none", {{ycocg, 0x01, 0, 4}, {rgtc, 0x8DBB, 1, 2}}},
+        {"none_single", {{dxt5, 0x83F3, 0, 5}}},
+        {"none_pair", {{ycocg, 0x01, 0, 1}, {rgtc, 0x8DBB, 0, 1}}},
+        {"noise_fallback_whole", {{noise, 0x83F3, 1, 2}}},
+        {"flat_rle", {{flat, 0x01, 1, 2}}},
+        {"big_multi_fragment", {{big, 0x01, 1, 2}}},
+        {"big_1chunk", {{big, 0x8E8C, 1, 1}}},
+        {"tiny_16", {{std::vector<uint8_t>(16, 0x55), 0x01, 1, 1}}},
+        {"tiny_8", {{std::vector<uint8_t>(8, 0x11), 0x83F0, 1, 1}}},
+        {"kat_a_64x55", {{std::vector<uint8_t>(64, 0x55), 0x83F0, 1, 1}}},
+    };
+    // per-chunk fallback: half compressible, half noise, two chunks
+    {
+        std::vector<uint8_t> mix(ycocg.begin(), ycocg.begin() + 16384);
+        mix.insert(mix.end(), noise.begin(), noise.begin() + 16384);
+        cases.push_back({"mixed_chunk_fallback", {{mix, 0x01, 1, 2}}});
+    }
+    for (int mode = 0; mode < modes; mode++)
+        for (auto &c : cases) {
+            double ratio = 0;
+            check(c.name, c.tex, mode, &ratio);
+            if (mode == 0) printf("  %-26s size vs oracle-encoded frame: %.3f\n", c.name.c_str(), ratio);
+        }
+    printf("%zu cases x %d modes, %d failures\n", cases.size(), modes, g_fail);
+    return g_fail ? 1 : 0;
+}
