@@ -144,7 +144,7 @@ HAP_HD void snap_channel(float &a, float &b, float a2, float b2, float ab, float
 // REFINE: least-squares rounds; RESNAP: extra rounds of Lloyd on the snapped endpoints; EXACT: final
 // indices by true nearest palette colour (else by projection onto the palette segment).
 template <int REFINE, int RESNAP, bool EXACT>
-HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const float b[16])
+HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const float b[16], int fixed_blue5 = -1)
 {
     // mean and covariance
     float mr = 0.f, mg = 0.f, mb = 0.f;
@@ -271,6 +271,7 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
     uint32_t b5r = (uint32_t)hap_clampi((int)floorf(hap_fma(br, 31.0f / 255.0f, 0.5f)), 0, 31);
     uint32_t b6g = (uint32_t)hap_clampi((int)floorf(hap_fma(bg, 63.0f / 255.0f, 0.5f)), 0, 63);
     uint32_t b5b = (uint32_t)hap_clampi((int)floorf(hap_fma(bb, 31.0f / 255.0f, 0.5f)), 0, 31);
+    if (fixed_blue5 >= 0) a5b = b5b = (uint32_t)fixed_blue5;  // scaled YCoCg: the scale code must survive exactly
     uint32_t c0 = (a5r << 11) | (a6g << 5) | a5b, c1 = (b5r << 11) | (b6g << 5) | b5b;
     Block8 out;
     if (c0 == c1) {
@@ -325,7 +326,7 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
 // ---- scaled YCoCg (van Waveren & Castano 2007) ----------------------------------------------------
 // Per block: co = (R-B)/2, cg = (-R+2G-B)/4 kept as exact half/quarter integers; scale = largest of
 // {4,2,1} with |co*scale|,|cg*scale| <= 127; stored texel (Co', Cg', (scale-1)*8, Y).
-HAP_HD void ycocg_block(const uint32_t px[16], float cr[16], float cg_[16], float cb[16], int yv[16])
+HAP_HD int ycocg_block(const uint32_t px[16], float cr[16], float cg_[16], float cb[16], int yv[16])
 {
     int m2 = 0, m4 = 0;
 #pragma unroll
@@ -351,6 +352,7 @@ HAP_HD void ycocg_block(const uint32_t px[16], float cr[16], float cg_[16], floa
         cb[t] = sb;
         yv[t] = (R + 2 * G + B + 2) >> 2;
     }
+    return scale - 1;  // 5-bit blue code 0, 1 or 3: expands to B' = 0, 8, 24
 }
 
 // ---- whole-block encoders: px = 16 RGBA8 texels, row-major inside the block, little-endian ------
@@ -377,9 +379,9 @@ HAP_HD void encode_ycocg_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colo
 {
     float r[16], g[16], b[16];
     int y[16];
-    ycocg_block(px, r, g, b, y);
+    const int code = ycocg_block(px, r, g, b, y);
     alpha = encode_bc4_block(y);
-    colour = encode_colour_block<2, 0, false>(r, g, b);
+    colour = encode_colour_block<2, 0, false>(r, g, b, code);
 }
 
 HAP_HD Block8 encode_rgtc1_alpha(const uint32_t px[16])

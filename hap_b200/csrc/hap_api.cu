@@ -1,0 +1,784 @@
+// hap_b200/csrc/hap_api.cu -- the C-ABI of libhap_b200.so: the six entry points of include/hap.h
+// (same signatures and behaviour as /root/reference/source/hap.h:76-152) and the extensions of
+// include/hap_b200.h.  Host code here only validates arguments, walks section headers, moves
+// buffers and launches kernels; all compression, decompression, block coding and frame assembly
+// runs in the kernels of this directory.  There is no CPU implementation of any of those steps in
+// this library: without a CUDA device the compute entry points return HapResult_Internal_Error.
+#include "../../include/hap_b200.h"
+
+#include "bc_decode.cuh"
+#include "bc_encode.cuh"
+#include "hap_assemble.cuh"
+#include "hap_host.h"
+#include "hap_parse.cuh"
+#include "snappy_decode.cuh"
+#include "snappy_encode.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+using namespace hapb200;
+
+namespace {
+
+std::atomic<unsigned long long> g_launches{0};
+#define HAP_KLAUNCH(kernel, grid, block, smem, stream, ...)                \
+    do {                                                                   \
+        HAP_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__);        \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                \
+    } while (0)
+
+struct Runtime {
+    std::mutex mu;          // serialises the host-pointer entry points (they share one stream)
+    bool ready = false;
+    bool failed = false;
+    cudaStream_t stream = nullptr;
+};
+Runtime g_rt;
+std::once_flag g_once;
+
+void runtime_init()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { g_rt.failed = true; cudaGetLastError(); return; }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;  // keep freed scratch in the pool: steady-state calls never hit the OS
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    bool ok = cudaFuncSetAttribute(snappy_decode_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(DecodeSmem)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(snappy_encode_fragments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(EncodeSmem)) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&g_rt.stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) { g_rt.failed = true; cudaGetLastError(); return; }
+    g_rt.ready = true;
+}
+
+bool runtime_ok()
+{
+    std::call_once(g_once, runtime_init);
+    return g_rt.ready;
+}
+
+bool is_device_pointer(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// stream-ordered scratch
+struct DevBuf {
+    void *p = nullptr;
+    cudaStream_t s;
+    explicit DevBuf(cudaStream_t st) : s(st) {}
+    bool alloc(size_t n) { return cudaMallocAsync(&p, n ? n : 16, s) == cudaSuccess; }
+    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+inline uint64_t align16(uint64_t v) { return (v + 15) & ~15ull; }
+
+// ---- codec tables ------------------------------------------------------------------------------
+struct CodecInfo {
+    uint32_t textures;
+    uint32_t fmt[2];
+    uint32_t block_bytes[2];
+    int bc_kind;
+};
+bool codec_info(unsigned codec, CodecInfo &c)
+{
+    switch (codec) {
+    case HapB200Codec_Hap1: c = {1, {HapFmt_RGB_DXT1, 0}, {8, 0}, kBcDxt1}; return true;
+    case HapB200Codec_Hap5: c = {1, {HapFmt_RGBA_DXT5, 0}, {16, 0}, kBcDxt5}; return true;
+    case HapB200Codec_HapY: c = {1, {HapFmt_YCoCg_DXT5, 0}, {16, 0}, kBcYCoCg}; return true;
+    case HapB200Codec_HapM: c = {2, {HapFmt_YCoCg_DXT5, HapFmt_A_RGTC1}, {16, 8}, kBcYCoCgPlusAlpha}; return true;
+    case HapB200Codec_HapA: c = {1, {HapFmt_A_RGTC1, 0}, {8, 0}, kBcRgtc1}; return true;
+    default: return false;
+    }
+}
+
+// ---- device pipelines (all asynchronous on `st`) -------------------------------------------------
+
+// textures of `frames` frames (device, described by G.s[i].in_offset/in_stride relative to `base`) ->
+// frames at out + f*out_stride, lengths in used[f]
+uint32_t launch_encode(const uint8_t *base, const FrameGeom &G, uint32_t frames, uint8_t *out, uint64_t out_stride,
+                       unsigned long long *used, cudaStream_t st)
+{
+    const uint64_t nfrag = (uint64_t)frames * G.frags_per_frame;
+    if (nfrag == 0 || nfrag >= (1ull << 31)) return HapResult_Bad_Arguments;
+    DevBuf scratch(st), fsize(st), fdst(st);
+    bool any_compress = false;
+    for (uint32_t i = 0; i < G.sections; i++) any_compress = any_compress || G.s[i].compress;
+    if (!scratch.alloc(any_compress ? nfrag * kFragCap : 16) || !fsize.alloc(nfrag * 4) || !fdst.alloc(nfrag * 4)) {
+        cudaGetLastError();
+        return HapResult_Internal_Error;
+    }
+    HAP_KLAUNCH(snappy_encode_fragments_kernel, dim3((unsigned)nfrag), dim3(kEncThreads), sizeof(EncodeSmem), st, base, G,
+                scratch.as<uint8_t>(), fsize.as<uint32_t>());
+    HAP_KLAUNCH(hap_plan_frames_kernel, dim3(frames), dim3(kPlanThreads), 0, st, G, base, fsize.as<uint32_t>(),
+                fdst.as<uint32_t>(), out, out_stride, used);
+    HAP_KLAUNCH(hap_place_fragments_kernel, dim3((unsigned)nfrag), dim3(kPlaceThreads), 0, st, G, base,
+                scratch.as<uint8_t>(), fsize.as<uint32_t>(), fdst.as<uint32_t>(), out, out_stride);
+    return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
+}
+
+uint32_t launch_block_encode(const uint8_t *rgba, uint32_t frames, uint64_t frame_stride, uint32_t width, uint32_t height,
+                             uint64_t row_bytes, const CodecInfo &ci, uint8_t *blocks, uint64_t blocks_stride,
+                             uint64_t second_offset, cudaStream_t st)
+{
+    BcGeom g;
+    g.blocks_x = width / 4;
+    g.blocks_y = height / 4;
+    g.row_bytes = (uint32_t)row_bytes;
+    g.pad = 0;
+    g.frame_bytes = frame_stride;
+    g.out_stride = blocks_stride;
+    g.second_offset = second_offset;
+    dim3 grid((g.blocks_x * g.blocks_y + kBcThreads - 1) / kBcThreads, frames);
+    switch (ci.bc_kind) {
+    case kBcDxt1: HAP_KLAUNCH(bc_encode_kernel<kBcDxt1>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
+    case kBcDxt5: HAP_KLAUNCH(bc_encode_kernel<kBcDxt5>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
+    case kBcYCoCg: HAP_KLAUNCH(bc_encode_kernel<kBcYCoCg>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
+    case kBcRgtc1: HAP_KLAUNCH(bc_encode_kernel<kBcRgtc1>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
+    default: HAP_KLAUNCH(bc_encode_kernel<kBcYCoCgPlusAlpha>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
+    }
+    return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
+}
+
+uint32_t launch_block_decode(const uint8_t *blocks, const uint8_t *alpha, uint32_t frames, uint64_t blocks_stride,
+                             uint64_t alpha_stride, uint32_t width, uint32_t height, const CodecInfo &ci, uint8_t *rgba,
+                             uint64_t frame_stride, uint64_t row_bytes, cudaStream_t st)
+{
+    BcDecodeGeom g;
+    g.blocks_x = width / 4;
+    g.blocks_y = height / 4;
+    g.row_bytes = (uint32_t)row_bytes;
+    g.merge_alpha = ci.textures == 2;
+    g.in_stride = blocks_stride;
+    g.alpha_stride = alpha_stride;
+    g.frame_bytes = frame_stride;
+    dim3 grid((g.blocks_x * g.blocks_y + kBcThreads - 1) / kBcThreads, frames);
+    switch (ci.bc_kind) {
+    case kBcDxt1: HAP_KLAUNCH(bc_decode_kernel<kBcDxt1>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
+    case kBcDxt5: HAP_KLAUNCH(bc_decode_kernel<kBcDxt5>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
+    case kBcRgtc1: HAP_KLAUNCH(bc_decode_kernel<kBcRgtc1>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
+    default: HAP_KLAUNCH(bc_decode_kernel<kBcYCoCg>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
+    }
+    return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
+}
+
+// device frames -> texture `index` of each; jobs scratch is allocated here
+uint32_t launch_decode_batch(const uint8_t *in, uint32_t frames, uint64_t in_stride, const unsigned long long *in_bytes,
+                             uint32_t index, uint32_t max_chunks, uint8_t *out, uint64_t out_stride,
+                             unsigned long long *used, uint32_t *formats, uint32_t *results, cudaStream_t st)
+{
+    const uint64_t njobs = (uint64_t)frames * max_chunks;
+    if (njobs == 0 || njobs >= (1ull << 31)) return HapResult_Bad_Arguments;
+    DevBuf jobs(st), whole(st);
+    if (!jobs.alloc(njobs * sizeof(ChunkJob)) || !whole.alloc((size_t)frames * 4)) { cudaGetLastError(); return HapResult_Internal_Error; }
+    HAP_KLAUNCH(hap_parse_frames_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, in, in_stride, in_bytes, frames, index,
+                max_chunks, out, out_stride, jobs.as<ChunkJob>(), used, formats, results, whole.as<uint32_t>());
+    HAP_KLAUNCH(snappy_decode_chunks_kernel, dim3((unsigned)njobs), dim3(kDecThreads), sizeof(DecodeSmem), st,
+                jobs.as<ChunkJob>(), (int)njobs);
+    HAP_KLAUNCH(hap_collect_status_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, jobs.as<ChunkJob>(), frames,
+                max_chunks, whole.as<uint32_t>(), results, used);
+    return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
+}
+
+// host-side view of a frame whose bytes may live on the device: fetches what header walks need
+struct HeaderView {
+    std::vector<uint8_t> copy;
+    const uint8_t *p = nullptr;
+    bool ok = true;
+    HeaderView(const void *frame, unsigned long bytes)
+    {
+        if (!is_device_pointer(frame)) { p = (const uint8_t *)frame; return; }
+        // headers + tables sit at the front of each section, but an inner section of a two-texture
+        // frame starts after the first texture's data: fetch the whole frame (queries on device
+        // frames are rare and not on the hot path; the batch decode parses on the device instead)
+        copy.resize(bytes ? bytes : 1);
+        ok = cudaMemcpy(copy.data(), frame, bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+        p = copy.data();
+    }
+};
+
+struct WorkState {
+    std::atomic<unsigned> claimed{0};
+};
+void work_function(void *p, unsigned int)
+{
+    // every chunk was submitted to the GPU before the callback ran (hap.h contract: the callee calls
+    // this once per chunk, from any threads, and returns when all calls returned)
+    reinterpret_cast<WorkState *>(p)->claimed.fetch_add(1, std::memory_order_relaxed);
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char *HapB200Version(void) { return "hap-b200 0.1 (sm_100a)"; }
+unsigned long long HapB200KernelLaunchCount(void) { return g_launches.load(); }
+
+// hap.c:324-353
+unsigned long HapMaxEncodedLength(unsigned int count, unsigned long *lengths, unsigned int *textureFormats,
+                                  unsigned int *chunkCounts)
+{
+    if (count == 0 || count > 2 || !lengths || !textureFormats || !chunkCounts) return 0;
+    unsigned long total = 8;
+    for (unsigned i = 0; i < count; i++) {
+        if (chunkCounts[i] == 0) return 0;
+        total += (unsigned long)max_encoded_length_one(lengths[i], textureFormats[i], HapCompressorSnappy, chunkCounts[i]);
+    }
+    return total;
+}
+
+// hap.c:1042-1087
+unsigned int HapGetFrameTextureCount(const void *inputBuffer, unsigned long inputBufferBytes, unsigned int *outputTextureCount)
+{
+    HeaderView hv(inputBuffer, inputBufferBytes);
+    if (!hv.ok) return HapResult_Internal_Error;
+    const uint8_t *in = hv.p;
+    Section top;
+    uint32_t r = read_section_header(in, (uint32_t)inputBufferBytes, top);
+    if (r != HapResult_No_Error) return r;
+    if (top.type != kSecMultipleImages) { *outputTextureCount = 1; return HapResult_No_Error; }
+    uint32_t off = top.hdr;
+    *outputTextureCount = 0;
+    while (off < top.len) {  // hap.c:1064 compares against the body length, as here
+        Section s;
+        r = read_section_header(in + off, (uint32_t)(inputBufferBytes - off), s);
+        if (r != HapResult_No_Error) return r;
+        off += s.hdr + s.len;
+        *outputTextureCount += 1;
+    }
+    return HapResult_No_Error;
+}
+
+// hap.c:1089-1126
+unsigned int HapGetFrameTextureFormat(const void *inputBuffer, unsigned long inputBufferBytes, unsigned int index,
+                                      unsigned int *outputBufferTextureFormat)
+{
+    if (!inputBuffer || index > 1 || !outputBufferTextureFormat) return HapResult_Bad_Arguments;
+    HeaderView hv(inputBuffer, inputBufferBytes);
+    if (!hv.ok) return HapResult_Internal_Error;
+    Located loc;
+    uint32_t r = locate_texture(hv.p, (uint32_t)inputBufferBytes, index, loc);
+    if (r != HapResult_No_Error) return r;
+    *outputBufferTextureFormat = format_from_nibble(loc.type & 0xF);
+    return *outputBufferTextureFormat ? HapResult_No_Error : HapResult_Bad_Frame;
+}
+
+// hap.c:1128-1188
+unsigned int HapGetFrameTextureChunkCount(const void *inputBuffer, unsigned long inputBufferBytes, unsigned int index,
+                                          int *chunk_count)
+{
+    *chunk_count = 0;  // before validation, like hap.c:1134
+    if (!inputBuffer || index > 1) return HapResult_Bad_Arguments;
+    HeaderView hv(inputBuffer, inputBufferBytes);
+    if (!hv.ok) return HapResult_Internal_Error;
+    Located loc;
+    uint32_t r = locate_texture(hv.p, (uint32_t)inputBufferBytes, index, loc);
+    if (r != HapResult_No_Error) return r;
+    const uint32_t compressor = (loc.type >> 4) & 0xF;
+    if (compressor == kHapComplex) {
+        ChunkTables t;
+        t.count = 0;
+        r = parse_decode_instructions(hv.p + loc.offset, loc.len, t);
+        *chunk_count = t.count;
+        return r;
+    }
+    if (compressor == kHapChunkSnappy || compressor == kHapChunkRaw) { *chunk_count = 1; return HapResult_No_Error; }
+    return HapResult_Bad_Frame;
+}
+
+// hap.c:506-604 + :355-504
+unsigned int HapEncode(unsigned int count, const void **inputBuffers, unsigned long *inputBuffersBytes,
+                       unsigned int *textureFormats, unsigned int *compressors, unsigned int *chunkCounts,
+                       void *outputBuffer, unsigned long outputBufferBytes, unsigned long *outputBufferBytesUsed)
+{
+    if (count == 0 || count > 2 || !inputBuffers || !inputBuffersBytes || !textureFormats || !compressors || !chunkCounts ||
+        !outputBuffer || outputBufferBytes == 0 || !outputBufferBytesUsed)
+        return HapResult_Bad_Arguments;
+    for (unsigned i = 0; i < count; i++)
+        if (chunkCounts[i] == 0) return HapResult_Bad_Arguments;
+    if (count == 2 && textureFormats[0] != HapFmt_YCoCg_DXT5 && textureFormats[1] != HapFmt_YCoCg_DXT5 &&
+        textureFormats[0] != HapFmt_A_RGTC1 && textureFormats[1] != HapFmt_A_RGTC1)
+        return HapResult_Bad_Arguments;  // hap.c:551-559
+
+    TextureArgs ta[2];
+    for (unsigned i = 0; i < count; i++) ta[i] = TextureArgs{inputBuffersBytes[i], textureFormats[i], compressors[i], chunkCounts[i]};
+    // hap.c:563-576: outer header from the worst case, with the REQUESTED chunk counts
+    uint64_t outer = 0;
+    if (count == 2) {
+        uint64_t worst = 0;
+        for (unsigned i = 0; i < 2; i++) worst += ta[i].bytes + decode_instructions_length(ta[i].chunks) + 4;
+        outer = worst > kU24Max ? 8 : 4;
+    }
+    // Errors surface in texture order: the reference encodes texture 0 completely before it looks at
+    // texture 1 (hap.c:580-596).  The capacity test of texture 1 is made against what section 0 really
+    // used (hap.c:589), which is only known after compression: checked further down.
+    if (!inputBuffers[0] || validate_texture_args(ta[0]) != HapResult_No_Error) return HapResult_Bad_Arguments;
+    if (outputBufferBytes < outer ||
+        outputBufferBytes - outer < max_encoded_length_one(ta[0].bytes, ta[0].format, ta[0].compressor, ta[0].chunks))
+        return HapResult_Buffer_Too_Small;
+    if (count == 2 && (!inputBuffers[1] || validate_texture_args(ta[1]) != HapResult_No_Error)) return HapResult_Bad_Arguments;
+    FrameGeom G;
+    {
+        uint32_t gr = build_frame_geom(count, ta, G);
+        if (gr != HapResult_No_Error) return gr;
+    }
+
+    bool all_host_verbatim = !is_device_pointer(outputBuffer);
+    for (unsigned i = 0; i < count; i++)
+        all_host_verbatim = all_host_verbatim && ta[i].compressor == HapCompressorNone && !is_device_pointer(inputBuffers[i]);
+    if (all_host_verbatim) {
+        // hap.c:490-501 for every texture: headers plus a copy, nothing to compute and nothing for a GPU to do
+        uint8_t *o = (uint8_t *)outputBuffer;
+        uint64_t pos = outer;
+        for (unsigned i = 0; i < count; i++) {
+            const uint32_t hdr = G.s[i].top_hdr;
+            if (i == 1 && (outputBufferBytes < pos ||
+                           outputBufferBytes - pos < max_encoded_length_one(ta[1].bytes, ta[1].format, ta[1].compressor, ta[1].chunks)))
+                return HapResult_Buffer_Too_Small;
+            uint8_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const uint32_t len = (uint32_t)ta[i].bytes;
+            if (hdr == 4) { h[0] = (uint8_t)len; h[1] = (uint8_t)(len >> 8); h[2] = (uint8_t)(len >> 16); }
+            else { h[4] = (uint8_t)len; h[5] = (uint8_t)(len >> 8); h[6] = (uint8_t)(len >> 16); h[7] = (uint8_t)(len >> 24); }
+            h[3] = (uint8_t)((kHapChunkRaw << 4) | G.s[i].fmt_nibble);
+            memcpy(o + pos, h, hdr);
+            memcpy(o + pos + hdr, inputBuffers[i], ta[i].bytes);
+            pos += hdr + ta[i].bytes;
+        }
+        if (count == 2) {
+            const uint32_t len = (uint32_t)(pos - outer);
+            uint8_t h[8] = {0, 0, 0, (uint8_t)kSecMultipleImages, 0, 0, 0, 0};
+            if (outer == 4) { h[0] = (uint8_t)len; h[1] = (uint8_t)(len >> 8); h[2] = (uint8_t)(len >> 16); }
+            else { h[4] = (uint8_t)len; h[5] = (uint8_t)(len >> 8); h[6] = (uint8_t)(len >> 16); h[7] = (uint8_t)(len >> 24); }
+            memcpy(o, h, outer);
+        }
+        *outputBufferBytesUsed = (unsigned long)pos;
+        return HapResult_No_Error;
+    }
+
+    if (!runtime_ok()) return HapResult_Internal_Error;
+    std::lock_guard<std::mutex> lock(g_rt.mu);
+    cudaStream_t st = g_rt.stream;
+
+    // worst-case frame in device scratch; textures staged into 16-byte aligned device memory
+    unsigned long lens[2] = {ta[0].bytes, count == 2 ? ta[1].bytes : 0};
+    unsigned fmts[2] = {ta[0].format, ta[1].format}, chunks[2] = {ta[0].chunks, ta[1].chunks};
+    const unsigned long cap = HapMaxEncodedLength(count, lens, fmts, chunks);
+    DevBuf tex(st), frame(st), used(st);
+    const uint64_t off1 = align16(ta[0].bytes);
+    const uint64_t tex_bytes = off1 + (count == 2 ? align16(ta[1].bytes) : 0) + 16;
+    if (!tex.alloc(tex_bytes) || !frame.alloc(cap) || !used.alloc(sizeof(unsigned long long) * 4)) { cudaGetLastError(); return HapResult_Internal_Error; }
+    for (unsigned i = 0; i < count; i++) {
+        uint8_t *d = tex.as<uint8_t>() + (i ? off1 : 0);
+        cudaMemcpyKind kind = is_device_pointer(inputBuffers[i]) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if (cudaMemcpyAsync(d, inputBuffers[i], ta[i].bytes, kind, st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+        G.s[i].in_offset = i ? off1 : 0;
+        G.s[i].in_stride = 0;
+    }
+    uint32_t r = launch_encode(tex.as<uint8_t>(), G, 1, frame.as<uint8_t>(), cap, used.as<unsigned long long>(), st);
+    if (r != HapResult_No_Error) return r;
+    unsigned long long total = 0;
+    if (cudaMemcpyAsync(&total, used.p, sizeof total, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+    if (total > outputBufferBytes) return HapResult_Buffer_Too_Small;
+    if (count == 2) {
+        // hap.c:589: capacity left for texture 1 = outputBufferBytes - (outer header + actual section 0)
+        Section s0;
+        uint8_t head[16];
+        if (cudaMemcpy(head, frame.as<uint8_t>() + outer, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+        if (read_section_header(head, 0xFFFFFFFFu, s0) == HapResult_No_Error) {
+            uint64_t before = outer + s0.hdr + s0.len;
+            if (outputBufferBytes < before ||
+                outputBufferBytes - before < max_encoded_length_one(ta[1].bytes, ta[1].format, ta[1].compressor, ta[1].chunks))
+                return HapResult_Buffer_Too_Small;
+        }
+    }
+    cudaMemcpyKind okind = is_device_pointer(outputBuffer) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (cudaMemcpyAsync(outputBuffer, frame.p, total, okind, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        cudaGetLastError();
+        return HapResult_Internal_Error;
+    }
+    *outputBufferBytesUsed = (unsigned long)total;
+    return HapResult_No_Error;
+}
+
+// hap.c:993-1040 + :732-930
+unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, unsigned int index,
+                       HapDecodeCallback callback, void *info, void *outputBuffer, unsigned long outputBufferBytes,
+                       unsigned long *outputBufferBytesUsed, unsigned int *outputBufferTextureFormat)
+{
+    if (!inputBuffer || index > 1 || !callback || !outputBuffer || !outputBufferTextureFormat) return HapResult_Bad_Arguments;
+    const bool in_dev = is_device_pointer(inputBuffer), out_dev = is_device_pointer(outputBuffer);
+    HeaderView hv(inputBuffer, inputBufferBytes);
+    if (!hv.ok) return HapResult_Internal_Error;
+    const uint8_t *frame = hv.p;
+    Located loc;
+    uint32_t r = locate_texture(frame, (uint32_t)inputBufferBytes, index, loc);
+    if (r != HapResult_No_Error) return r;
+    const uint8_t *sec = frame + loc.offset;
+    const uint32_t compressor = (loc.type >> 4) & 0xF;
+    *outputBufferTextureFormat = format_from_nibble(loc.type & 0xF);
+    if (*outputBufferTextureFormat == 0) return HapResult_Bad_Frame;
+
+    struct HostJob { uint32_t src_off, src_bytes, dst_off, dst_bytes, compressor; };
+    std::vector<HostJob> hj;
+    uint64_t produced = 0;
+    bool whole = false;
+    if (compressor == kHapComplex) {
+        ChunkTables t;
+        t.count = 0;
+        r = parse_decode_instructions(sec, loc.len, t);
+        if (r != HapResult_No_Error) return r;
+        if (t.count > 0) {
+            uint64_t in_run = 0, out_run = 0;
+            hj.resize((size_t)t.count);
+            for (int i = 0; i < t.count; i++) {
+                const uint32_t cc = sec[t.compressors + i];
+                const uint32_t sz = rd_le32(sec + t.sizes + 4 * i);
+                const uint64_t start = t.data + (t.offsets != 0xFFFFFFFFu ? (uint64_t)rd_le32(sec + t.offsets + 4 * i) : in_run);
+                in_run += sz;
+                if (start + sz > loc.len) return HapResult_Bad_Frame;  // the reference reads out of bounds here
+                uint32_t usz = sz;
+                if (cc == kHapChunkSnappy && !snappy_preamble(sec + start, sz, usz)) return HapResult_Bad_Frame;  // hap.c:817-829
+                hj[i] = HostJob{(uint32_t)start, sz, 0, usz, (cc == kHapChunkSnappy || cc == kHapChunkRaw) ? cc : 0xFFu};
+                if (out_run > 0xFFFFFFFFull) return HapResult_Buffer_Too_Small;
+                hj[i].dst_off = (uint32_t)out_run;
+                out_run += usz;
+            }
+            if (out_run > outputBufferBytes) return HapResult_Buffer_Too_Small;  // hap.c:840-843
+            produced = out_run;
+        }
+    } else if (compressor == kHapChunkSnappy) {
+        uint32_t usz = 0;
+        if (!snappy_preamble(sec, loc.len, usz)) return HapResult_Internal_Error;  // hap.c:890-894
+        if (usz > outputBufferBytes) return HapResult_Buffer_Too_Small;
+        hj.push_back(HostJob{0, loc.len, 0, usz, kHapChunkSnappy});
+        produced = usz;
+        whole = true;
+    } else if (compressor == kHapChunkRaw) {
+        if (loc.len > outputBufferBytes) return HapResult_Buffer_Too_Small;
+        // hap.c:905-916: a verbatim texture is a copy; nothing to compute
+        if (!in_dev && !out_dev) {
+            memcpy(outputBuffer, sec, loc.len);
+        } else {
+            if (!runtime_ok()) return HapResult_Internal_Error;
+            const uint8_t *src = in_dev ? (const uint8_t *)inputBuffer + loc.offset : sec;
+            if (cudaMemcpy(outputBuffer, src, loc.len, cudaMemcpyDefault) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+        }
+        if (outputBufferBytesUsed) *outputBufferBytesUsed = loc.len;
+        return HapResult_No_Error;
+    } else {
+        return HapResult_Bad_Frame;
+    }
+
+    if (!hj.empty()) {
+        if (!runtime_ok()) return HapResult_Internal_Error;
+        std::lock_guard<std::mutex> lock(g_rt.mu);
+        cudaStream_t st = g_rt.stream;
+        DevBuf din(st), dout(st), djobs(st);
+        const uint8_t *dsec;
+        if (in_dev) {
+            dsec = (const uint8_t *)inputBuffer + loc.offset;
+        } else {
+            if (!din.alloc(loc.len) || cudaMemcpyAsync(din.p, sec, loc.len, cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+            dsec = din.as<uint8_t>();
+        }
+        uint8_t *ddst;
+        if (out_dev) ddst = (uint8_t *)outputBuffer;
+        else {
+            if (!dout.alloc(produced)) { cudaGetLastError(); return HapResult_Internal_Error; }
+            ddst = dout.as<uint8_t>();
+        }
+        std::vector<ChunkJob> jobs(hj.size());
+        for (size_t i = 0; i < hj.size(); i++) {
+            jobs[i].src = dsec + hj[i].src_off;
+            jobs[i].dst = ddst + hj[i].dst_off;
+            jobs[i].src_bytes = hj[i].src_bytes;
+            jobs[i].dst_bytes = hj[i].dst_bytes;
+            jobs[i].compressor = hj[i].compressor;
+            jobs[i].status = HapResult_Internal_Error;
+        }
+        if (!djobs.alloc(jobs.size() * sizeof(ChunkJob)) ||
+            cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(ChunkJob), cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+        HAP_KLAUNCH(snappy_decode_chunks_kernel, dim3((unsigned)jobs.size()), dim3(kDecThreads), sizeof(DecodeSmem), st,
+                    djobs.as<ChunkJob>(), (int)jobs.size());
+        if (compressor == kHapComplex && jobs.size() > 1) {
+            WorkState ws;
+            callback(work_function, &ws, (unsigned)jobs.size(), info);  // hap.c:861
+        }
+        if (cudaMemcpyAsync(jobs.data(), djobs.p, jobs.size() * sizeof(ChunkJob), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+        for (size_t i = 0; i < jobs.size(); i++)
+            if (jobs[i].status != HapResult_No_Error) return whole ? (uint32_t)HapResult_Internal_Error : jobs[i].status;  // hap.c:867-875, :899-903
+        if (!out_dev && produced) {
+            if (cudaMemcpyAsync(outputBuffer, ddst, produced, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+        }
+    }
+    if (outputBufferBytesUsed) *outputBufferBytesUsed = (unsigned long)produced;
+    return HapResult_No_Error;
+}
+
+// ---- extensions ----------------------------------------------------------------------------------
+
+unsigned long HapB200TextureBytes(unsigned int width, unsigned int height, unsigned int codec, unsigned int index)
+{
+    CodecInfo ci;
+    if (!codec_info(codec, ci) || index >= ci.textures || width % 4 || height % 4) return 0;
+    return (unsigned long)(width / 4) * (height / 4) * ci.block_bytes[index];
+}
+
+unsigned long HapB200MaxEncodedLengthRGBA(unsigned int width, unsigned int height, unsigned int codec, unsigned int chunkCount)
+{
+    CodecInfo ci;
+    if (!codec_info(codec, ci)) return 0;
+    unsigned long lens[2] = {HapB200TextureBytes(width, height, codec, 0), HapB200TextureBytes(width, height, codec, 1)};
+    unsigned fmts[2] = {ci.fmt[0], ci.fmt[1]}, chunks[2] = {chunkCount, chunkCount};
+    if (lens[0] == 0) return 0;
+    return HapMaxEncodedLength(ci.textures, lens, fmts, chunks);
+}
+
+unsigned int HapB200BlockEncodeBatch(const void *rgba, unsigned int frames, unsigned long frameStride, unsigned int width,
+                                     unsigned int height, unsigned long rowBytes, unsigned int codec, void *blocks,
+                                     unsigned long blocksStride, void *stream)
+{
+    CodecInfo ci;
+    if (!rgba || !blocks || frames == 0 || !codec_info(codec, ci) || width == 0 || height == 0 || width % 4 || height % 4 ||
+        rowBytes < 4ul * width || rowBytes % 16 || ((uintptr_t)rgba | (uintptr_t)blocks | frameStride | blocksStride) % 16)
+        return HapResult_Bad_Arguments;
+    if (!runtime_ok()) return HapResult_Internal_Error;
+    cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
+    uint32_t r = launch_block_encode((const uint8_t *)rgba, frames, frameStride, width, height, rowBytes, ci, (uint8_t *)blocks,
+                                     blocksStride, HapB200TextureBytes(width, height, codec, 0), st);
+    if (r == HapResult_No_Error && !stream && cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); r = HapResult_Internal_Error; }
+    return r;
+}
+
+unsigned int HapB200BlockDecodeBatch(const void *blocks, unsigned int frames, unsigned long blocksStride, unsigned int width,
+                                     unsigned int height, unsigned int codec, void *rgba, unsigned long frameStride,
+                                     unsigned long rowBytes, void *stream)
+{
+    CodecInfo ci;
+    if (!rgba || !blocks || frames == 0 || !codec_info(codec, ci) || width == 0 || height == 0 || width % 4 || height % 4 ||
+        rowBytes < 4ul * width || rowBytes % 16 || ((uintptr_t)rgba | (uintptr_t)blocks | frameStride | blocksStride) % 16)
+        return HapResult_Bad_Arguments;
+    if (!runtime_ok()) return HapResult_Internal_Error;
+    cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
+    const uint8_t *b = (const uint8_t *)blocks;
+    uint32_t r = launch_block_decode(b, b + HapB200TextureBytes(width, height, codec, 0), frames, blocksStride, blocksStride, width,
+                                     height, ci, (uint8_t *)rgba, frameStride, rowBytes, st);
+    if (r == HapResult_No_Error && !stream && cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); r = HapResult_Internal_Error; }
+    return r;
+}
+
+unsigned int HapB200EncodeBatch(unsigned int count, const void **textures, unsigned long *textureStrides,
+                                unsigned long *textureBytes, unsigned int *textureFormats, unsigned int *compressors,
+                                unsigned int *chunkCounts, unsigned int frames, void *out, unsigned long outStride,
+                                unsigned long long *used, void *stream)
+{
+    if (count == 0 || count > 2 || !textures || !textureStrides || !textureBytes || !textureFormats || !compressors ||
+        !chunkCounts || frames == 0 || !out || !used)
+        return HapResult_Bad_Arguments;
+    TextureArgs ta[2];
+    for (unsigned i = 0; i < count; i++) {
+        if (chunkCounts[i] == 0 || !textures[i] || ((uintptr_t)textures[i] | textureStrides[i]) % 16) return HapResult_Bad_Arguments;
+        ta[i] = TextureArgs{textureBytes[i], textureFormats[i], compressors[i], chunkCounts[i]};
+        if (validate_texture_args(ta[i]) != HapResult_No_Error) return HapResult_Bad_Arguments;
+    }
+    if (count == 2 && textureFormats[0] != HapFmt_YCoCg_DXT5 && textureFormats[1] != HapFmt_YCoCg_DXT5 &&
+        textureFormats[0] != HapFmt_A_RGTC1 && textureFormats[1] != HapFmt_A_RGTC1)
+        return HapResult_Bad_Arguments;
+    if (outStride < HapMaxEncodedLength(count, textureBytes, textureFormats, chunkCounts)) return HapResult_Buffer_Too_Small;
+    FrameGeom G;
+    uint32_t r = build_frame_geom(count, ta, G);
+    if (r != HapResult_No_Error) return r;
+    if (!runtime_ok()) return HapResult_Internal_Error;
+    cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
+    const uint8_t *base = (const uint8_t *)textures[0];
+    for (unsigned i = 0; i < count; i++) {
+        G.s[i].in_offset = (uint64_t)((const uint8_t *)textures[i] - base);  // wraps for i = 1 when below base; 64-bit add undoes it
+        G.s[i].in_stride = textureStrides[i];
+    }
+    r = launch_encode(base, G, frames, (uint8_t *)out, outStride, used, st);
+    if (r == HapResult_No_Error && !stream && cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); r = HapResult_Internal_Error; }
+    return r;
+}
+
+unsigned int HapB200EncodeRGBABatch(const void *rgba, unsigned int frames, unsigned long frameStride, unsigned int width,
+                                    unsigned int height, unsigned long rowBytes, unsigned int codec, unsigned int compressor,
+                                    unsigned int chunkCount, void *out, unsigned long outStride, unsigned long long *used,
+                                    void *stream)
+{
+    CodecInfo ci;
+    if (!rgba || !out || !used || frames == 0 || chunkCount == 0 || !codec_info(codec, ci) || width == 0 || height == 0 ||
+        width % 4 || height % 4 || rowBytes < 4ul * width || rowBytes % 16 || ((uintptr_t)rgba | frameStride) % 16 ||
+        (compressor != HapCompressorNone && compressor != HapCompressorSnappy))
+        return HapResult_Bad_Arguments;
+    if (outStride < HapB200MaxEncodedLengthRGBA(width, height, codec, chunkCount)) return HapResult_Buffer_Too_Small;
+    if (!runtime_ok()) return HapResult_Internal_Error;
+    cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
+    const uint64_t t0 = HapB200TextureBytes(width, height, codec, 0), t1 = HapB200TextureBytes(width, height, codec, 1);
+    const uint64_t dxt_stride = align16(t0) + align16(t1);
+    DevBuf dxt(st);
+    if (!dxt.alloc(dxt_stride * frames + 16)) { cudaGetLastError(); return HapResult_Internal_Error; }
+    uint32_t r = launch_block_encode((const uint8_t *)rgba, frames, frameStride, width, height, rowBytes, ci, dxt.as<uint8_t>(),
+                                     dxt_stride, align16(t0), st);
+    if (r != HapResult_No_Error) return r;
+    TextureArgs ta[2] = {{t0, ci.fmt[0], compressor, chunkCount}, {t1, ci.fmt[1], compressor, chunkCount}};
+    FrameGeom G;
+    r = build_frame_geom(ci.textures, ta, G);
+    if (r != HapResult_No_Error) return r;
+    for (unsigned i = 0; i < ci.textures; i++) {
+        G.s[i].in_offset = i ? align16(t0) : 0;
+        G.s[i].in_stride = dxt_stride;
+    }
+    r = launch_encode(dxt.as<uint8_t>(), G, frames, (uint8_t *)out, outStride, used, st);
+    if (r == HapResult_No_Error && !stream && cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); r = HapResult_Internal_Error; }
+    return r;
+}
+
+unsigned int HapB200EncodeRGBA(const void *rgba, unsigned int width, unsigned int height, unsigned long rowBytes,
+                               unsigned int codec, unsigned int compressor, unsigned int chunkCount, void *outputBuffer,
+                               unsigned long outputBufferBytes, unsigned long *outputBufferBytesUsed)
+{
+    CodecInfo ci;
+    if (!rgba || !outputBuffer || !outputBufferBytesUsed || chunkCount == 0 || !codec_info(codec, ci) || width == 0 ||
+        height == 0 || width % 4 || height % 4 || rowBytes < 4ul * width ||
+        (compressor != HapCompressorNone && compressor != HapCompressorSnappy))
+        return HapResult_Bad_Arguments;
+    const unsigned long cap = HapB200MaxEncodedLengthRGBA(width, height, codec, chunkCount);
+    if (outputBufferBytes < cap) return HapResult_Buffer_Too_Small;
+    if (!runtime_ok()) return HapResult_Internal_Error;
+    std::lock_guard<std::mutex> lock(g_rt.mu);
+    cudaStream_t st = g_rt.stream;
+    DevBuf img(st), frame(st), used(st);
+    const uint64_t tight = 4ull * width;
+    if (!img.alloc(tight * height) || !frame.alloc(cap) || !used.alloc(32)) { cudaGetLastError(); return HapResult_Internal_Error; }
+    if (cudaMemcpy2DAsync(img.p, tight, rgba, rowBytes, tight, height, cudaMemcpyDefault, st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+    uint32_t r = HapB200EncodeRGBABatch(img.p, 1, align16(tight * height), width, height, tight, codec, compressor, chunkCount,
+                                        frame.p, cap, used.as<unsigned long long>(), st);
+    if (r != HapResult_No_Error) return r;
+    unsigned long long total = 0;
+    if (cudaMemcpyAsync(&total, used.p, sizeof total, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess ||
+        total > outputBufferBytes || cudaMemcpyAsync(outputBuffer, frame.p, total, cudaMemcpyDefault, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+    *outputBufferBytesUsed = (unsigned long)total;
+    return HapResult_No_Error;
+}
+
+unsigned int HapB200DecodeBatch(const void *in, unsigned int frames, unsigned long inStride, const unsigned long long *inBytes,
+                                unsigned int index, unsigned int maxChunks, void *out, unsigned long outStride,
+                                unsigned long long *used, unsigned int *formats, unsigned int *results, void *stream)
+{
+    if (!in || !inBytes || !out || !used || !formats || !results || frames == 0 || maxChunks == 0 || index > 1)
+        return HapResult_Bad_Arguments;
+    if (!runtime_ok()) return HapResult_Internal_Error;
+    cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
+    uint32_t r = launch_decode_batch((const uint8_t *)in, frames, inStride, inBytes, index, maxChunks, (uint8_t *)out, outStride, used,
+                                     formats, results, st);
+    if (r == HapResult_No_Error && !stream && cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); r = HapResult_Internal_Error; }
+    return r;
+}
+
+unsigned int HapB200DecodeRGBABatch(const void *in, unsigned int frames, unsigned long inStride, const unsigned long long *inBytes,
+                                    unsigned int maxChunks, unsigned int codec, unsigned int width, unsigned int height, void *rgba,
+                                    unsigned long frameStride, unsigned long rowBytes, unsigned int *results, void *stream)
+{
+    CodecInfo ci;
+    if (!in || !inBytes || !rgba || !results || frames == 0 || maxChunks == 0 || !codec_info(codec, ci) || width == 0 ||
+        height == 0 || width % 4 || height % 4 || rowBytes < 4ul * width || rowBytes % 16 || ((uintptr_t)rgba | frameStride) % 16)
+        return HapResult_Bad_Arguments;
+    if (!runtime_ok()) return HapResult_Internal_Error;
+    cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
+    const uint64_t t0 = HapB200TextureBytes(width, height, codec, 0), t1 = HapB200TextureBytes(width, height, codec, 1);
+    const uint64_t dxt_stride = align16(t0) + align16(t1);
+    DevBuf dxt(st), used(st), formats(st), res1(st);
+    if (!dxt.alloc(dxt_stride * frames + 16) || !used.alloc(8ull * frames) || !formats.alloc(4ull * frames) || !res1.alloc(4ull * frames)) {
+        cudaGetLastError();
+        return HapResult_Internal_Error;
+    }
+    uint32_t r = HapResult_No_Error;
+    for (uint32_t ti = 0; ti < ci.textures && r == HapResult_No_Error; ti++) {
+        uint32_t *res = ti == 0 ? results : res1.as<uint32_t>();
+        // the decoded size must equal the texture size: offer exactly that much room per frame
+        r = launch_decode_batch((const uint8_t *)in, frames, inStride, inBytes, ti, maxChunks, dxt.as<uint8_t>() + (ti ? align16(t0) : 0),
+                                dxt_stride, used.as<unsigned long long>(), formats.as<uint32_t>(), res, st);
+        if (r != HapResult_No_Error) break;
+        HAP_KLAUNCH(hap_check_texture_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, frames, used.as<unsigned long long>(),
+                    formats.as<uint32_t>(), res, (unsigned long long)(ti ? t1 : t0), ci.fmt[ti], results);
+    }
+    if (r == HapResult_No_Error)
+        r = launch_block_decode(dxt.as<uint8_t>(), dxt.as<uint8_t>() + align16(t0), frames, dxt_stride, dxt_stride, width, height, ci,
+                                (uint8_t *)rgba, frameStride, rowBytes, st);
+    if (r == HapResult_No_Error && !stream && cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); r = HapResult_Internal_Error; }
+    return r;
+}
+
+unsigned int HapB200DecodeRGBA(const void *inputBuffer, unsigned long inputBufferBytes, unsigned int width, unsigned int height,
+                               void *rgba, unsigned long rowBytes)
+{
+    if (!inputBuffer || !rgba || width == 0 || height == 0 || width % 4 || height % 4 || rowBytes < 4ul * width)
+        return HapResult_Bad_Arguments;
+    unsigned count = 0, f0 = 0, f1 = 0;
+    uint32_t r = HapGetFrameTextureCount(inputBuffer, inputBufferBytes, &count);
+    if (r != HapResult_No_Error) return r;
+    r = HapGetFrameTextureFormat(inputBuffer, inputBufferBytes, 0, &f0);
+    if (r != HapResult_No_Error) return r;
+    unsigned codec;
+    if (count == 2) {
+        r = HapGetFrameTextureFormat(inputBuffer, inputBufferBytes, 1, &f1);
+        if (r != HapResult_No_Error) return r;
+        if (f0 != HapFmt_YCoCg_DXT5 || f1 != HapFmt_A_RGTC1) return HapResult_Bad_Frame;
+        codec = HapB200Codec_HapM;
+    } else if (count == 1) {
+        codec = f0 == HapFmt_RGB_DXT1 ? HapB200Codec_Hap1 : f0 == HapFmt_RGBA_DXT5 ? HapB200Codec_Hap5 :
+                f0 == HapFmt_YCoCg_DXT5 ? HapB200Codec_HapY : f0 == HapFmt_A_RGTC1 ? HapB200Codec_HapA : 99u;
+    } else {
+        return HapResult_Bad_Frame;
+    }
+    CodecInfo ci;
+    if (!codec_info(codec, ci)) return HapResult_Bad_Frame;  // BPTC frames carry no RGBA decoder here
+    if (!runtime_ok()) return HapResult_Internal_Error;
+    const uint64_t t0 = HapB200TextureBytes(width, height, codec, 0), t1 = HapB200TextureBytes(width, height, codec, 1);
+    void *dxt = nullptr, *img = nullptr;
+    const uint64_t tight = 4ull * width;
+    if (cudaMalloc(&dxt, align16(t0) + align16(t1) + 16) != cudaSuccess || cudaMalloc(&img, tight * height) != cudaSuccess) {
+        cudaGetLastError();
+        if (dxt) cudaFree(dxt);
+        return HapResult_Internal_Error;
+    }
+    auto serial = [](HapDecodeWorkFunction fn, void *p, unsigned n, void *) { for (unsigned i = 0; i < n; i++) fn(p, i); };
+    unsigned long used = 0;
+    unsigned fmt = 0;
+    r = HapDecode(inputBuffer, inputBufferBytes, 0, serial, nullptr, dxt, t0, &used, &fmt);
+    if (r == HapResult_No_Error && used != t0) r = HapResult_Bad_Frame;
+    if (r == HapResult_No_Error && count == 2) {
+        r = HapDecode(inputBuffer, inputBufferBytes, 1, serial, nullptr, (uint8_t *)dxt + align16(t0), t1, &used, &fmt);
+        if (r == HapResult_No_Error && used != t1) r = HapResult_Bad_Frame;
+    }
+    if (r == HapResult_No_Error) {
+        std::lock_guard<std::mutex> lock(g_rt.mu);
+        cudaStream_t st = g_rt.stream;
+        r = launch_block_decode((const uint8_t *)dxt, (const uint8_t *)dxt + align16(t0), 1, 0, 0, width, height, ci, (uint8_t *)img,
+                                0, tight, st);
+        if (r == HapResult_No_Error &&
+            (cudaMemcpy2DAsync(rgba, rowBytes, img, tight, tight, height, cudaMemcpyDefault, st) != cudaSuccess ||
+             cudaStreamSynchronize(st) != cudaSuccess)) { cudaGetLastError(); r = HapResult_Internal_Error; }
+    }
+    cudaFree(dxt);
+    cudaFree(img);
+    return r;
+}
+
+}  // extern "C"

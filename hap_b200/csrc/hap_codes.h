@@ -3,18 +3,14 @@
 #pragma once
 #include <stdint.h>
 
+#include "../../include/hap.h"
+
 namespace hapb200 {
 
-// HapResult (hap.h:55-61)
-enum : uint32_t {
-    HapResult_No_Error = 0,
-    HapResult_Bad_Arguments = 1,
-    HapResult_Buffer_Too_Small = 2,
-    HapResult_Bad_Frame = 3,
-    HapResult_Internal_Error = 4,
-};
+// HapResult (hap.h:55-61), HapCompressor (hap.h:50-53) and the HapTextureFormat enumerators come from
+// include/hap.h itself (plain C enums, usable in device code as compile-time constants).
 
-// HapTextureFormat (hap.h:40-48)
+// HapTextureFormat (hap.h:40-48) under short names
 enum : uint32_t {
     HapFmt_RGB_DXT1 = 0x83F0,
     HapFmt_RGBA_DXT5 = 0x83F3,
@@ -24,9 +20,6 @@ enum : uint32_t {
     HapFmt_RGB_BPTC_UFLOAT = 0x8E8F,
     HapFmt_RGB_BPTC_SFLOAT = 0x8E8E,
 };
-
-// HapCompressor (hap.h:50-53)
-enum : uint32_t { HapCompressorNone = 0, HapCompressorSnappy = 1 };
 
 // stored compressor nibbles / chunk compressor bytes (hap.c:41-43)
 enum : uint32_t { kHapChunkRaw = 0xA, kHapChunkSnappy = 0xB, kHapComplex = 0xC };

@@ -120,4 +120,18 @@ __global__ void hap_collect_status_kernel(const ChunkJob *__restrict__ jobs, uin
     }
 }
 
+// RGBA decode path: a texture must have the format and size the caller's codec implies; the first
+// failing texture of a frame decides that frame's result (merged into `merged`, which may alias `res`).
+__global__ void hap_check_texture_kernel(uint32_t frames, const unsigned long long *__restrict__ used,
+                                         const uint32_t *__restrict__ formats, const uint32_t *res,
+                                         unsigned long long want_bytes, uint32_t want_format, uint32_t *merged)
+{
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= frames) return;
+    uint32_t r = res[f];
+    if (r == HapResult_No_Error && (formats[f] != want_format || used[f] != want_bytes)) r = HapResult_Bad_Frame;
+    if (res == merged) merged[f] = r;
+    else if (merged[f] == HapResult_No_Error) merged[f] = r;
+}
+
 }  // namespace hapb200

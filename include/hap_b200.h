@@ -69,10 +69,11 @@ unsigned int HapB200DecodeBatch(const void *in, unsigned int frames, unsigned lo
                                 void *out, unsigned long outStride, unsigned long long *used,
                                 unsigned int *formats, unsigned int *results, void *stream);
 
-/* Decode straight to RGBA8: HapDecode of every texture + block decode (+ YCoCg, + alpha merge). */
+/* Decode straight to RGBA8: HapDecode of every texture + block decode (+ YCoCg, + alpha merge).
+ * codec = the HapB200Codec of the stream (its FourCC); frames of another flavour report Bad_Frame. */
 unsigned int HapB200DecodeRGBABatch(const void *in, unsigned int frames, unsigned long inStride,
                                     const unsigned long long *inBytes, unsigned int maxChunks,
-                                    unsigned int width, unsigned int height, void *rgba,
+                                    unsigned int codec, unsigned int width, unsigned int height, void *rgba,
                                     unsigned long frameStride, unsigned long rowBytes, unsigned int *results,
                                     void *stream);
 
