@@ -1,0 +1,367 @@
+#!/usr/bin/env python3
+"""bench.py -- 4K Hap Q encode+decode throughput of libhap_b200.so (contract: see the task brief).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json `metric` "4K Hap-Q encode/decode GB/s per GPU", configs[2]): 3840x2160 RGBA8
+synthetic video frames -> Hap Q (scaled-YCoCg-DXT5, Snappy, 8 chunks) -> decoded back to the DXT
+texture bytes (what HapDecode returns).  One STEP = one pass of that round trip over a batch of
+`--frames` device-resident frames per GPU (default 32 = 1.06 GB of RGBA, far larger than the 126 MB
+L2, so nothing is served from cache between steps).  `value` = RGBA bytes pushed through the round
+trip per second, all GPUs together (frames are independent: ranks take disjoint frames, no collective
+on the data path, weak scaling).
+Extra legs, outside the timed region: per-stage CUDA-event timing for the roofline object, the
+end-to-end leg through the host-pointer C-ABI (PCIe inside the timed region), and a bounded CPU run
+of the reference path for `cpu_baseline`.  `--impl reference` times only that CPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, CHUNKS = 3840, 2160, 8
+RGBA_BYTES = 4 * W * H            # 33 177 600
+DXT_BYTES = W * H                 # 8 294 400 (16 B per 4x4 block)
+WORKLOAD = "hap_q_4k_rgba_encode_decode(3840x2160,YCoCg-DXT5,snappy,8chunks)"
+METRIC = "hapq_4k_encode_decode_rgba_GBps"
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured(MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback(B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# =====================================================================================================
+# CPU reference path (bounded sample): used by cpu_baseline and by --impl reference
+# =====================================================================================================
+
+def cpu_reference_sample(steps: int, warmup: int):
+    """One step = a 1/8 band of a 4K frame (3840x272 rounded to 3840x272 -> one chunk's worth of blocks):
+    RGBA -> YCoCg-DXT5 on all host cores (oracle cluster fit, 1 iteration, the CPU stand-in for the
+    encoder the reference ecosystem puts upstream of HapEncode -- the reference repo itself ships
+    none), then the UNMODIFIED reference HapEncode (Snappy) and HapDecode (oracle/_ref), threads =
+    host cores.  Returns (GB/s RGBA-equivalent, cores, kind, sample description)."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracles
+    from hap_b200 import synth
+    from hap_b200.abi import HapTextureFormat_YCoCg_DXT5
+
+    cores = os.cpu_count() or 1
+    band_h = 272 - 272 % 4
+    img = synth.frame(W, H, 0).numpy()[540:540 + band_h]  # picture content, not the letterbox
+    img = np.ascontiguousarray(img)
+    ref = oracles.ref_abi()
+    kind = "reference" if ref is not None else "port"
+    codec = ref if ref is not None else oracles.oracle_abi()
+    rows = [(y, min(y + 16, band_h)) for y in range(0, band_h, 16)]
+    pool = ThreadPoolExecutor(cores)
+
+    def dxt_stage():
+        parts = list(pool.map(lambda r: oracles.bc_encode_clusterfit("ycocg", img[r[0]:r[1]], 1), rows))
+        return b"".join(parts)
+
+    n_tex = (W // 4) * (band_h // 4) * 16
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        tex = dxt_stage()
+        r, frame = codec.encode([tex], [HapTextureFormat_YCoCg_DXT5], [1], [1])
+        assert r == 0 and len(tex) == n_tex
+        r, back, fmt, _ = codec.decode(frame, 0, n_tex)
+        assert r == 0 and back == tex
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t = statistics.median(times)
+    gbps = (4 * W * band_h) / t / 1e9
+    sample = (f"3840x{band_h} band (1/8 of a 4K frame, one chunk): oracle cluster-fit YCoCg-DXT5 on {cores} threads + "
+              f"{'unmodified reference hap.c + Google Snappy' if kind == 'reference' else 'oracle port'} HapEncode/HapDecode, "
+              f"median of {steps}")
+    return gbps, cores, kind, sample, t
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    gbps, cores, kind, sample, t = cpu_reference_sample(args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbps, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": {"workload": WORKLOAD, "l2": "cpu"},
+        "cpu_baseline": {"value": gbps, "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# =====================================================================================================
+# GPU arm
+# =====================================================================================================
+
+def run_gpu_arm(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import hap_b200
+    from hap_b200 import synth
+    from hap_b200.lib import HapB200Codec_HapY
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = hap_b200.load()
+    F = args.frames
+    codec = HapB200Codec_HapY
+
+    # ---- synthetic, device-resident input: F distinct frames per rank -------------------------------
+    rgba = torch.empty((F, H, W, 4), dtype=torch.uint8, device=dev)
+    for i in range(F):
+        rgba[i] = synth.frame(W, H, rank * F + i, device=dev)
+    cap = (lib.max_encoded_length_rgba(W, H, codec, CHUNKS) + 15) // 16 * 16
+    frames_buf = torch.empty(F * cap, dtype=torch.uint8, device=dev)
+    used = torch.zeros(F, dtype=torch.int64, device=dev)
+    tex = torch.empty(F * DXT_BYTES, dtype=torch.uint8, device=dev)
+    tex_used = torch.zeros(F, dtype=torch.int64, device=dev)
+    fmts = torch.zeros(F, dtype=torch.int32, device=dev)
+    res = torch.zeros(F, dtype=torch.int32, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    sp = stream.cuda_stream
+
+    def step():
+        r = lib.encode_rgba_batch(rgba.data_ptr(), F, RGBA_BYTES, W, H, codec, 1, CHUNKS, frames_buf.data_ptr(), cap,
+                                  used.data_ptr(), stream=sp)
+        assert r == 0, r
+        r = lib.decode_batch(frames_buf.data_ptr(), F, cap, used.data_ptr(), 0, CHUNKS, tex.data_ptr(), DXT_BYTES,
+                             tex_used.data_ptr(), fmts.data_ptr(), res.data_ptr(), stream=sp)
+        assert r == 0, r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        assert res.tolist() == [0] * F and tex_used.tolist() == [DXT_BYTES] * F, "decode failed in warm-up"
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = lib.launches()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        launches = lib.launches() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_per_step = ms_total / args.steps
+    value = world * F * RGBA_BYTES / (ms_per_step * 1e-3) / 1e9
+    mean_frame = float(used.double().mean().item())
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline leg: per-stage CUDA events (not part of the timed region) ------------------------------
+    lib.set_stage_timing(True)
+    lib.stage_times()
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            step()
+    st = lib.stage_times()
+    lib.set_stage_timing(False)
+    stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in st.items()}
+    per_step = {k: v[0] / 3 for k, v in st.items()}
+    dominant = max(stage_ms, key=lambda k: per_step[k])
+    alg_bytes = {
+        "bc_encode": F * (RGBA_BYTES + DXT_BYTES),                   # RGBA read once + DXT written once
+        "snappy_encode": F * DXT_BYTES + F * mean_frame,             # DXT read + element streams written
+        "plan": F * 4096.0,
+        "place": 2 * F * mean_frame,                                 # element streams read + frame written
+        "parse": F * 256.0,
+        "snappy_decode": F * mean_frame + F * DXT_BYTES,             # frame read + texture written
+        "collect": F * 64.0,
+        "bc_decode": F * (DXT_BYTES + RGBA_BYTES),
+    }
+    peak, peak_src = measured_peak_hbm()
+    dom_ms = stage_ms[dominant]
+    achieved = alg_bytes[dominant] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dominant)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes[dominant], "ms_per_launch": dom_ms,
+                "stage_ms_per_step": per_step}
+
+    # ---- end-to-end leg: the host-pointer C-ABI, PCIe copies inside the timed region ------------------
+    FE = min(args.e2e_frames, F)
+    host_rgba = torch.empty((FE, H, W, 4), dtype=torch.uint8).pin_memory()
+    host_rgba.copy_(rgba[:FE])
+    host_frame = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    host_tex = torch.empty(DXT_BYTES, dtype=torch.uint8).pin_memory()
+    import ctypes as C
+    from hap_b200.abi import DECODE_CB, WORK_FN
+
+    def _cb(function, p, count, info):
+        for i in range(count):
+            function(p, i)
+    cb = DECODE_CB(_cb)
+    usedc, fmtc = C.c_ulong(0), C.c_uint(0)
+
+    def e2e_step():
+        total_in = total_out = 0
+        for i in range(FE):
+            r = lib.lib.HapB200EncodeRGBA(host_rgba[i].data_ptr(), W, H, 4 * W, codec, 1, CHUNKS, host_frame.data_ptr(), cap,
+                                          C.byref(usedc))
+            assert r == 0, r
+            n = usedc.value
+            r = lib._dec(host_frame.data_ptr(), n, 0, cb, None, host_tex.data_ptr(), DXT_BYTES, C.byref(usedc), C.byref(fmtc))
+            assert r == 0 and usedc.value == DXT_BYTES, (r, usedc.value)
+            total_in += RGBA_BYTES + n
+            total_out += n + DXT_BYTES
+        return total_in, total_out
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    e2e_iters = 3
+    for _ in range(e2e_iters):
+        h2d, d2h = e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_t = (time.perf_counter() - t0) / e2e_iters
+    e2e = {"value": FE * RGBA_BYTES / e2e_t / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "frames_per_step": FE, "api": "HapB200EncodeRGBA + HapDecode, pinned host buffers, one frame per call"}
+
+    # ---- CPU baseline leg (bounded) ------------------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            gbps, cores, kind, sample, _ = cpu_reference_sample(5, 1)
+            cpu = {"value": gbps, "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample}
+        except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
+            cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port", "sample": f"unavailable: {e}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "l2": "inputs larger than L2 (%.2f GB RGBA per step per GPU)" % (F * RGBA_BYTES / 1e9),
+                   "compression_ratio": mean_frame / DXT_BYTES, "parallelism": f"frames sharded over {world} gpu(s), no collective"},
+        "fps": world * F / (ms_per_step * 1e-3),
+        "encode_decode_split_ms": {"encode": per_step["bc_encode"] + per_step["snappy_encode"] + per_step["plan"] + per_step["place"],
+                                   "decode": per_step["parse"] + per_step["snappy_decode"] + per_step["collect"]},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=32, help="device-resident frames per GPU per step")
+    ap.add_argument("--e2e-frames", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    run_gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,8 +25,41 @@ using namespace hapb200;
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
-#define HAP_KLAUNCH(kernel, grid, block, smem, stream, ...)                \
+
+// Optional per-stage device timing (HapB200SetStageTiming): CUDA events around every kernel, on the
+// stream the kernel is launched on.  Off by default; bench.py turns it on for its roofline pass only.
+enum Stage { kStBcEncode = 0, kStSnappyEncode, kStPlan, kStPlace, kStParse, kStSnappyDecode, kStCollect, kStBcDecode, kStCount };
+struct StageTimer {
+    std::mutex mu;
+    bool on = false;
+    struct Rec { int stage; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    double ms[kStCount] = {0};
+    unsigned long long n[kStCount] = {0};
+};
+StageTimer g_timer;
+
+struct StageScope {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t st;
+    int stage;
+    bool live;
+    StageScope(int stage_, cudaStream_t st_) : st(st_), stage(stage_), live(g_timer.on)
+    {
+        if (live) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~StageScope()
+    {
+        if (!live) return;
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> l(g_timer.mu);
+        g_timer.recs.push_back({stage, a, b});
+    }
+};
+
+#define HAP_KLAUNCH(stage, kernel, grid, block, smem, stream, ...)         \
     do {                                                                   \
+        StageScope hap_scope_(stage, stream);                              \
         HAP_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__);        \
         g_launches.fetch_add(1, std::memory_order_relaxed);                \
     } while (0)
@@ -118,11 +151,11 @@ uint32_t launch_encode(const uint8_t *base, const FrameGeom &G, uint32_t frames,
         cudaGetLastError();
         return HapResult_Internal_Error;
     }
-    HAP_KLAUNCH(snappy_encode_fragments_kernel, dim3((unsigned)nfrag), dim3(kEncThreads), sizeof(EncodeSmem), st, base, G,
+    HAP_KLAUNCH(kStSnappyEncode, snappy_encode_fragments_kernel, dim3((unsigned)nfrag), dim3(kEncThreads), sizeof(EncodeSmem), st, base, G,
                 scratch.as<uint8_t>(), fsize.as<uint32_t>());
-    HAP_KLAUNCH(hap_plan_frames_kernel, dim3(frames), dim3(kPlanThreads), 0, st, G, base, fsize.as<uint32_t>(),
+    HAP_KLAUNCH(kStPlan, hap_plan_frames_kernel, dim3(frames), dim3(kPlanThreads), 0, st, G, base, fsize.as<uint32_t>(),
                 fdst.as<uint32_t>(), out, out_stride, used);
-    HAP_KLAUNCH(hap_place_fragments_kernel, dim3((unsigned)nfrag), dim3(kPlaceThreads), 0, st, G, base,
+    HAP_KLAUNCH(kStPlace, hap_place_fragments_kernel, dim3((unsigned)nfrag), dim3(kPlaceThreads), 0, st, G, base,
                 scratch.as<uint8_t>(), fsize.as<uint32_t>(), fdst.as<uint32_t>(), out, out_stride);
     return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
 }
@@ -141,11 +174,11 @@ uint32_t launch_block_encode(const uint8_t *rgba, uint32_t frames, uint64_t fram
     g.second_offset = second_offset;
     dim3 grid((g.blocks_x * g.blocks_y + kBcThreads - 1) / kBcThreads, frames);
     switch (ci.bc_kind) {
-    case kBcDxt1: HAP_KLAUNCH(bc_encode_kernel<kBcDxt1>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
-    case kBcDxt5: HAP_KLAUNCH(bc_encode_kernel<kBcDxt5>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
-    case kBcYCoCg: HAP_KLAUNCH(bc_encode_kernel<kBcYCoCg>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
-    case kBcRgtc1: HAP_KLAUNCH(bc_encode_kernel<kBcRgtc1>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
-    default: HAP_KLAUNCH(bc_encode_kernel<kBcYCoCgPlusAlpha>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
+    case kBcDxt1: HAP_KLAUNCH(kStBcEncode, bc_encode_kernel<kBcDxt1>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
+    case kBcDxt5: HAP_KLAUNCH(kStBcEncode, bc_encode_kernel<kBcDxt5>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
+    case kBcYCoCg: HAP_KLAUNCH(kStBcEncode, bc_encode_kernel<kBcYCoCg>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
+    case kBcRgtc1: HAP_KLAUNCH(kStBcEncode, bc_encode_kernel<kBcRgtc1>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
+    default: HAP_KLAUNCH(kStBcEncode, bc_encode_kernel<kBcYCoCgPlusAlpha>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
     }
     return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
 }
@@ -164,10 +197,10 @@ uint32_t launch_block_decode(const uint8_t *blocks, const uint8_t *alpha, uint32
     g.frame_bytes = frame_stride;
     dim3 grid((g.blocks_x * g.blocks_y + kBcThreads - 1) / kBcThreads, frames);
     switch (ci.bc_kind) {
-    case kBcDxt1: HAP_KLAUNCH(bc_decode_kernel<kBcDxt1>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
-    case kBcDxt5: HAP_KLAUNCH(bc_decode_kernel<kBcDxt5>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
-    case kBcRgtc1: HAP_KLAUNCH(bc_decode_kernel<kBcRgtc1>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
-    default: HAP_KLAUNCH(bc_decode_kernel<kBcYCoCg>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
+    case kBcDxt1: HAP_KLAUNCH(kStBcDecode, bc_decode_kernel<kBcDxt1>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
+    case kBcDxt5: HAP_KLAUNCH(kStBcDecode, bc_decode_kernel<kBcDxt5>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
+    case kBcRgtc1: HAP_KLAUNCH(kStBcDecode, bc_decode_kernel<kBcRgtc1>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
+    default: HAP_KLAUNCH(kStBcDecode, bc_decode_kernel<kBcYCoCg>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
     }
     return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
 }
@@ -181,11 +214,11 @@ uint32_t launch_decode_batch(const uint8_t *in, uint32_t frames, uint64_t in_str
     if (njobs == 0 || njobs >= (1ull << 31)) return HapResult_Bad_Arguments;
     DevBuf jobs(st), whole(st);
     if (!jobs.alloc(njobs * sizeof(ChunkJob)) || !whole.alloc((size_t)frames * 4)) { cudaGetLastError(); return HapResult_Internal_Error; }
-    HAP_KLAUNCH(hap_parse_frames_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, in, in_stride, in_bytes, frames, index,
+    HAP_KLAUNCH(kStParse, hap_parse_frames_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, in, in_stride, in_bytes, frames, index,
                 max_chunks, out, out_stride, jobs.as<ChunkJob>(), used, formats, results, whole.as<uint32_t>());
-    HAP_KLAUNCH(snappy_decode_chunks_kernel, dim3((unsigned)njobs), dim3(kDecThreads), sizeof(DecodeSmem), st,
+    HAP_KLAUNCH(kStSnappyDecode, snappy_decode_chunks_kernel, dim3((unsigned)njobs), dim3(kDecThreads), sizeof(DecodeSmem), st,
                 jobs.as<ChunkJob>(), (int)njobs);
-    HAP_KLAUNCH(hap_collect_status_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, jobs.as<ChunkJob>(), frames,
+    HAP_KLAUNCH(kStCollect, hap_collect_status_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, jobs.as<ChunkJob>(), frames,
                 max_chunks, whole.as<uint32_t>(), results, used);
     return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
 }
@@ -225,6 +258,32 @@ extern "C" {
 
 const char *HapB200Version(void) { return "hap-b200 0.1 (sm_100a)"; }
 unsigned long long HapB200KernelLaunchCount(void) { return g_launches.load(); }
+
+void HapB200SetStageTiming(int enabled)
+{
+    std::lock_guard<std::mutex> l(g_timer.mu);
+    g_timer.on = enabled != 0;
+}
+
+// Synchronises the device, folds the recorded events into per-stage totals and returns them:
+// ms[i], launches[i] for i < n (stage order: bc_encode, snappy_encode, plan, place, parse, snappy_decode,
+// collect, bc_decode).  Totals are reset by the call.
+int HapB200StageTimes(double *ms, unsigned long long *launches, int n)
+{
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> l(g_timer.mu);
+    for (auto &r : g_timer.recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { g_timer.ms[r.stage] += t; g_timer.n[r.stage]++; }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_timer.recs.clear();
+    for (int i = 0; i < n && i < kStCount; i++) { ms[i] = g_timer.ms[i]; launches[i] = g_timer.n[i]; }
+    for (int i = 0; i < kStCount; i++) { g_timer.ms[i] = 0; g_timer.n[i] = 0; }
+    cudaGetLastError();
+    return kStCount;
+}
 
 // hap.c:324-353
 unsigned long HapMaxEncodedLength(unsigned int count, unsigned long *lengths, unsigned int *textureFormats,
@@ -511,7 +570,7 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
         }
         if (!djobs.alloc(jobs.size() * sizeof(ChunkJob)) ||
             cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(ChunkJob), cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
-        HAP_KLAUNCH(snappy_decode_chunks_kernel, dim3((unsigned)jobs.size()), dim3(kDecThreads), sizeof(DecodeSmem), st,
+        HAP_KLAUNCH(kStSnappyDecode, snappy_decode_chunks_kernel, dim3((unsigned)jobs.size()), dim3(kDecThreads), sizeof(DecodeSmem), st,
                     djobs.as<ChunkJob>(), (int)jobs.size());
         if (compressor == kHapComplex && jobs.size() > 1) {
             WorkState ws;
@@ -715,7 +774,7 @@ unsigned int HapB200DecodeRGBABatch(const void *in, unsigned int frames, unsigne
         r = launch_decode_batch((const uint8_t *)in, frames, inStride, inBytes, ti, maxChunks, dxt.as<uint8_t>() + (ti ? align16(t0) : 0),
                                 dxt_stride, used.as<unsigned long long>(), formats.as<uint32_t>(), res, st);
         if (r != HapResult_No_Error) break;
-        HAP_KLAUNCH(hap_check_texture_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, frames, used.as<unsigned long long>(),
+        HAP_KLAUNCH(kStCollect, hap_check_texture_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, frames, used.as<unsigned long long>(),
                     formats.as<uint32_t>(), res, (unsigned long long)(ti ? t1 : t0), ci.fmt[ti], results);
     }
     if (r == HapResult_No_Error)

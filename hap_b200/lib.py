@@ -26,6 +26,10 @@ class HapB200(HapABI):
         vp, u, ul, ull_p, u_p = C.c_void_p, C.c_uint, C.c_ulong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint)
         L.HapB200Version.restype = C.c_char_p
         L.HapB200KernelLaunchCount.restype = C.c_ulonglong
+        L.HapB200SetStageTiming.restype = None
+        L.HapB200SetStageTiming.argtypes = [C.c_int]
+        L.HapB200StageTimes.restype = C.c_int
+        L.HapB200StageTimes.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), C.c_int]
         L.HapB200MaxEncodedLengthRGBA.restype = ul
         L.HapB200MaxEncodedLengthRGBA.argtypes = [u, u, u, u]
         L.HapB200TextureBytes.restype = ul
@@ -52,6 +56,18 @@ class HapB200(HapABI):
 
     def launches(self) -> int:
         return int(self.lib.HapB200KernelLaunchCount())
+
+    STAGES = ("bc_encode", "snappy_encode", "plan", "place", "parse", "snappy_decode", "collect", "bc_decode")
+
+    def set_stage_timing(self, on: bool):
+        self.lib.HapB200SetStageTiming(1 if on else 0)
+
+    def stage_times(self):
+        """{stage: (total ms, launches)} since the last call; synchronises the device."""
+        ms = (C.c_double * 8)()
+        n = (C.c_ulonglong * 8)()
+        self.lib.HapB200StageTimes(ms, n, 8)
+        return {s: (float(ms[i]), int(n[i])) for i, s in enumerate(self.STAGES)}
 
     def max_encoded_length_rgba(self, w, h, codec, chunks) -> int:
         return int(self.lib.HapB200MaxEncodedLengthRGBA(w, h, codec, chunks))

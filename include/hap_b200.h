@@ -29,6 +29,12 @@ enum HapB200Codec {
 const char *HapB200Version(void);
 /* kernels launched by this library in this process so far (bench.py reports the delta) */
 unsigned long long HapB200KernelLaunchCount(void);
+/* Per-stage device timing for profiling runs: when enabled every kernel launch is bracketed by CUDA
+ * events on its own stream.  HapB200StageTimes synchronises, returns milliseconds and launch counts
+ * per stage (bc_encode, snappy_encode, plan, place, parse, snappy_decode, collect, bc_decode) and
+ * resets them; its return value is the number of stages. */
+void HapB200SetStageTiming(int enabled);
+int HapB200StageTimes(double *ms, unsigned long long *launches, int n);
 
 /* worst-case frame size for a width x height frame of `codec` (HapMaxEncodedLength on its textures) */
 unsigned long HapB200MaxEncodedLengthRGBA(unsigned int width, unsigned int height, unsigned int codec,

@@ -1,0 +1,203 @@
+"""Parity of the CUDA path (libhap_b200.so, through its C-ABI) against the reference: golden vectors
+produced by the unmodified hap.c, the CPU oracle on seeded inputs, and size-independent round-trip
+properties at BASELINE.json's full sizes.  Bit-exact throughout (byte work)."""
+import numpy as np
+import pytest
+import torch
+
+import hap_b200
+import oracles
+from golden_util import container_checks, golden, kat_c_bytes, noise_bytes, sha
+from hap_b200 import synth
+from hap_b200.abi import (HapCompressorNone, HapCompressorSnappy, HapTextureFormat_A_RGTC1, HapTextureFormat_RGB_DXT1,
+                          HapTextureFormat_RGBA_DXT5, HapTextureFormat_YCoCg_DXT5)
+
+pytestmark = pytest.mark.gpu
+DXT1, DXT5, YCOCG, RGTC1 = HapTextureFormat_RGB_DXT1, HapTextureFormat_RGBA_DXT5, HapTextureFormat_YCoCg_DXT5, HapTextureFormat_A_RGTC1
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return hap_b200.load()
+
+
+def dxt_like(rng, blocks, bs):
+    base = rng.integers(0, 256, size=bs * 8, dtype=np.uint8)
+    p = np.tile(base, blocks // 8 + 1)[: blocks * bs].copy()
+    p[:: int(rng.integers(5, 60))] = rng.integers(0, 256)
+    return p.tobytes()
+
+
+def test_golden_vectors_of_the_reference(lib):
+    assert container_checks(lib) == []
+
+
+def test_kernels_really_ran(lib):
+    before = lib.launches()
+    x = bytes([0x55]) * 64
+    r, f = lib.encode([x], [DXT1], [HapCompressorSnappy], [1])
+    assert r == 0 and lib.launches() >= before + 3
+    assert lib.decode(f, 0, 64)[:3] == (0, x, DXT1)
+    assert lib.launches() >= before + 4
+
+
+def test_encode_kats(lib):
+    G = golden()
+    orc = oracles.oracle_abi()
+    x = bytes([0x55]) * 64
+    r, f = lib.encode([x], [DXT1], [HapCompressorSnappy], [1])
+    # container bytes up to the size table are fixed by the format; the Snappy bytes are ours
+    assert r == 0 and f[3] == 0xCB and f[4:17].hex() == G["kat_a"]["frame"][8:34]
+    assert orc.decode(f, 0, 64)[:3] == (0, x, DXT1)
+    # KAT-B: incompressible -> whole-texture fallback, byte-identical to the reference
+    nb = noise_bytes(4147200)
+    r, f = lib.encode([nb], [DXT1], [HapCompressorSnappy], [4])
+    assert r == 0 and len(f) == G["kat_b"]["frame_len"] and sha(f) == G["kat_b"]["frame_sha256"]
+    # KAT-C: 8-byte header chosen before compression
+    cb = kat_c_bytes()
+    r, f = lib.encode([cb], [YCOCG], [HapCompressorSnappy], [8])
+    assert r == 0 and f[:4].hex() == "000000cf" and f[8:28].hex() == G["kat_c"]["header"][16:56]
+    assert lib.chunk_count(f, 0) == (0, 8)
+    assert lib.decode(f, 0, len(cb) - 1)[0] == G["kat_c"]["results"]["short_out"]
+    assert lib.decode(f[:-5], 0, len(cb))[0] == G["kat_c"]["results"]["truncated_in"]
+    r, data, fmt, calls = lib.decode(f, 0, len(cb))
+    assert r == 0 and data == cb and calls == [8]
+    assert orc.decode(f, 0, len(cb))[:2] == (0, cb)
+    # KAT-D: two textures
+    t0, t1 = kat_c_bytes(4096), bytes([0x55]) * 2048
+    r, f = lib.encode([t0, t1], [YCOCG, RGTC1], [1, 1], [2, 2])
+    assert r == 0 and lib.texture_count(f) == (0, 2)
+    assert orc.decode(f, 0, 4096)[:3] == (0, t0, YCOCG) and orc.decode(f, 1, 2048)[:3] == (0, t1, RGTC1)
+    # KAT-E: chunk limiting
+    payload = kat_c_bytes(1036800)
+    for ask, e in G["kat_e"].items():
+        r, f = lib.encode([payload], [DXT1], [HapCompressorSnappy], [int(ask)])
+        assert r == e["result"] and lib.chunk_count(f, 0)[1] == e["chunk_count"] and f[3] == e["type"], ask
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_differential_against_oracle_and_reference(lib, seed):
+    rng = np.random.default_rng(seed)
+    fmt = [DXT1, YCOCG, RGTC1, DXT5, 0x8E8C][seed % 5]
+    bs = 8 if fmt in (DXT1, RGTC1) else 16
+    blocks = int(rng.integers(1, 40000))
+    payload = dxt_like(rng, blocks, bs)
+    k = int(rng.integers(1, 20))
+    orc, ref = oracles.oracle_abi(), oracles.ref_abi()
+    for comp in (HapCompressorNone, HapCompressorSnappy):
+        r, f = lib.encode([payload], [fmt], [comp], [k])
+        assert r == 0
+        ro, fo = orc.encode([payload], [fmt], [comp], [k])
+        if comp == HapCompressorNone:
+            assert f == fo
+        assert lib.chunk_count(f, 0) == orc.chunk_count(fo, 0)
+        for dec in (orc, ref, lib):
+            if dec is not None:
+                assert dec.decode(f, 0, len(payload))[:3] == (0, payload, fmt)
+        # frames compressed by the oracle (and by Google Snappy through the reference) decode on the GPU
+        assert lib.decode(fo, 0, len(payload))[:3] == (0, payload, fmt)
+        if ref is not None:
+            rr, fr = ref.encode([payload], [fmt], [comp], [k])
+            assert lib.decode(fr, 0, len(payload))[:3] == (0, payload, fmt)
+
+
+def test_corrupt_streams_never_crash_and_match_oracle_status(lib):
+    rng = np.random.default_rng(5)
+    orc = oracles.oracle_abi()
+    payload = dxt_like(rng, 5000, 16)
+    r, good = orc.encode([payload], [YCOCG], [1], [3])
+    for i in range(60):
+        f = bytearray(good)
+        what = i % 3
+        if what == 0:
+            f = f[: len(f) - 1 - int(rng.integers(0, 300))]
+        elif what == 1:
+            f[int(rng.integers(4, len(f)))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            p = int(rng.integers(40, len(f) - 2))
+            f[p] = int(rng.integers(0, 256))
+        f = bytes(f)
+        want = orc.decode(f, 0, len(payload))
+        got = lib.decode(f, 0, len(payload))
+        if want[0] == 0:
+            assert got[:3] == want[:3], i
+        else:
+            # the oracle may run off the section like hap.c does; ours must say Bad_Frame or agree
+            assert got[0] != 0, i
+
+
+def test_device_pointers_and_callback_contract(lib):
+    rng = np.random.default_rng(9)
+    payload = dxt_like(rng, 8192, 16)
+    r, f = lib.encode([payload], [YCOCG], [1], [8])
+    dev_frame = torch.frombuffer(bytearray(f), dtype=torch.uint8).cuda()
+    dev_out = torch.empty(len(payload), dtype=torch.uint8, device="cuda")
+    r, used, fmt, calls = lib.decode((dev_frame.data_ptr(), len(f)), 0, len(payload), out=(dev_out.data_ptr(), len(payload)))
+    assert (r, used, fmt, calls) == (0, len(payload), YCOCG, [8])
+    assert dev_out.cpu().numpy().tobytes() == payload
+    # one chunk: the callback must not be called
+    r, f1 = lib.encode([payload], [YCOCG], [1], [1])
+    assert lib.decode(f1, 0, len(payload))[3] == []
+    # device texture in, device frame out
+    dev_tex = torch.frombuffer(bytearray(payload), dtype=torch.uint8).cuda()
+    cap = lib.max_encoded_length([len(payload)], [YCOCG], [8])
+    dev_f = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    r, used = lib.encode([(dev_tex.data_ptr(), len(payload))], [YCOCG], [1], [8], out=(dev_f.data_ptr(), cap), out_capacity=cap)
+    assert r == 0 and dev_f[:used].cpu().numpy().tobytes() == f
+
+
+def test_batch_encode_decode_roundtrip(lib):
+    from hap_b200.lib import HapB200Codec_HapY
+    frames, n = 6, 16 * 4096
+    rng = np.random.default_rng(11)
+    tex = torch.frombuffer(bytearray(b"".join(dxt_like(rng, 4096, 16) for _ in range(frames))), dtype=torch.uint8).cuda()
+    cap = (lib.max_encoded_length([n], [YCOCG], [4]) + 15) // 16 * 16
+    out = torch.zeros(frames * cap, dtype=torch.uint8, device="cuda")
+    used = torch.zeros(frames, dtype=torch.int64, device="cuda")
+    assert lib.encode_batch([tex.data_ptr()], [n], [n], [YCOCG], [1], [4], frames, out.data_ptr(), cap, used.data_ptr()) == 0
+    orc = oracles.oracle_abi()
+    host = out.cpu().numpy()
+    for f in range(frames):
+        fr = host[f * cap: f * cap + int(used[f])].tobytes()
+        assert orc.decode(fr, 0, n)[:2] == (0, tex[f * n:(f + 1) * n].cpu().numpy().tobytes())
+    back = torch.zeros(frames * n, dtype=torch.uint8, device="cuda")
+    bused = torch.zeros(frames, dtype=torch.int64, device="cuda")
+    fmts = torch.zeros(frames, dtype=torch.int32, device="cuda")
+    res = torch.full((frames,), 77, dtype=torch.int32, device="cuda")
+    assert lib.decode_batch(out.data_ptr(), frames, cap, used.data_ptr(), 0, 4, back.data_ptr(), n, bused.data_ptr(),
+                            fmts.data_ptr(), res.data_ptr()) == 0
+    assert res.tolist() == [0] * frames and bused.tolist() == [n] * frames and fmts.tolist() == [YCOCG] * frames
+    assert torch.equal(back, tex)
+    # max_chunks too small is reported per frame, not a crash
+    assert lib.decode_batch(out.data_ptr(), frames, cap, used.data_ptr(), 0, 2, back.data_ptr(), n, bused.data_ptr(),
+                            fmts.data_ptr(), res.data_ptr()) == 0
+    assert res.tolist() == [1] * frames
+
+
+@pytest.mark.parametrize("w,h,codec_name,k", [(1920, 1080, "Hap1", 1), (3840, 2160, "Hap1", 1), (3840, 2160, "HapY", 8),
+                                               (7680, 4320, "HapM", 32)])
+def test_full_size_roundtrip_properties(lib, w, h, codec_name, k):
+    """BASELINE.json configs 1-4 at full size: encode on the GPU, decode on the GPU AND in the reference
+    (bit-exact texture bytes), decoded picture close to the source."""
+    import hap_b200.lib as L
+    codec = getattr(L, "HapB200Codec_" + codec_name)
+    img = synth.frame(w, h, 0, alpha="ramp" if codec_name == "HapM" else "opaque", device="cuda")
+    cap = (lib.max_encoded_length_rgba(w, h, codec, k) + 15) // 16 * 16
+    out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    used = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert lib.encode_rgba_batch(img.data_ptr(), 1, img.numel(), w, h, codec, 1, k, out.data_ptr(), cap, used.data_ptr()) == 0
+    frame = out[: int(used[0])].cpu().numpy().tobytes()
+    ref = oracles.ref_abi() or oracles.oracle_abi()
+    ntex = 2 if codec_name == "HapM" else 1
+    assert lib.texture_count(frame) == (0, ntex)
+    for i in range(ntex):
+        n = lib.texture_bytes(w, h, codec, i)
+        a = ref.decode(frame, i, n)
+        b = lib.decode(frame, i, n)
+        assert a[0] == 0 and b[0] == 0 and a[1] == b[1] and a[2] == b[2] and len(a[1]) == n
+    r, rgba = lib.decode_rgba(frame, w, h)
+    assert r == 0
+    dec = np.frombuffer(rgba, np.uint8).reshape(h, w, 4)
+    src = img.cpu().numpy()
+    ch = (0, 1, 2, 3) if codec_name == "HapM" else (0, 1, 2)
+    assert oracles.psnr(src, dec, ch) > 38.0
