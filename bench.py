@@ -245,11 +245,15 @@ def run_gpu_arm(args, rank, local_rank, world):
     # ---- roofline leg: per-stage CUDA events (not part of the timed region) ------------------------------
     lib.set_stage_timing(True)
     lib.stage_times()
+    lib.decode_phase_cycles(reset=True)
     with torch.cuda.stream(stream):
         for _ in range(3):
             step()
     st = lib.stage_times()
     lib.set_stage_timing(False)
+    ph = lib.decode_phase_cycles(reset=True)
+    ph_total = max(sum(ph.values()), 1)
+    decode_phase_share = {k: round(v / ph_total, 4) for k, v in ph.items()}
     stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in st.items()}
     per_step = {k: v[0] / 3 for k, v in st.items()}
     dominant = max(stage_ms, key=lambda k: per_step[k])
@@ -276,7 +280,10 @@ def run_gpu_arm(args, rank, local_rank, world):
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes[dominant], "ms_per_launch": dom_ms,
-                "stage_ms_per_step": per_step}
+                "stage_ms_per_step": per_step, "decode_phase_share": decode_phase_share}
+    if args.profile:
+        print(json.dumps({"profile_only": True, "ms_per_step": ms_per_step, "value": value, "roofline": roofline}))
+        return
 
     # ---- end-to-end leg: the host-pointer C-ABI, PCIe copies inside the timed region ------------------
     FE = min(args.e2e_frames, F)
@@ -353,6 +360,7 @@ def main():
     ap.add_argument("--frames", type=int, default=32, help="device-resident frames per GPU per step")
     ap.add_argument("--e2e-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: skip the e2e and CPU legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -14,6 +14,7 @@ OUT = os.path.join(HERE, "libhap_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
+    "-DHAPB200_DECODE_PHASE_CYCLES",   # per-phase cycle counters of the decode kernel (5 atomics per window)
     "-fmad=false",             # FMAs are written explicitly (bc_block.cuh) so the CPU twin matches bit for bit
     "-Xcompiler", "-fPIC",
     "-shared", "--cudart", "shared",

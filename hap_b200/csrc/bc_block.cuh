@@ -141,11 +141,40 @@ HAP_HD void snap_channel(float &a, float &b, float a2, float b2, float ab, float
     b = best_b;
 }
 
+// One round of [project texels onto the segment a-b -> 4 clusters] + accumulate the normal-equation sums.
+struct FitSums {
+    float a2, b2, ab, axr, axg, axb, bxr, bxg, bxb;
+};
+HAP_HD bool cluster_sums(const float r[16], const float g[16], const float b[16], float ar, float ag, float ab_, float br,
+                         float bg, float bb, FitSums &S)
+{
+    float dr = br - ar, dg = bg - ag, db = bb - ab_;
+    float dd = hap_fma(dr, dr, hap_fma(dg, dg, db * db));
+    if (dd < 1e-6f) return false;
+    float scale = 3.0f / dd;
+    S.a2 = S.b2 = S.ab = S.axr = S.axg = S.axb = S.bxr = S.bxg = S.bxb = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        float s = hap_fma(r[t] - ar, dr, hap_fma(g[t] - ag, dg, (b[t] - ab_) * db)) * scale;
+        float q = fminf(fmaxf(floorf(s + 0.5f), 0.0f), 3.0f);
+        float be = q * (1.0f / 3.0f), al = 1.0f - be;
+        S.a2 = hap_fma(al, al, S.a2); S.b2 = hap_fma(be, be, S.b2); S.ab = hap_fma(al, be, S.ab);
+        S.axr = hap_fma(al, r[t], S.axr); S.axg = hap_fma(al, g[t], S.axg); S.axb = hap_fma(al, b[t], S.axb);
+        S.bxr = hap_fma(be, r[t], S.bxr); S.bxg = hap_fma(be, g[t], S.bxg); S.bxb = hap_fma(be, b[t], S.bxb);
+    }
+    return S.a2 * S.b2 - S.ab * S.ab >= 1e-4f;
+}
+
 // REFINE: least-squares rounds; RESNAP: extra rounds of Lloyd on the snapped endpoints; EXACT: final
 // indices by true nearest palette colour (else by projection onto the palette segment).
+// r,g,b arrive PRE-MULTIPLIED by the metric (sr,sg,sb) so that plain Euclidean distance in that space
+// is the error to minimise (RGB: 1,1,1; scaled YCoCg: sqrt2, sqrt3 -- an error (dCo,dCg) costs
+// 2 dCo^2 + 3 dCg^2 in RGB); endpoints go back to storage units before they meet the 5:6:5 grid.
 template <int REFINE, int RESNAP, bool EXACT>
-HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const float b[16], int fixed_blue5 = -1)
+HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const float b[16], int fixed_blue5 = -1,
+                                  float sr = 1.0f, float sg = 1.0f, float sb = 1.0f)
 {
+    const float isr = 1.0f / sr, isg = 1.0f / sg, isb = 1.0f / sb;
     // mean and covariance
     float mr = 0.f, mg = 0.f, mb = 0.f;
 #pragma unroll
@@ -158,14 +187,15 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
         crr = hap_fma(dr, dr, crr); crg = hap_fma(dr, dg, crg); crb = hap_fma(dr, db, crb);
         cgg = hap_fma(dg, dg, cgg); cgb = hap_fma(dg, db, cgb); cbb = hap_fma(db, db, cbb);
     }
-    float ar, ag, ab_, br, bg, bb;  // float endpoints a (index 0 side) and b
+    float ar, ag, ab_, br, bg, bb;  // endpoints a (index 0 side) and b, in STORAGE units from here on
     const float var = crr + cgg + cbb;
     if (var < 0.5f) {
-        // (near-)flat block: bracket the mean with its 5:6:5 grid neighbours so the 4 palette entries
-        // straddle it; the final nearest-index pass picks the closest
-        ar = floorf(mr * (31.0f / 255.0f)) * (255.0f / 31.0f); br = ceilf(mr * (31.0f / 255.0f)) * (255.0f / 31.0f);
-        ag = floorf(mg * (63.0f / 255.0f)) * (255.0f / 63.0f); bg = ceilf(mg * (63.0f / 255.0f)) * (255.0f / 63.0f);
-        ab_ = floorf(mb * (31.0f / 255.0f)) * (255.0f / 31.0f); bb = ceilf(mb * (31.0f / 255.0f)) * (255.0f / 31.0f);
+        // flat block: bracket the colour with its 5:6:5 grid neighbours so the 4 palette entries straddle
+        // it; the final index pass picks the closest
+        const float fr = mr * isr, fg = mg * isg, fb = mb * isb;
+        ar = floorf(fr * (31.0f / 255.0f)) * (255.0f / 31.0f); br = ceilf(fr * (31.0f / 255.0f)) * (255.0f / 31.0f);
+        ag = floorf(fg * (63.0f / 255.0f)) * (255.0f / 63.0f); bg = ceilf(fg * (63.0f / 255.0f)) * (255.0f / 63.0f);
+        ab_ = floorf(fb * (31.0f / 255.0f)) * (255.0f / 31.0f); bb = ceilf(fb * (31.0f / 255.0f)) * (255.0f / 31.0f);
     } else {
         // principal axis: power iteration from the covariance row with the largest diagonal
         float vr, vg, vb;
@@ -181,7 +211,7 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
             float inv = 1.0f / m;
             vr = nr * inv; vg = ng * inv; vb = nb * inv;
         }
-        // extent along the axis
+        // extent along the axis -> first endpoints (metric space)
         float tmin = 1e30f, tmax = -1e30f;
         const float vv = hap_fma(vr, vr, hap_fma(vg, vg, vb * vb));
         const float ivv = 1.0f / vv;
@@ -191,75 +221,47 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
             tmin = fminf(tmin, d);
             tmax = fmaxf(tmax, d);
         }
-        ar = hap_fma(vr, tmin, mr); ag = hap_fma(vg, tmin, mg); ab_ = hap_fma(vb, tmin, mb);
-        br = hap_fma(vr, tmax, mr); bg = hap_fma(vg, tmax, mg); bb = hap_fma(vb, tmax, mb);
+        float mar = hap_fma(vr, tmin, mr), mag = hap_fma(vg, tmin, mg), mab = hap_fma(vb, tmin, mb);
+        float mbr = hap_fma(vr, tmax, mr), mbg = hap_fma(vg, tmax, mg), mbb = hap_fma(vb, tmax, mb);
         // refinement: clusters implied by the current segment, then least squares for the endpoints
-        float a2 = 0.f, b2 = 0.f, ab = 0.f;
-        float axr = 0.f, axg = 0.f, axb = 0.f, bxr = 0.f, bxg = 0.f, bxb = 0.f;
+        FitSums S;
+        bool have = false;
 #pragma unroll 1
         for (int it = 0; it < REFINE; it++) {
-            float dr = br - ar, dg = bg - ag, db = bb - ab_;
-            float dd = hap_fma(dr, dr, hap_fma(dg, dg, db * db));
-            if (dd < 1e-6f) break;
-            float scale = 3.0f / dd;
-            float na2 = 0.f, nb2 = 0.f, nab = 0.f;
-            float naxr = 0.f, naxg = 0.f, naxb = 0.f, nbxr = 0.f, nbxg = 0.f, nbxb = 0.f;
-#pragma unroll
-            for (int t = 0; t < 16; t++) {
-                float s = hap_fma(r[t] - ar, dr, hap_fma(g[t] - ag, dg, (b[t] - ab_) * db)) * scale;
-                float q = floorf(s + 0.5f);
-                q = fminf(fmaxf(q, 0.0f), 3.0f);
-                float be = q * (1.0f / 3.0f), al = 1.0f - be;
-                na2 = hap_fma(al, al, na2); nb2 = hap_fma(be, be, nb2); nab = hap_fma(al, be, nab);
-                naxr = hap_fma(al, r[t], naxr); naxg = hap_fma(al, g[t], naxg); naxb = hap_fma(al, b[t], naxb);
-                nbxr = hap_fma(be, r[t], nbxr); nbxg = hap_fma(be, g[t], nbxg); nbxb = hap_fma(be, b[t], nbxb);
-            }
-            float det = na2 * nb2 - nab * nab;
-            if (det < 1e-4f) break;
-            a2 = na2; b2 = nb2; ab = nab;
-            axr = naxr; axg = naxg; axb = naxb; bxr = nbxr; bxg = nbxg; bxb = nbxb;
-            float idet = 1.0f / det;
-            ar = fminf(fmaxf((axr * b2 - bxr * ab) * idet, 0.f), 255.f);
-            ag = fminf(fmaxf((axg * b2 - bxg * ab) * idet, 0.f), 255.f);
-            ab_ = fminf(fmaxf((axb * b2 - bxb * ab) * idet, 0.f), 255.f);
-            br = fminf(fmaxf((bxr * a2 - axr * ab) * idet, 0.f), 255.f);
-            bg = fminf(fmaxf((bxg * a2 - axg * ab) * idet, 0.f), 255.f);
-            bb = fminf(fmaxf((bxb * a2 - axb * ab) * idet, 0.f), 255.f);
+            FitSums N;
+            if (!cluster_sums(r, g, b, mar, mag, mab, mbr, mbg, mbb, N)) break;
+            S = N;
+            have = true;
+            float idet = 1.0f / (S.a2 * S.b2 - S.ab * S.ab);
+            mar = (S.axr * S.b2 - S.bxr * S.ab) * idet; mbr = (S.bxr * S.a2 - S.axr * S.ab) * idet;
+            mag = (S.axg * S.b2 - S.bxg * S.ab) * idet; mbg = (S.bxg * S.a2 - S.axg * S.ab) * idet;
+            mab = (S.axb * S.b2 - S.bxb * S.ab) * idet; mbb = (S.bxb * S.a2 - S.axb * S.ab) * idet;
         }
+        ar = fminf(fmaxf(mar * isr, 0.f), 255.f); br = fminf(fmaxf(mbr * isr, 0.f), 255.f);
+        ag = fminf(fmaxf(mag * isg, 0.f), 255.f); bg = fminf(fmaxf(mbg * isg, 0.f), 255.f);
+        ab_ = fminf(fmaxf(mab * isb, 0.f), 255.f); bb = fminf(fmaxf(mbb * isb, 0.f), 255.f);
         // Grid snapping: for fixed clusters the squared error is separable per channel,
         //   E(a,b) = a^2 A2 + b^2 B2 + 2ab AB - 2a AX - 2b BX,
         // so each channel tries floor/ceil of both endpoints on its 5- or 6-bit grid (4 candidates).
-        if (a2 + b2 > 0.f) {
-            snap_channel(ar, br, a2, b2, ab, axr, bxr, 31.0f);
-            snap_channel(ag, bg, a2, b2, ab, axg, bxg, 63.0f);
-            snap_channel(ab_, bb, a2, b2, ab, axb, bxb, 31.0f);
+        if (have) {
+            snap_channel(ar, br, S.a2, S.b2, S.ab, S.axr * isr, S.bxr * isr, 31.0f);
+            snap_channel(ag, bg, S.a2, S.b2, S.ab, S.axg * isg, S.bxg * isg, 63.0f);
+            snap_channel(ab_, bb, S.a2, S.b2, S.ab, S.axb * isb, S.bxb * isb, 31.0f);
 #pragma unroll 1
             for (int it = 0; it < RESNAP; it++) {
                 // Lloyd on the quantised problem: re-cluster against the snapped segment, re-solve, re-snap
-                float dr = br - ar, dg = bg - ag, db = bb - ab_;
-                float dd = hap_fma(dr, dr, hap_fma(dg, dg, db * db));
-                if (dd < 1e-6f) break;
-                float scale = 3.0f / dd;
-                float na2 = 0.f, nb2 = 0.f, nab = 0.f;
-                float naxr = 0.f, naxg = 0.f, naxb = 0.f, nbxr = 0.f, nbxg = 0.f, nbxb = 0.f;
-#pragma unroll
-                for (int t = 0; t < 16; t++) {
-                    float s2 = hap_fma(r[t] - ar, dr, hap_fma(g[t] - ag, dg, (b[t] - ab_) * db)) * scale;
-                    float q = fminf(fmaxf(floorf(s2 + 0.5f), 0.0f), 3.0f);
-                    float be = q * (1.0f / 3.0f), al = 1.0f - be;
-                    na2 = hap_fma(al, al, na2); nb2 = hap_fma(be, be, nb2); nab = hap_fma(al, be, nab);
-                    naxr = hap_fma(al, r[t], naxr); naxg = hap_fma(al, g[t], naxg); naxb = hap_fma(al, b[t], naxb);
-                    nbxr = hap_fma(be, r[t], nbxr); nbxg = hap_fma(be, g[t], nbxg); nbxb = hap_fma(be, b[t], nbxb);
-                }
-                float det = na2 * nb2 - nab * nab;
-                if (det < 1e-4f) break;
-                float idet = 1.0f / det;
-                float car = fminf(fmaxf((naxr * nb2 - nbxr * nab) * idet, 0.f), 255.f), cbr = fminf(fmaxf((nbxr * na2 - naxr * nab) * idet, 0.f), 255.f);
-                float cag = fminf(fmaxf((naxg * nb2 - nbxg * nab) * idet, 0.f), 255.f), cbg = fminf(fmaxf((nbxg * na2 - naxg * nab) * idet, 0.f), 255.f);
-                float cab = fminf(fmaxf((naxb * nb2 - nbxb * nab) * idet, 0.f), 255.f), cbb2 = fminf(fmaxf((nbxb * na2 - naxb * nab) * idet, 0.f), 255.f);
-                snap_channel(car, cbr, na2, nb2, nab, naxr, nbxr, 31.0f);
-                snap_channel(cag, cbg, na2, nb2, nab, naxg, nbxg, 63.0f);
-                snap_channel(cab, cbb2, na2, nb2, nab, naxb, nbxb, 31.0f);
+                FitSums N;
+                if (!cluster_sums(r, g, b, ar * sr, ag * sg, ab_ * sb, br * sr, bg * sg, bb * sb, N)) break;
+                float idet = 1.0f / (N.a2 * N.b2 - N.ab * N.ab);
+                float car = fminf(fmaxf((N.axr * N.b2 - N.bxr * N.ab) * idet * isr, 0.f), 255.f);
+                float cbr = fminf(fmaxf((N.bxr * N.a2 - N.axr * N.ab) * idet * isr, 0.f), 255.f);
+                float cag = fminf(fmaxf((N.axg * N.b2 - N.bxg * N.ab) * idet * isg, 0.f), 255.f);
+                float cbg = fminf(fmaxf((N.bxg * N.a2 - N.axg * N.ab) * idet * isg, 0.f), 255.f);
+                float cab = fminf(fmaxf((N.axb * N.b2 - N.bxb * N.ab) * idet * isb, 0.f), 255.f);
+                float cbb2 = fminf(fmaxf((N.bxb * N.a2 - N.axb * N.ab) * idet * isb, 0.f), 255.f);
+                snap_channel(car, cbr, N.a2, N.b2, N.ab, N.axr * isr, N.bxr * isr, 31.0f);
+                snap_channel(cag, cbg, N.a2, N.b2, N.ab, N.axg * isg, N.bxg * isg, 63.0f);
+                snap_channel(cab, cbb2, N.a2, N.b2, N.ab, N.axb * isb, N.bxb * isb, 31.0f);
                 ar = car; br = cbr; ag = cag; bg = cbg; ab_ = cab; bb = cbb2;
             }
         }
@@ -286,18 +288,16 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
         tmp = a6g; a6g = b6g; b6g = tmp;
         tmp = a5b; a5b = b5b; b5b = tmp;
     }
-    // decoder palette ends (c0 = first endpoint), float for the projection
-    const float p0r = (float)expand5(a5r), p0g = (float)expand6(a6g), p0b = (float)expand5(a5b);
-    const float p1r = (float)expand5(b5r), p1g = (float)expand6(b6g), p1b = (float)expand5(b5b);
-    const float er = p1r - p0r, eg = p1g - p0g, eb = p1b - p0b;
-    const float ee = hap_fma(er, er, hap_fma(eg, eg, eb * eb));
-    const float sc = 3.0f / ee;
+    // decoder palette ends (c0 = first endpoint) in storage units, then in metric space for the comparisons
+    const float e0r = (float)expand5(a5r), e0g = (float)expand6(a6g), e0b = (float)expand5(a5b);
+    const float e1r = (float)expand5(b5r), e1g = (float)expand6(b6g), e1b = (float)expand5(b5b);
+    const float p0r = e0r * sr, p0g = e0g * sg, p0b = e0b * sb, p1r = e1r * sr, p1g = e1g * sg, p1b = e1b * sb;
     uint32_t bits = 0;
     if (EXACT) {
         // decoder palette (truncating thirds), DXT numbering 0 = c0, 1 = c1, 2, 3
-        const float q2r = floorf((2.0f * p0r + p1r) * (1.0f / 3.0f) + 0.01f), q3r = floorf((p0r + 2.0f * p1r) * (1.0f / 3.0f) + 0.01f);
-        const float q2g = floorf((2.0f * p0g + p1g) * (1.0f / 3.0f) + 0.01f), q3g = floorf((p0g + 2.0f * p1g) * (1.0f / 3.0f) + 0.01f);
-        const float q2b = floorf((2.0f * p0b + p1b) * (1.0f / 3.0f) + 0.01f), q3b = floorf((p0b + 2.0f * p1b) * (1.0f / 3.0f) + 0.01f);
+        const float q2r = floorf((2.0f * e0r + e1r) * (1.0f / 3.0f) + 0.01f) * sr, q3r = floorf((e0r + 2.0f * e1r) * (1.0f / 3.0f) + 0.01f) * sr;
+        const float q2g = floorf((2.0f * e0g + e1g) * (1.0f / 3.0f) + 0.01f) * sg, q3g = floorf((e0g + 2.0f * e1g) * (1.0f / 3.0f) + 0.01f) * sg;
+        const float q2b = floorf((2.0f * e0b + e1b) * (1.0f / 3.0f) + 0.01f) * sb, q3b = floorf((e0b + 2.0f * e1b) * (1.0f / 3.0f) + 0.01f) * sb;
 #pragma unroll
         for (int t = 0; t < 16; t++) {
             float d0 = hap_fma(r[t] - p0r, r[t] - p0r, hap_fma(g[t] - p0g, g[t] - p0g, (b[t] - p0b) * (b[t] - p0b)));
@@ -309,6 +309,9 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
             bits |= idx << (2 * t);
         }
     } else {
+        const float er = p1r - p0r, eg = p1g - p0g, eb = p1b - p0b;
+        const float ee = hap_fma(er, er, hap_fma(eg, eg, eb * eb));
+        const float sc = 3.0f / ee;
 #pragma unroll
         for (int t = 0; t < 16; t++) {
             float s = hap_fma(r[t] - p0r, er, hap_fma(g[t] - p0g, eg, (b[t] - p0b) * eb)) * sc;
@@ -326,6 +329,13 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
 // ---- scaled YCoCg (van Waveren & Castano 2007) ----------------------------------------------------
 // Per block: co = (R-B)/2, cg = (-R+2G-B)/4 kept as exact half/quarter integers; scale = largest of
 // {4,2,1} with |co*scale|,|cg*scale| <= 127; stored texel (Co', Cg', (scale-1)*8, Y).
+// RGB error of a chroma error (dCo, dCg): (dCo-dCg)^2 + dCg^2 + (dCo+dCg)^2 = 2 dCo^2 + 3 dCg^2
+#ifndef HAP_YCOCG_FIT
+#define HAP_YCOCG_FIT 2, 0, true
+#endif
+constexpr float kYCoCgMetricCo = 1.41421356f, kYCoCgMetricCg = 1.73205081f;
+
+// Returns the 5-bit scale code; cr/cg_ come back pre-multiplied by the metric above.
 HAP_HD int ycocg_block(const uint32_t px[16], float cr[16], float cg_[16], float cb[16], int yv[16])
 {
     int m2 = 0, m4 = 0;
@@ -347,8 +357,8 @@ HAP_HD int ycocg_block(const uint32_t px[16], float cr[16], float cg_[16], float
         // round half up of co2*scale/2 and cg4*scale/4 (arithmetic shift floors)
         int co = ((R - B) * scale + 1) >> 1;
         int cg = ((-R + 2 * G - B) * scale + 2) >> 2;
-        cr[t] = (float)hap_clampi(co + 128, 0, 255);
-        cg_[t] = (float)hap_clampi(cg + 128, 0, 255);
+        cr[t] = (float)hap_clampi(co + 128, 0, 255) * kYCoCgMetricCo;
+        cg_[t] = (float)hap_clampi(cg + 128, 0, 255) * kYCoCgMetricCg;
         cb[t] = sb;
         yv[t] = (R + 2 * G + B + 2) >> 2;
     }
@@ -381,7 +391,7 @@ HAP_HD void encode_ycocg_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colo
     int y[16];
     const int code = ycocg_block(px, r, g, b, y);
     alpha = encode_bc4_block(y);
-    colour = encode_colour_block<2, 0, false>(r, g, b, code);
+    colour = encode_colour_block<HAP_YCOCG_FIT>(r, g, b, code, kYCoCgMetricCo, kYCoCgMetricCg, 1.0f);
 }
 
 HAP_HD Block8 encode_rgtc1_alpha(const uint32_t px[16])

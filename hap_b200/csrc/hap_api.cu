@@ -65,7 +65,7 @@ struct StageScope {
     } while (0)
 
 struct Runtime {
-    std::mutex mu;          // serialises the host-pointer entry points (they share one stream)
+    std::mutex mu;          // serialises the host-pointer entry points (they share the legacy default stream)
     bool ready = false;
     bool failed = false;
     cudaStream_t stream = nullptr;
@@ -86,7 +86,10 @@ void runtime_init()
                                    (int)sizeof(DecodeSmem)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(snappy_encode_fragments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(EncodeSmem)) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&g_rt.stream, cudaStreamNonBlocking) == cudaSuccess;
+    // NULL-stream calls and the host-pointer entry points run on the LEGACY default stream: it orders itself
+    // against every blocking stream of the process, so buffers a caller produced on its own (blocking) stream --
+    // torch's current stream, cudaMemset, ... -- are complete before our kernels touch them.
+    g_rt.stream = cudaStreamLegacy;
     if (!ok) { g_rt.failed = true; cudaGetLastError(); return; }
     g_rt.ready = true;
 }
@@ -258,6 +261,20 @@ extern "C" {
 
 const char *HapB200Version(void) { return "hap-b200 0.1 (sm_100a)"; }
 unsigned long long HapB200KernelLaunchCount(void) { return g_launches.load(); }
+
+// Cycle counters of K7's phases (stage window, parse fixpoint, scans, descriptors, execute), summed over
+// CTAs by thread 0 of each; a profiling aid for kernel work, not part of the stable API.
+int HapB200DebugDecodePhaseCycles(unsigned long long *out, int n, int reset)
+{
+    unsigned long long h[8] = {0};
+    if (cudaMemcpyFromSymbol(h, g_decode_phase_cycles, sizeof h) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (int i = 0; i < n && i < 8; i++) out[i] = h[i];
+    if (reset) {
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_decode_phase_cycles, z, sizeof z);
+    }
+    return 8;
+}
 
 void HapB200SetStageTiming(int enabled)
 {

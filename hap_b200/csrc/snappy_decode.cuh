@@ -39,6 +39,9 @@ constexpr int kDecSub = 64;                        // compressed bytes owned by 
 constexpr int kDecWin = kDecThreads * kDecSub;     // 16 KiB of compressed input per window
 constexpr int kDecMaxElems = 3072;                 // descriptors held in shared memory per window
 constexpr uint32_t kLiteralMark = 0xFFFFFFFFu;
+constexpr uint32_t kLongLiteral = 1024;            // literals this long are copied by the whole CTA
+constexpr int kMaxLong = 64;
+constexpr int kGroups = kDecThreads / 8;           // 8-lane groups, one element each
 
 struct DecodeSmem {
     uint32_t e_dst[kDecMaxElems];    // output offset inside the chunk
@@ -49,6 +52,8 @@ struct DecodeSmem {
     uint8_t cin[kDecWin + 16];       // staged window of compressed bytes (+ header slack)
     uint32_t scratch[kDecThreads / 32];
     uint32_t bcast[4];
+    uint32_t n_long;                 // long literals of the current window
+    uint32_t long_list[kMaxLong];
     int fail;        // preamble / parse stage
     int fail_desc;   // descriptor stage (separate word: it is written while slow threads may still read `fail`)
 };
@@ -121,13 +126,51 @@ __device__ __forceinline__ WalkResult walk_subblock(const uint8_t *cin, uint32_t
     return r;
 }
 
+// dst/src any alignment.  `lane` of `n_lanes` cooperating threads; 4 bytes per thread per step once the
+// destination is word-aligned, the source word assembled from two aligned words when it is not.
+template <int N_LANES>
+__device__ __forceinline__ void lanes_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t lane)
+{
+    uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
+    if (head > len) head = len;
+    if (lane < head) dst[lane] = src[lane];
+    const uint32_t body = len - head;
+    uint32_t nw = body >> 2;
+    const uint8_t *s2 = src + head;
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + head);
+    const uint32_t mis = (uint32_t)((uintptr_t)s2 & 3);
+    if (mis == 0) {
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s2);
+        for (uint32_t k = lane; k < nw; k += N_LANES) d32[k] = s32[k];
+    } else {
+        // word k needs aligned words k and k+1; the last one would read past the source: leave it to the tail
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s2 - mis);
+        if (nw) nw -= 1;
+        for (uint32_t k = lane; k < nw; k += N_LANES) d32[k] = __funnelshift_r(s32[k], s32[k + 1], 8 * mis);
+    }
+    const uint32_t done = head + (nw << 2);
+    for (uint32_t i = done + lane; i < len; i += N_LANES) dst[i] = src[i];
+}
+__device__ __forceinline__ void group_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t glane) { lanes_copy<8>(dst, src, len, glane); }
+__device__ __forceinline__ void cta_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t t) { lanes_copy<kDecThreads>(dst, src, len, t); }
+
+#ifdef HAPB200_DECODE_PHASE_CYCLES
+__device__ unsigned long long g_decode_phase_cycles[8];
+#define PHASE_MARK(i) do { if (t == 0) { long long now_ = clock64(); atomicAdd(&g_decode_phase_cycles[i], (unsigned long long)(now_ - phase_t0_)); phase_t0_ = now_; } } while (0)
+#define PHASE_INIT long long phase_t0_ = clock64()
+#else
+#define PHASE_MARK(i) do { } while (0)
+#define PHASE_INIT do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(ChunkJob *jobs, int njobs)
 {
     HAP_DYN_SMEM(smem_raw);
     DecodeSmem &S = *reinterpret_cast<DecodeSmem *>(smem_raw);
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    constexpr int kWarps = kDecThreads / 32;
+    const int t = threadIdx.x;
+    const uint32_t grp = t >> 3, glane = t & 7;
     if ((int)blockIdx.x >= njobs) return;
+    PHASE_INIT;
     ChunkJob &job = jobs[blockIdx.x];
     const uint8_t *__restrict__ src = job.src;
     uint8_t *__restrict__ dst = job.dst;
@@ -184,12 +227,14 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
 
     while (wb < in_end) {
         // ---- stage the window ---------------------------------------------------------------
+        if (t == 0) S.n_long = 0;
         for (uint32_t i = t; i < kDecWin + 16; i += kDecThreads) {
             uint64_t g = (uint64_t)wb + i;
             S.cin[i] = g < in_end ? src[g] : 0;
         }
         __syncthreads();
 
+        PHASE_MARK(0);
         // ---- 1. speculative parallel parse to the fixpoint -----------------------------------
         const uint32_t blk_start = (uint64_t)wb + (uint64_t)t * kDecSub < in_end ? wb + t * kDecSub : in_end;
         const uint32_t blk_end = (uint64_t)wb + (uint64_t)(t + 1) * kDecSub < in_end ? wb + (t + 1) * kDecSub : in_end;
@@ -213,6 +258,7 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
             if (!__syncthreads_or(need ? 1 : 0)) break;
         }
 
+        PHASE_MARK(1);
         // ---- 2. scans: element slots and output offsets; window truncation -------------------
         uint32_t total_e, total_o;
         uint32_t ebase = block_excl_sum<kDecThreads>(w.count, &total_e, S.scratch);
@@ -229,6 +275,7 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
         __syncthreads();
         if (S.fail) break;
 
+        PHASE_MARK(2);
         // ---- descriptors ------------------------------------------------------------------------
         if (keep && entry < blk_end) {
             uint32_t pos = entry, e = ebase, o = d0 + obase;
@@ -240,7 +287,11 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
                 S.e_src[e] = aux;
                 if (kind == 0) {
                     S.e_base[e] = kLiteralMark;
-                    S.e_done[e] = 1;
+                    S.e_done[e] = 0;
+                    if (len >= kLongLiteral) {
+                        uint32_t q = atomicAdd(&S.n_long, 1u);
+                        if (q < (uint32_t)kMaxLong) S.long_list[q] = e;
+                    }
                     pos += hdr + len;
                 } else {
                     if (aux == 0 || aux > o) S.fail_desc = 1;  // offset 0 or before the start of the output
@@ -283,62 +334,84 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
         }
         __syncthreads();
 
-        // ---- 3a. literals: independent, source is the compressed stream --------------------------
-        for (uint32_t e = warp; e < total_e; e += kWarps) {
-            if (S.e_base[e] != kLiteralMark) continue;
-            const uint32_t len = S.e_len[e];
-            const uint8_t *s = src + S.e_src[e];
-            uint8_t *d = dst + S.e_dst[e];
-            for (uint32_t i = lane; i < len; i += 32) d[i] = s[i];
-        }
-        __syncthreads();
-
-        // ---- 3b. copies in dependency rounds -------------------------------------------------------
-        for (uint32_t round = 2;; round++) {
+        PHASE_MARK(3);
+        // ---- 3. execute: round 1 = literals and copies that only read earlier windows; later rounds =
+        //         copies whose producers finished in an earlier round.  An element is owned by a group of
+        //         8 lanes (4 bytes per lane per step), so a warp moves four elements at a time.
+        for (uint32_t round = 1;; round++) {
             int pending = 0;
-            for (uint32_t e = warp; e < total_e; e += kWarps) {
-                if (S.e_done[e]) continue;
-                const uint32_t len = S.e_len[e], off = S.e_src[e], base = S.e_base[e], o = S.e_dst[e];
-                const uint32_t rel = o - base;  // position of this element inside its run
-                // bytes this element reads: the run's base period, or just its own window of it
-                uint32_t need_lo, need_hi;
-                if (rel + len <= off) {
-                    need_lo = o - off;
-                    need_hi = need_lo + len;
-                } else {
-                    need_lo = base - off;
-                    need_hi = base;
-                }
-                bool ready = true;
-                if (need_hi > d0) {
-                    uint32_t x = need_lo > d0 ? need_lo : d0;
-                    // last element with e_dst <= x
-                    uint32_t a = 0, b = e;  // the producer is before e
-                    while (b - a > 1) {
-                        uint32_t m = (a + b) >> 1;
-                        if (S.e_dst[m] <= x) a = m; else b = m;
-                    }
-                    for (uint32_t f = a; f < e && S.e_dst[f] < need_hi; f++) {
-                        uint32_t dn = S.e_done[f];
-                        if (dn == 0 || dn >= round) { ready = false; break; }
-                    }
-                }
-                if (!ready) {
-                    pending = 1;
+            for (uint32_t e = grp; e < total_e; e += kGroups) {
+                const uint32_t dn = S.e_done[e];
+                if (dn != 0 && dn != round) continue;          // finished in an earlier round
+                const uint32_t len = S.e_len[e], base = S.e_base[e], o = S.e_dst[e];
+                uint8_t *d = dst + o;
+                if (base == kLiteralMark) {
+                    if (len >= kLongLiteral) continue;           // moved by the whole CTA below
+                    const uint32_t sp = S.e_src[e];
+                    // payload inside the staged window -> shared memory, else straight from the input
+                    const uint8_t *sl = (sp >= wb && (uint64_t)sp + len <= (uint64_t)wb + kDecWin + 16) ? S.cin + (sp - wb) : src + sp;
+                    group_copy(d, sl, len, glane);
+                    if (glane == 0) S.e_done[e] = (uint16_t)round;
                     continue;
                 }
-                const uint8_t *period = dst + (base - off);
-                uint8_t *d = dst + o;
-                for (uint32_t i = lane; i < len; i += 32) {
-                    uint32_t idx = rel + i;
-                    if (idx >= off) idx %= off;
-                    d[i] = period[idx];
+                const uint32_t off = S.e_src[e];
+                const uint32_t rel = o - base;  // position of this element inside its same-offset run
+                if (dn == 0) {
+                    // bytes this element reads: its own window of the output, or the run's base period
+                    uint32_t need_lo, need_hi;
+                    if (rel + len <= off) { need_lo = o - off; need_hi = need_lo + len; }
+                    else { need_lo = base - off; need_hi = base; }
+                    bool ready = true;
+                    if (need_hi > d0) {
+                        uint32_t x = need_lo > d0 ? need_lo : d0;
+                        uint32_t a = 0, b = e;  // last element with e_dst <= x; the producer is before e
+                        while (b - a > 1) {
+                            uint32_t m = (a + b) >> 1;
+                            if (S.e_dst[m] <= x) a = m; else b = m;
+                        }
+                        for (uint32_t f = a; f < e && S.e_dst[f] < need_hi; f++) {
+                            uint32_t df = S.e_done[f];
+                            if (df == 0 || df >= round) { ready = false; break; }
+                        }
+                    }
+                    if (!ready) { pending = 1; continue; }
                 }
-                __syncwarp();  // every lane has read e_done[e] above before it changes
-                if (lane == 0) S.e_done[e] = (uint16_t)round;
+                if (rel + len <= off) {
+                    group_copy(d, dst + (o - off), len, glane);
+                } else {
+                    const uint8_t *period = dst + (base - off);
+                    if (((off | rel | len) & 3) == 0 && (((uintptr_t)d | (uintptr_t)period) & 3) == 0) {
+                        const uint32_t *p32 = reinterpret_cast<const uint32_t *>(period);
+                        uint32_t *d32 = reinterpret_cast<uint32_t *>(d);
+                        const uint32_t pw = off >> 2, rw = rel >> 2;
+                        for (uint32_t k = glane; k < (len >> 2); k += 8) d32[k] = p32[(rw + k) % pw];
+                    } else {
+                        for (uint32_t i = glane; i < len; i += 8) d[i] = period[(rel + i) % off];
+                    }
+                }
+                if (glane == 0) S.e_done[e] = (uint16_t)round;
+            }
+            if (round == 1) {
+                // long literals: the whole CTA moves each one
+                const uint32_t nlong = S.n_long < (uint32_t)kMaxLong ? S.n_long : (uint32_t)kMaxLong;
+                for (uint32_t q = 0; q < nlong; q++) {
+                    const uint32_t e = S.long_list[q];
+                    cta_copy(dst + S.e_dst[e], src + S.e_src[e], S.e_len[e], t);
+                    if (t == 0) S.e_done[e] = 1;
+                }
+                if (S.n_long > (uint32_t)kMaxLong) {
+                    // overflow of the list (pathological): sweep the descriptors instead
+                    for (uint32_t e = 0; e < total_e; e++)
+                        if (S.e_base[e] == kLiteralMark && S.e_len[e] >= kLongLiteral && S.e_done[e] == 0) {
+                            cta_copy(dst + S.e_dst[e], src + S.e_src[e], S.e_len[e], t);
+                            __syncthreads();
+                            if (t == 0) S.e_done[e] = 1;
+                        }
+                }
             }
             if (!__syncthreads_or(pending)) break;
         }
+        PHASE_MARK(4);
 
         d0 += total_o;
         wb = next_wb;

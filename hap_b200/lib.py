@@ -69,6 +69,11 @@ class HapB200(HapABI):
         self.lib.HapB200StageTimes(ms, n, 8)
         return {s: (float(ms[i]), int(n[i])) for i, s in enumerate(self.STAGES)}
 
+    def decode_phase_cycles(self, reset=True):
+        out = (C.c_ulonglong * 8)()
+        self.lib.HapB200DebugDecodePhaseCycles(out, 8, 1 if reset else 0)
+        return dict(zip(("stage", "parse", "scan", "describe", "execute"), [int(v) for v in out[:5]]))
+
     def max_encoded_length_rgba(self, w, h, codec, chunks) -> int:
         return int(self.lib.HapB200MaxEncodedLengthRGBA(w, h, codec, chunks))
 

@@ -3,7 +3,8 @@
 One implementation on torch integer ops, so the same code produces the host frames the CPU oracle
 is fed in tests and the device-resident frame streams bench.py times.  Pinned by a CRC in
 tests/test_synth.py.  Kinds:
-  video  smooth triangle-wave gradients + small hash noise + letterbox bars (partly compressible)
+  video  smooth triangle-wave gradients, hash noise on a 64-px checkerboard of tiles, letterbox bars
+         (partly compressible: Snappy ratio ~0.6 on the Hap Q payload)
   flat   constant 0x336699FF (maximum compressibility, exercises the RLE paths)
   noise  hash bytes (incompressible, exercises both raw fallbacks of hap.c:460 and :478)
 """
@@ -52,6 +53,9 @@ def frame(width: int, height: int, index: int = 0, kind: str = "video", alpha: s
     py = (5 * y * k2 * 512) // height
     half = 1 << (noise_bits - 1) if noise_bits > 0 else 0
     nz = (h >> (32 - noise_bits)) - half if noise_bits > 0 else torch.zeros_like(h)
+    # camera-like grain only on every other 64x64 tile: the rest stays clean gradient (graphics-like), so the
+    # DXT payload is PARTLY compressible like real footage (Snappy ratio ~0.6) instead of all-or-nothing
+    nz = nz * (((x >> 6) + (y >> 6)) & 1)
     v = 43 + _tri8(px) // 3 + _tri8(py) // 3 + nz
     v = v.clamp(0, 255)
     bar = height // 10

@@ -100,6 +100,34 @@ static void check(const std::string &name, const std::vector<Tex> &tex, int mode
             if (memcmp(back.data(), tex[i].data.data(), used) != 0) { ok = false; why = std::string(which ? "reference" : "oracle") + " payload mismatch"; break; }
         }
     }
+    // and through our own decode kernel (K7), jobs built with the host-side parser of the product
+    for (unsigned i = 0; i < tex.size() && ok; i++) {
+        Located loc;
+        if (locate_texture(frame.data(), (uint32_t)frame.size(), i, loc) != 0) { ok = false; why = "locate"; break; }
+        const uint8_t *sec = frame.data() + loc.offset;
+        std::vector<ChunkJob> jobs;
+        std::vector<uint8_t> back(tex[i].data.size() + 64, 0x99);
+        if (((loc.type >> 4) & 0xF) == kHapComplex) {
+            ChunkTables t; t.count = 0;
+            if (parse_decode_instructions(sec, loc.len, t) != 0) { ok = false; why = "parse DI"; break; }
+            uint64_t in_run = 0, out_run = 0;
+            for (int c = 0; c < t.count; c++) {
+                uint32_t cc = sec[t.compressors + c], sz = rd_le32(sec + t.sizes + 4 * c), usz = sz;
+                if (cc == kHapChunkSnappy && !snappy_preamble(sec + t.data + in_run, sz, usz)) { ok = false; why = "preamble"; break; }
+                jobs.push_back(ChunkJob{sec + t.data + in_run, back.data() + 32 + out_run, sz, usz, cc, 99});
+                in_run += sz; out_run += usz;
+            }
+        } else {
+            jobs.push_back(ChunkJob{sec, back.data() + 32, loc.len, loc.len, kHapChunkRaw, 99});
+        }
+        if (!ok) break;
+        HAP_LAUNCH(snappy_decode_chunks_kernel, dim3((unsigned)jobs.size()), dim3(kDecThreads), sizeof(DecodeSmem), nullptr,
+                   jobs.data(), (int)jobs.size());
+        size_t total = 0;
+        for (auto &j : jobs) { if (j.status != 0) { ok = false; why = "K7 status " + std::to_string(j.status); } total += j.dst_bytes; }
+        if (ok && memcmp(back.data() + 32, tex[i].data.data(), total) != 0) { ok = false; why = "K7 payload mismatch"; }
+        for (int g = 0; g < 32 && ok; g++) if (back[g] != 0x99 || back[32 + total + g] != 0x99) { ok = false; why = "K7 wrote outside its chunk"; }
+    }
     if (!ok) { g_fail++; fprintf(stderr, "FAIL %s mode %d: %s (frame %zu bytes)\n", name.c_str(), mode, why.c_str(), frame.size()); }
 }
 
