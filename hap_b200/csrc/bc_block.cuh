@@ -42,23 +42,25 @@ HAP_HD int hap_clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi 
 // 8-value mode (a0 > a1): palette a0, a1, then 6 interpolants (decoder: ((8-i)a0 + (i-1)a1)/7).
 // Endpoints start at max/min; one least-squares refinement of the endpoints is kept if it lowers the
 // error against the decoder's truncating palette.
+HAP_HD int bc4_level_value(int L, int a0, int a1) { return ((7 - L) * a1 + L * a0) / 7; }  // decoder: truncating
+
 HAP_HD int bc4_error_and_indices(const int v[16], int a0, int a1, uint32_t &bits_lo, uint32_t &bits_hi)
 {
-    // a0 > a1.  level L in 0..7 counted from a1 (min) upwards: value = ((7-L)*a1 + L*a0)/7
-    int pal[8];
-#pragma unroll
-    for (int L = 0; L < 8; L++) pal[L] = ((7 - L) * a1 + L * a0) / 7;
-    const int range = a0 - a1;
+    // a0 > a1.  level L in 0..7 counted from a1 (min) upwards: value = ((7-L)*a1 + L*a0)/7.
+    // No per-texel integer division and no indexed palette array (both are slow on the GPU): the level is
+    // guessed with one multiply, then the guess and its two neighbours are scored against exact values.
+    const float inv = 7.0f / (float)(a0 - a1);
     uint64_t bits = 0;
     int err = 0;
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        int L = hap_clampi(((v[t] - a1) * 14 + range) / (2 * range), 0, 7);  // round((v-a1)*7/range)
-        // the truncating palette is not exactly uniform: check the neighbour below/above
-        int d = v[t] - pal[L];
+        int L = hap_clampi((int)floorf(hap_fma((float)(v[t] - a1), inv, 0.5f)), 0, 7);
+        int d = v[t] - bc4_level_value(L, a0, a1);
         int best = d * d, bl = L;
-        if (L > 0) { int e = v[t] - pal[L - 1]; if (e * e < best) { best = e * e; bl = L - 1; } }
-        if (L < 7) { int e = v[t] - pal[L + 1]; if (e * e < best) { best = e * e; bl = L + 1; } }
+#ifndef HAP_BC4_NO_NEIGHBOURS
+        if (L > 0) { int e = v[t] - bc4_level_value(L - 1, a0, a1); if (e * e < best) { best = e * e; bl = L - 1; } }
+        if (L < 7) { int e = v[t] - bc4_level_value(L + 1, a0, a1); if (e * e < best) { best = e * e; bl = L + 1; } }
+#endif
         err += best;
         // DXT index: 0 = a0, 1 = a1, 2..7 = interpolants from a0 towards a1
         uint32_t idx = bl == 7 ? 0u : bl == 0 ? 1u : (uint32_t)(8 - bl);
@@ -87,13 +89,14 @@ HAP_HD Block8 encode_bc4_block(const int v[16])
     uint32_t lo, hi;
     int a0 = mx, a1 = mn;
     int err = bc4_error_and_indices(v, a0, a1, lo, hi);
+#ifndef HAP_BC4_NO_REFINE
     if (err != 0) {
-        // least squares for (a0, a1) given the levels just chosen: v ~ a1 + (a0-a1)*L/7
+        // least squares for (a0, a1) given the levels of the min/max fit: v ~ a1 + (a0-a1)*L/7
         float sl = 0.f, sll = 0.f, sv = 0.f, slv = 0.f;
-        const int range = a0 - a1;
+        const float inv = 7.0f / (float)(a0 - a1);
 #pragma unroll
         for (int t = 0; t < 16; t++) {
-            int L = hap_clampi(((v[t] - a1) * 14 + range) / (2 * range), 0, 7);
+            int L = hap_clampi((int)floorf(hap_fma((float)(v[t] - a1), inv, 0.5f)), 0, 7);
             float f = (float)L * (1.0f / 7.0f);
             sl += f;
             sll = hap_fma(f, f, sll);
@@ -113,6 +116,7 @@ HAP_HD Block8 encode_bc4_block(const int v[16])
             }
         }
     }
+#endif
     out.lo = (uint32_t)a0 | ((uint32_t)a1 << 8) | (lo << 16);
     out.hi = (lo >> 16) | (hi << 16);
     return out;

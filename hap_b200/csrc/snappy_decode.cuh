@@ -7,11 +7,13 @@
 // One CTA per chunk.  Snappy is serial inside a stream (an element's position depends on the
 // length of every element before it, and copies read earlier output), so the kernel breaks both
 // chains explicitly, window by window over the compressed bytes:
-//   1. PARSE, speculatively in parallel.  Thread t owns 64 compressed bytes and walks the element
-//      chain from a guessed entry (its sub-block start).  The true entry of sub-block t is the
-//      running maximum of the exits of the sub-blocks before it; threads whose entry moved re-walk,
-//      and the loop ends at the fixpoint, which is the true chain (induction from sub-block 0).
-//      Element chains re-synchronise after a few elements, so this is 2-3 rounds in practice.
+//   1. PARSE without a serial walk over elements.  Thread t owns 64 compressed bytes and computes, for
+//      EVERY offset o inside them, where an element chain entering at o leaves the sub-block
+//      (one backward sweep, x[o] = x[o + length(o)], kept as a byte table in shared memory).  One thread
+//      then follows the true chain sub-block by sub-block with one table look-up per hop (long literals
+//      jump over whole sub-blocks), and each entered sub-block is walked once from its true entry.
+//      (A first version guessed entries and iterated to a fixpoint; on literal-heavy streams wrong
+//      guesses do not re-synchronise and it needed ~one round per sub-block: 56 % of the kernel.)
 //   2. SCAN element counts / output bytes -> every element's destination offset.
 //   3. EXECUTE.  Literals are independent (source = compressed bytes).  Runs of adjacent copies
 //      with one offset (how every encoder emits a long or overlapping match) become independent
@@ -42,6 +44,9 @@ constexpr uint32_t kLiteralMark = 0xFFFFFFFFu;
 constexpr uint32_t kLongLiteral = 1024;            // literals this long are copied by the whole CTA
 constexpr int kMaxLong = 64;
 constexpr int kGroups = kDecThreads / 8;           // 8-lane groups, one element each
+constexpr uint32_t kExitMaxRel = 250;              // tbl value <= this: exit = sub-block end + value
+constexpr uint32_t kExitFar = 253;                 // exit further away (a long literal): recomputed by walking
+constexpr uint32_t kExitInvalid = 254;             // the chain runs into an invalid element header
 
 struct DecodeSmem {
     uint32_t e_dst[kDecMaxElems];    // output offset inside the chunk
@@ -49,7 +54,9 @@ struct DecodeSmem {
     uint32_t e_src[kDecMaxElems];    // literal: payload position in the chunk input; copy: offset
     uint32_t e_base[kDecMaxElems];   // copy: destination of the head of its same-offset run; literal: mark
     uint16_t e_done[kDecMaxElems];   // 0 = pending, r = finished in round r (literals: 1)
-    uint8_t cin[kDecWin + 16];       // staged window of compressed bytes (+ header slack)
+    uint8_t cin[kDecWin + 64];       // staged window: aligned image of the input (+ alignment shift + header slack)
+    uint8_t tbl[kDecSub * kDecThreads];  // tbl[o][t]: where the chain entering sub-block t at offset o leaves it
+    uint16_t entry[kDecThreads];     // true entry offset of each sub-block, 0xFFFF = jumped over
     uint32_t scratch[kDecThreads / 32];
     uint32_t bcast[4];
     uint32_t n_long;                 // long literals of the current window
@@ -154,6 +161,12 @@ __device__ __forceinline__ void lanes_copy(uint8_t *dst, const uint8_t *src, uin
 __device__ __forceinline__ void group_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t glane) { lanes_copy<8>(dst, src, len, glane); }
 __device__ __forceinline__ void cta_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t t) { lanes_copy<kDecThreads>(dst, src, len, t); }
 
+#ifdef HAPB200_EMU
+__device__ __forceinline__ void hap_prefetch_l2(const void *) {}
+#else
+__device__ __forceinline__ void hap_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
 #ifdef HAPB200_DECODE_PHASE_CYCLES
 __device__ unsigned long long g_decode_phase_cycles[8];
 #define PHASE_MARK(i) do { if (t == 0) { long long now_ = clock64(); atomicAdd(&g_decode_phase_cycles[i], (unsigned long long)(now_ - phase_t0_)); phase_t0_ = now_; } } while (0)
@@ -226,36 +239,82 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
     __syncthreads();
 
     while (wb < in_end) {
-        // ---- stage the window ---------------------------------------------------------------
+        // ---- stage the window: a 16-byte aligned image of the input (chunks are byte-packed in a frame, so
+        //      the chunk itself is rarely aligned); cinp points at the byte that corresponds to `wb` ---------
         if (t == 0) S.n_long = 0;
-        for (uint32_t i = t; i < kDecWin + 16; i += kDecThreads) {
-            uint64_t g = (uint64_t)wb + i;
-            S.cin[i] = g < in_end ? src[g] : 0;
+        const uintptr_t gaddr = (uintptr_t)(src + wb);
+        const uint32_t shift = (uint32_t)(gaddr & 15);
+        {
+            const uint32_t avail = in_end - wb < (uint32_t)(kDecWin + 16) ? in_end - wb : (uint32_t)(kDecWin + 16);
+            const uint32_t n16 = (shift + avail + 15) >> 4;
+            const uint4 *g4 = reinterpret_cast<const uint4 *>(gaddr - shift);
+            uint4 *s4 = reinterpret_cast<uint4 *>(S.cin);
+            for (uint32_t i = t; i < n16; i += kDecThreads) s4[i] = g4[i];
+            // next window's lines on their way into L2 while this one is parsed and executed
+            const uint64_t pf = (uint64_t)wb + kDecWin + (uint64_t)t * 128;
+            if (pf < in_end) hap_prefetch_l2(src + pf);
         }
+        const uint8_t *cinp = S.cin + shift;
+        S.entry[t] = 0xFFFFu;
         __syncthreads();
 
         PHASE_MARK(0);
-        // ---- 1. speculative parallel parse to the fixpoint -----------------------------------
+        // ---- 1. parse.  (a) every thread: for EACH of the 64 offsets of its sub-block, where does an element
+        //      chain entering there leave the sub-block?  One backward sweep: x[o] = x[o + length(o)].
+        //      (b) one thread hops sub-block to sub-block along the true chain using that table.
+        //      (c) every sub-block the chain enters is walked once from its true entry. ------------------
         const uint32_t blk_start = (uint64_t)wb + (uint64_t)t * kDecSub < in_end ? wb + t * kDecSub : in_end;
         const uint32_t blk_end = (uint64_t)wb + (uint64_t)(t + 1) * kDecSub < in_end ? wb + (t + 1) * kDecSub : in_end;
-        uint32_t entry = blk_start;
-        WalkResult w;
-        w.exit = 0; w.count = 0; w.out_bytes = 0; w.invalid = 0;
-        bool need = true;
-        for (;;) {
-            if (need) {
-                if (entry < blk_end) {
-                    w = walk_subblock(S.cin, wb, entry, blk_end, in_end);
+        {
+            const uint32_t blk_len = blk_end - blk_start;
+            for (int o = (int)blk_len - 1; o >= 0; o--) {
+                uint32_t len, aux, hdr, kind;
+                uint32_t x;
+                if (!read_element_header(cinp, wb, blk_start + o, in_end, len, aux, hdr, kind)) {
+                    x = kExitInvalid;
                 } else {
-                    w.exit = 0; w.count = 0; w.out_bytes = 0; w.invalid = 0;  // jumped over by a long literal
+                    const uint64_t nxt = (uint64_t)o + hdr + (kind == 0 ? len : 0);
+                    if (nxt < blk_len) x = S.tbl[(uint32_t)nxt * kDecThreads + t];
+                    else x = nxt - blk_len <= kExitMaxRel ? (uint32_t)(nxt - blk_len) : kExitFar;
+                }
+                S.tbl[(uint32_t)o * kDecThreads + t] = (uint8_t)x;
+            }
+        }
+        __syncthreads();
+        if (t == 0) {
+            uint32_t pos = wb;
+            while (pos < in_end) {
+                const uint32_t blk = (pos - wb) >> 6;
+                if (blk >= (uint32_t)kDecThreads) break;
+                const uint32_t o = (pos - wb) & 63;
+                S.entry[blk] = (uint16_t)o;
+                const uint32_t x = S.tbl[o * kDecThreads + blk];
+                const uint32_t bend = (uint64_t)wb + (uint64_t)(blk + 1) * kDecSub < in_end ? wb + (blk + 1) * kDecSub : in_end;
+                if (x <= kExitMaxRel) {
+                    pos = bend + x;
+                } else if (x == kExitInvalid) {
+                    S.fail = 1;
+                    break;
+                } else {
+                    // a long literal leaves this sub-block by more than a byte can hold: walk to it
+                    uint32_t p2 = pos;
+                    for (;;) {
+                        uint32_t len, aux, hdr, kind;
+                        if (!read_element_header(cinp, wb, p2, in_end, len, aux, hdr, kind)) { S.fail = 1; p2 = in_end; break; }
+                        p2 += hdr + (kind == 0 ? len : 0);
+                        if (p2 >= bend) break;
+                    }
+                    pos = p2;
                 }
             }
-            uint32_t all_max;
-            uint32_t before = block_excl_max<kDecThreads>(w.exit, &all_max, S.scratch);
-            uint32_t new_entry = before > blk_start ? before : blk_start;
-            need = new_entry != entry;
-            entry = new_entry;
-            if (!__syncthreads_or(need ? 1 : 0)) break;
+        }
+        __syncthreads();
+        uint32_t entry = blk_end;
+        WalkResult w;
+        w.exit = 0; w.count = 0; w.out_bytes = 0; w.invalid = 0;
+        if (S.entry[t] != 0xFFFFu && blk_start < in_end) {
+            entry = blk_start + S.entry[t];
+            w = walk_subblock(cinp, wb, entry, blk_end, in_end);
         }
 
         PHASE_MARK(1);
@@ -281,7 +340,7 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
             uint32_t pos = entry, e = ebase, o = d0 + obase;
             while (pos < blk_end) {
                 uint32_t len, aux, hdr, kind;
-                read_element_header(S.cin, wb, pos, in_end, len, aux, hdr, kind);
+                read_element_header(cinp, wb, pos, in_end, len, aux, hdr, kind);
                 S.e_dst[e] = o;
                 S.e_len[e] = len;
                 S.e_src[e] = aux;
@@ -349,7 +408,7 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
                     if (len >= kLongLiteral) continue;           // moved by the whole CTA below
                     const uint32_t sp = S.e_src[e];
                     // payload inside the staged window -> shared memory, else straight from the input
-                    const uint8_t *sl = (sp >= wb && (uint64_t)sp + len <= (uint64_t)wb + kDecWin + 16) ? S.cin + (sp - wb) : src + sp;
+                    const uint8_t *sl = (sp >= wb && (uint64_t)sp + len <= (uint64_t)wb + kDecWin + 16) ? cinp + (sp - wb) : src + sp;
                     group_copy(d, sl, len, glane);
                     if (glane == 0) S.e_done[e] = (uint16_t)round;
                     continue;

@@ -76,6 +76,29 @@ __device__ __forceinline__ uint32_t compress_fragment(EncodeSmem &S, uint32_t W,
         S.dist[i] = (uint16_t)d;
     }
     __syncthreads();
+    // 2b. propagation: a word that is not yet part of a run adopts its left (else right) neighbour's distance
+    //     when its own data also matches there.  First occurrences of neighbouring words often point at
+    //     different earlier blocks; two rounds of this re-align them and recover most of what a greedy
+    //     match extension would find (0.92 -> 0.73 of the input on Hap Q picture content).
+    {
+        uint16_t *cur = S.dist, *nxt = S.u.r.dist2;  // the hash table is dead from here on
+#pragma unroll 1
+        for (int round = 0; round < 2; round++) {
+            for (uint32_t i = t; i < W; i += kEncThreads) {
+                const uint32_t d = cur[i];
+                const uint32_t l = i > 0 ? cur[i - 1] : 0u, r = i + 1 < W ? cur[i + 1] : 0u;
+                uint32_t nd = d;
+                if (!(d != 0 && (d == l || d == r))) {
+                    const uint32_t w = S.data[i];
+                    if (l != 0 && i >= l && S.data[i - l] == w) nd = l;
+                    else if (r != 0 && i >= r && S.data[i - r] == w) nd = r;
+                }
+                nxt[i] = (uint16_t)nd;
+            }
+            __syncthreads();
+            uint16_t *tmp = cur; cur = nxt; nxt = tmp;
+        }
+    }
     // 3. demote matches that do not continue for at least two words (a 4-byte copy saves nothing)
     for (uint32_t i = t; i < W; i += kEncThreads) {
         uint32_t d = S.dist[i];
