@@ -40,9 +40,11 @@ HAP_HD int hap_clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi 
 
 // ---- BC4 / RGTC1: 16 values -> 8 bytes ------------------------------------------------------------
 // 8-value mode (a0 > a1): palette a0, a1, then 6 interpolants (decoder: ((8-i)a0 + (i-1)a1)/7).
-// Endpoints start at max/min; one least-squares refinement of the endpoints is kept if it lowers the
-// error against the decoder's truncating palette.
-HAP_HD int bc4_level_value(int L, int a0, int a1) { return ((7 - L) * a1 + L * a0) / 7; }  // decoder: truncating
+// Endpoints are the block's max/min (a least-squares refinement of them was measured to change nothing);
+// each texel takes the nearest of the decoder's truncating palette values.
+// decoder palette, truncating: ((7-L)*a1 + L*a0)/7 = a1 + floor(L*(a0-a1)/7); L*(a0-a1) <= 1785, where
+// floor(q/7) == (q*9363)>>16 exactly (checked exhaustively)
+HAP_HD int bc4_level_value(int L, int a0, int a1) { return a1 + (int)(((uint32_t)(L * (a0 - a1)) * 9363u) >> 16); }
 
 HAP_HD int bc4_error_and_indices(const int v[16], int a0, int a1, uint32_t &bits_lo, uint32_t &bits_hi)
 {
@@ -57,10 +59,8 @@ HAP_HD int bc4_error_and_indices(const int v[16], int a0, int a1, uint32_t &bits
         int L = hap_clampi((int)floorf(hap_fma((float)(v[t] - a1), inv, 0.5f)), 0, 7);
         int d = v[t] - bc4_level_value(L, a0, a1);
         int best = d * d, bl = L;
-#ifndef HAP_BC4_NO_NEIGHBOURS
         if (L > 0) { int e = v[t] - bc4_level_value(L - 1, a0, a1); if (e * e < best) { best = e * e; bl = L - 1; } }
         if (L < 7) { int e = v[t] - bc4_level_value(L + 1, a0, a1); if (e * e < best) { best = e * e; bl = L + 1; } }
-#endif
         err += best;
         // DXT index: 0 = a0, 1 = a1, 2..7 = interpolants from a0 towards a1
         uint32_t idx = bl == 7 ? 0u : bl == 0 ? 1u : (uint32_t)(8 - bl);
@@ -89,34 +89,6 @@ HAP_HD Block8 encode_bc4_block(const int v[16])
     uint32_t lo, hi;
     int a0 = mx, a1 = mn;
     int err = bc4_error_and_indices(v, a0, a1, lo, hi);
-#ifndef HAP_BC4_NO_REFINE
-    if (err != 0) {
-        // least squares for (a0, a1) given the levels of the min/max fit: v ~ a1 + (a0-a1)*L/7
-        float sl = 0.f, sll = 0.f, sv = 0.f, slv = 0.f;
-        const float inv = 7.0f / (float)(a0 - a1);
-#pragma unroll
-        for (int t = 0; t < 16; t++) {
-            int L = hap_clampi((int)floorf(hap_fma((float)(v[t] - a1), inv, 0.5f)), 0, 7);
-            float f = (float)L * (1.0f / 7.0f);
-            sl += f;
-            sll = hap_fma(f, f, sll);
-            sv += (float)v[t];
-            slv = hap_fma(f, (float)v[t], slv);
-        }
-        float det = 16.0f * sll - sl * sl;
-        if (det > 1e-3f) {
-            float slope = (16.0f * slv - sl * sv) / det;
-            float base = (sv - slope * sl) * (1.0f / 16.0f);
-            int n1 = hap_clampi((int)floorf(base + 0.5f), 0, 255);
-            int n0 = hap_clampi((int)floorf(base + slope + 0.5f), 0, 255);
-            if (n0 > n1 && (n0 != a0 || n1 != a1)) {
-                uint32_t lo2, hi2;
-                int err2 = bc4_error_and_indices(v, n0, n1, lo2, hi2);
-                if (err2 < err) { a0 = n0; a1 = n1; lo = lo2; hi = hi2; }
-            }
-        }
-    }
-#endif
     out.lo = (uint32_t)a0 | ((uint32_t)a1 << 8) | (lo << 16);
     out.hi = (lo >> 16) | (hi << 16);
     return out;
@@ -335,7 +307,7 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
 // {4,2,1} with |co*scale|,|cg*scale| <= 127; stored texel (Co', Cg', (scale-1)*8, Y).
 // RGB error of a chroma error (dCo, dCg): (dCo-dCg)^2 + dCg^2 + (dCo+dCg)^2 = 2 dCo^2 + 3 dCg^2
 #ifndef HAP_YCOCG_FIT
-#define HAP_YCOCG_FIT 2, 0, true
+#define HAP_YCOCG_FIT 1, 0, true
 #endif
 constexpr float kYCoCgMetricCo = 1.41421356f, kYCoCgMetricCg = 1.73205081f;
 

@@ -15,10 +15,13 @@
 //      (A first version guessed entries and iterated to a fixpoint; on literal-heavy streams wrong
 //      guesses do not re-synchronise and it needed ~one round per sub-block: 56 % of the kernel.)
 //   2. SCAN element counts / output bytes -> every element's destination offset.
-//   3. EXECUTE.  Literals are independent (source = compressed bytes).  Runs of adjacent copies
+//   3. FLATTEN + EXECUTE.  Literals are independent (source = compressed bytes).  Runs of adjacent copies
 //      with one offset (how every encoder emits a long or overlapping match) become independent
-//      periodic fills of the run's base period.  Remaining copies go in dependency rounds: a copy
-//      runs once every element overlapping its source range finished in an earlier round.
+//      periodic fills of the run's base period.  DXT payloads are full of copy-of-copy chains ("same as
+//      the previous block except a few bytes"); a copy whose source lies inside one earlier element takes
+//      over that element's source (pointer jumping), which ends at input bytes or at earlier windows, so
+//      almost everything runs in the first round.  What is left goes in dependency rounds: a copy runs
+//      once every element overlapping its source range finished in an earlier round.
 // Every decision is taken on device; the host only reads one status word per chunk.
 #pragma once
 #include "block_primitives.cuh"
@@ -39,8 +42,9 @@ struct ChunkJob {
 constexpr int kDecThreads = 256;
 constexpr int kDecSub = 64;                        // compressed bytes owned by one thread per window
 constexpr int kDecWin = kDecThreads * kDecSub;     // 16 KiB of compressed input per window
-constexpr int kDecMaxElems = 3072;                 // descriptors held in shared memory per window
-constexpr uint32_t kLiteralMark = 0xFFFFFFFFu;
+constexpr int kDecMaxElems = 2048;                 // descriptors held in shared memory per window
+constexpr uint32_t kSrcIn = 0u << 30, kSrcOut = 1u << 30, kSrcRun = 2u << 30, kSrcMask = 3u << 30, kPosMask = (1u << 30) - 1;
+constexpr int kFlattenRounds = 2, kFlattenHops = 12;
 constexpr uint32_t kLongLiteral = 1024;            // literals this long are copied by the whole CTA
 constexpr int kMaxLong = 64;
 constexpr int kGroups = kDecThreads / 8;           // 8-lane groups, one element each
@@ -51,9 +55,9 @@ constexpr uint32_t kExitInvalid = 254;             // the chain runs into an inv
 struct DecodeSmem {
     uint32_t e_dst[kDecMaxElems];    // output offset inside the chunk
     uint32_t e_len[kDecMaxElems];
-    uint32_t e_src[kDecMaxElems];    // literal: payload position in the chunk input; copy: offset
-    uint32_t e_base[kDecMaxElems];   // copy: destination of the head of its same-offset run; literal: mark
-    uint16_t e_done[kDecMaxElems];   // 0 = pending, r = finished in round r (literals: 1)
+    uint32_t e_a[kDecMaxElems];      // packed source: kSrcIn|input position, kSrcOut|output position, kSrcRun|offset
+    uint32_t e_b[kDecMaxElems];      // destination of the head of the element's same-offset run (its own, if alone)
+    uint16_t e_done[kDecMaxElems];   // 0 = pending, r = finished in round r
     uint8_t cin[kDecWin + 64];       // staged window: aligned image of the input (+ alignment shift + header slack)
     uint8_t tbl[kDecSub * kDecThreads];  // tbl[o][t]: where the chain entering sub-block t at offset o leaves it
     uint16_t entry[kDecThreads];     // true entry offset of each sub-block, 0xFFFF = jumped over
@@ -210,8 +214,9 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
         if (t == 0) job.status = HapResult_No_Error;
         return;
     }
-    if (job.compressor != kHapChunkSnappy) {
-        if (t == 0) job.status = HapResult_Bad_Frame;  // hap.c:637-640
+    if (job.compressor != kHapChunkSnappy || in_end > kPosMask || expected > kPosMask) {
+        // hap.c:637-640; also chunks of 1 GiB and more, whose positions do not fit the packed descriptors
+        if (t == 0) job.status = HapResult_Bad_Frame;
         return;
     }
 
@@ -335,7 +340,10 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
         if (S.fail) break;
 
         PHASE_MARK(2);
-        // ---- descriptors ------------------------------------------------------------------------
+        // ---- descriptors.  e_a packs the SOURCE of an element as (kind << 30) | position:
+        //      kSrcIn  : bytes of the compressed input at `position` (literals, and copies flattened onto them)
+        //      kSrcOut : bytes of the output at `position` (plain copies; offset >= length)
+        //      kSrcRun : periodic fill with period `position` (= the offset) of the e_b[e] - offset .. e_b[e] bytes
         if (keep && entry < blk_end) {
             uint32_t pos = entry, e = ebase, o = d0 + obase;
             while (pos < blk_end) {
@@ -343,10 +351,10 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
                 read_element_header(cinp, wb, pos, in_end, len, aux, hdr, kind);
                 S.e_dst[e] = o;
                 S.e_len[e] = len;
-                S.e_src[e] = aux;
+                S.e_done[e] = 0;
                 if (kind == 0) {
-                    S.e_base[e] = kLiteralMark;
-                    S.e_done[e] = 0;
+                    S.e_a[e] = kSrcIn | aux;
+                    S.e_b[e] = 0;  // literals break same-offset runs (a copy's offset is never 0)
                     if (len >= kLongLiteral) {
                         uint32_t q = atomicAdd(&S.n_long, 1u);
                         if (q < (uint32_t)kMaxLong) S.long_list[q] = e;
@@ -354,8 +362,8 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
                     pos += hdr + len;
                 } else {
                     if (aux == 0 || aux > o) S.fail_desc = 1;  // offset 0 or before the start of the output
-                    S.e_base[e] = o;
-                    S.e_done[e] = 0;
+                    S.e_a[e] = aux >= len ? (kSrcOut | (o - aux)) : (kSrcRun | aux);
+                    S.e_b[e] = aux;  // the offset, for run detection below; becomes the run base afterwards
                     pos += hdr;
                 }
                 o += len;
@@ -365,36 +373,75 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
         __syncthreads();
         if (S.fail_desc) break;
 
-        // ---- same-offset runs: base of a continuation copy = destination of the run head ---------
+        // ---- same-offset runs: a copy with the offset of the copy right before it continues that copy's
+        //      match, so it is a periodic fill of the run head's base period, independent of its neighbours --
         {
             const uint32_t strip = (total_e + kDecThreads - 1) / kDecThreads;
             const uint32_t lo = t * strip < total_e ? t * strip : total_e;
             const uint32_t hi = lo + strip < total_e ? lo + strip : total_e;
-            // Pass 1: flag continuation copies (same offset as the copy right before them) in the
-            // spare top bit of e_len (copies are at most 64 long) and find the last run head of the strip.
-            uint32_t last_head = 0;  // index + 1; literals count as heads (they end every run)
+            // Pass 1: flag continuations in the spare top bit of e_len (copies are at most 64 long) and find
+            // the last run head of the strip.
+            uint32_t last_head = 0;  // index + 1
             for (uint32_t e = lo; e < hi; e++) {
-                bool cont = e > 0 && S.e_base[e] != kLiteralMark && S.e_base[e - 1] != kLiteralMark &&
-                            S.e_src[e] == S.e_src[e - 1];
+                const uint32_t off = S.e_b[e];
+                const bool cont = e > 0 && off != 0 && off == S.e_b[e - 1];
                 if (cont) S.e_len[e] |= 0x80000000u;
                 else last_head = e + 1;
             }
             uint32_t unused;
             uint32_t head = block_excl_max<kDecThreads>(last_head, &unused, S.scratch);  // ends with a barrier
-            // Pass 2: a continuation copy reads the base period of its run head.
+            // Pass 2: e_b becomes the base (destination of the run head); continuations become periodic fills.
             for (uint32_t e = lo; e < hi; e++) {
+                const uint32_t off = S.e_b[e];
                 if (S.e_len[e] & 0x80000000u) {
                     S.e_len[e] &= 0x7FFFFFFFu;
-                    S.e_base[e] = S.e_dst[head - 1];
+                    S.e_a[e] = kSrcRun | off;
+                    S.e_b[e] = S.e_dst[head - 1];
                 } else {
                     head = e + 1;
+                    S.e_b[e] = S.e_dst[e];
                 }
             }
         }
         __syncthreads();
 
+        // ---- flatten copy-of-copy chains.  DXT payloads are full of "same as the previous block except a few
+        //      bytes": a copy whose source is itself a copy, hundreds deep.  A plain copy whose source bytes lie
+        //      inside ONE earlier element of this window takes over that element's source (pointer jumping on
+        //      the packed e_a words; a racing update only makes the hop longer, never wrong).  Chains end at
+        //      literals (-> read the input instead) or at earlier windows (-> already written). --------------
+#pragma unroll 1
+        for (int fr = 0; fr < kFlattenRounds; fr++) {
+            for (uint32_t e = t; e < total_e; e += kDecThreads) {
+                uint32_t a = S.e_a[e];
+                if ((a & kSrcMask) != kSrcOut) continue;
+                const uint32_t len = S.e_len[e];
+                bool changed = false;
+#pragma unroll 1
+                for (int hop = 0; hop < kFlattenHops; hop++) {
+                    const uint32_t sp = a & kPosMask;
+                    if (sp + len <= d0) break;                 // reads finished output of earlier windows
+                    if (sp < d0) break;                        // straddles the window start: leave it
+                    uint32_t lo2 = 0, hi2 = e;                 // last element with e_dst <= sp (it is before e)
+                    while (hi2 - lo2 > 1) {
+                        const uint32_t m = (lo2 + hi2) >> 1;
+                        if (S.e_dst[m] <= sp) lo2 = m; else hi2 = m;
+                    }
+                    const uint32_t f = lo2, fd = S.e_dst[f];
+                    if (sp + len > fd + S.e_len[f]) break;     // spans several producers
+                    const uint32_t fa = S.e_a[f];
+                    if ((fa & kSrcMask) == kSrcRun) break;     // periodic producer: stay dependent on it
+                    a = (fa & kSrcMask) | ((fa & kPosMask) + (sp - fd));
+                    changed = true;
+                    if ((fa & kSrcMask) == kSrcIn) break;      // landed on input bytes: fully resolved
+                }
+                if (changed) S.e_a[e] = a;
+            }
+            __syncthreads();
+        }
+
         PHASE_MARK(3);
-        // ---- 3. execute: round 1 = literals and copies that only read earlier windows; later rounds =
+        // ---- 3. execute: round 1 = everything whose source is the input or earlier windows; later rounds =
         //         copies whose producers finished in an earlier round.  An element is owned by a group of
         //         8 lanes (4 bytes per lane per step), so a warp moves four elements at a time.
         for (uint32_t round = 1;; round++) {
@@ -402,42 +449,44 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
             for (uint32_t e = grp; e < total_e; e += kGroups) {
                 const uint32_t dn = S.e_done[e];
                 if (dn != 0 && dn != round) continue;          // finished in an earlier round
-                const uint32_t len = S.e_len[e], base = S.e_base[e], o = S.e_dst[e];
+                const uint32_t len = S.e_len[e], a = S.e_a[e], o = S.e_dst[e];
+                const uint32_t kind = a & kSrcMask, ap = a & kPosMask;
                 uint8_t *d = dst + o;
-                if (base == kLiteralMark) {
+                if (kind == kSrcIn) {
                     if (len >= kLongLiteral) continue;           // moved by the whole CTA below
-                    const uint32_t sp = S.e_src[e];
-                    // payload inside the staged window -> shared memory, else straight from the input
-                    const uint8_t *sl = (sp >= wb && (uint64_t)sp + len <= (uint64_t)wb + kDecWin + 16) ? cinp + (sp - wb) : src + sp;
+                    // bytes inside the staged window -> shared memory, else straight from the input
+                    const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= (uint64_t)wb + kDecWin + 16) ? cinp + (ap - wb) : src + ap;
                     group_copy(d, sl, len, glane);
                     if (glane == 0) S.e_done[e] = (uint16_t)round;
                     continue;
                 }
-                const uint32_t off = S.e_src[e];
+                const uint32_t base = S.e_b[e];
                 const uint32_t rel = o - base;  // position of this element inside its same-offset run
-                if (dn == 0) {
-                    // bytes this element reads: its own window of the output, or the run's base period
-                    uint32_t need_lo, need_hi;
-                    if (rel + len <= off) { need_lo = o - off; need_hi = need_lo + len; }
-                    else { need_lo = base - off; need_hi = base; }
+                // bytes this element reads
+                uint32_t need_lo, need_hi;
+                if (kind == kSrcOut) { need_lo = ap; need_hi = ap + len; }
+                else if (rel + len <= ap) { need_lo = o - ap; need_hi = need_lo + len; }
+                else { need_lo = base - ap; need_hi = base; }
+                if (dn == 0 && need_hi > d0) {
                     bool ready = true;
-                    if (need_hi > d0) {
-                        uint32_t x = need_lo > d0 ? need_lo : d0;
-                        uint32_t a = 0, b = e;  // last element with e_dst <= x; the producer is before e
-                        while (b - a > 1) {
-                            uint32_t m = (a + b) >> 1;
-                            if (S.e_dst[m] <= x) a = m; else b = m;
-                        }
-                        for (uint32_t f = a; f < e && S.e_dst[f] < need_hi; f++) {
-                            uint32_t df = S.e_done[f];
-                            if (df == 0 || df >= round) { ready = false; break; }
-                        }
+                    uint32_t x = need_lo > d0 ? need_lo : d0;
+                    uint32_t lo2 = 0, hi2 = e;  // last element with e_dst <= x; the producer is before e
+                    while (hi2 - lo2 > 1) {
+                        uint32_t m = (lo2 + hi2) >> 1;
+                        if (S.e_dst[m] <= x) lo2 = m; else hi2 = m;
+                    }
+                    for (uint32_t f = lo2; f < e && S.e_dst[f] < need_hi; f++) {
+                        uint32_t df = S.e_done[f];
+                        if (df == 0 || df >= round) { ready = false; break; }
                     }
                     if (!ready) { pending = 1; continue; }
                 }
-                if (rel + len <= off) {
-                    group_copy(d, dst + (o - off), len, glane);
+                if (kind == kSrcOut) {
+                    group_copy(d, dst + ap, len, glane);
+                } else if (rel + len <= ap) {
+                    group_copy(d, dst + (o - ap), len, glane);
                 } else {
+                    const uint32_t off = ap;
                     const uint8_t *period = dst + (base - off);
                     if (((off | rel | len) & 3) == 0 && (((uintptr_t)d | (uintptr_t)period) & 3) == 0) {
                         const uint32_t *p32 = reinterpret_cast<const uint32_t *>(period);
@@ -455,14 +504,14 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
                 const uint32_t nlong = S.n_long < (uint32_t)kMaxLong ? S.n_long : (uint32_t)kMaxLong;
                 for (uint32_t q = 0; q < nlong; q++) {
                     const uint32_t e = S.long_list[q];
-                    cta_copy(dst + S.e_dst[e], src + S.e_src[e], S.e_len[e], t);
+                    cta_copy(dst + S.e_dst[e], src + (S.e_a[e] & kPosMask), S.e_len[e], t);
                     if (t == 0) S.e_done[e] = 1;
                 }
                 if (S.n_long > (uint32_t)kMaxLong) {
                     // overflow of the list (pathological): sweep the descriptors instead
                     for (uint32_t e = 0; e < total_e; e++)
-                        if (S.e_base[e] == kLiteralMark && S.e_len[e] >= kLongLiteral && S.e_done[e] == 0) {
-                            cta_copy(dst + S.e_dst[e], src + S.e_src[e], S.e_len[e], t);
+                        if ((S.e_a[e] & kSrcMask) == kSrcIn && S.e_len[e] >= kLongLiteral && S.e_done[e] == 0) {
+                            cta_copy(dst + S.e_dst[e], src + (S.e_a[e] & kPosMask), S.e_len[e], t);
                             __syncthreads();
                             if (t == 0) S.e_done[e] = 1;
                         }
