@@ -6,8 +6,9 @@
 Workload (BASELINE.json `metric` "4K Hap-Q encode/decode GB/s per GPU", configs[2]): 3840x2160 RGBA8
 synthetic video frames -> Hap Q (scaled-YCoCg-DXT5, Snappy, 8 chunks) -> decoded back to the DXT
 texture bytes (what HapDecode returns).  One STEP = one pass of that round trip over a batch of
-`--frames` device-resident frames per GPU (default 32 = 1.06 GB of RGBA, far larger than the 126 MB
-L2, so nothing is served from cache between steps).  `value` = RGBA bytes pushed through the round
+`--frames` device-resident frames per GPU (default 55 = 1.8 GB of RGBA, far larger than the 126 MB
+L2, so nothing is served from cache between steps; 55 frames x 8 chunks = 440 decode CTAs = one full
+wave of 148 SMs x 3 resident CTAs).  `value` = RGBA bytes pushed through the round
 trip per second, all GPUs together (frames are independent: ranks take disjoint frames, no collective
 on the data path, weak scaling).
 Extra legs, outside the timed region: per-stage CUDA-event timing for the roofline object, the
@@ -60,7 +61,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -188,22 +189,57 @@ def run_gpu_arm(args, rank, local_rank, world):
     for i in range(F):
         rgba[i] = synth.frame(W, H, rank * F + i, device=dev)
     cap = (lib.max_encoded_length_rgba(W, H, codec, CHUNKS) + 15) // 16 * 16
-    frames_buf = torch.empty(F * cap, dtype=torch.uint8, device=dev)
-    used = torch.zeros(F, dtype=torch.int64, device=dev)
+    # two frame buffers: while the frames encoded in step i are being decoded (stream B), step i+1 already
+    # encodes into the other buffer (stream A).  Every step encodes one batch and decodes one batch; the
+    # decoded batch is the one the previous step encoded, i.e. a two-stage software pipeline over the stream.
+    frames_buf = [torch.empty(F * cap, dtype=torch.uint8, device=dev) for _ in range(2)]
+    used = [torch.zeros(F, dtype=torch.int64, device=dev) for _ in range(2)]
     tex = torch.empty(F * DXT_BYTES, dtype=torch.uint8, device=dev)
     tex_used = torch.zeros(F, dtype=torch.int64, device=dev)
     fmts = torch.zeros(F, dtype=torch.int32, device=dev)
     res = torch.zeros(F, dtype=torch.int32, device=dev)
-    stream = torch.cuda.Stream(device=dev)
-    sp = stream.cuda_stream
+    stream = torch.cuda.Stream(device=dev)     # A: encode (and everything, when --no-overlap)
+    stream_b = torch.cuda.Stream(device=dev)   # B: decode
+    sp, spb = stream.cuda_stream, stream_b.cuda_stream
+    overlap = not args.no_overlap
+    encoded = [torch.cuda.Event() for _ in range(2)]   # buffer k holds a freshly encoded batch
+    drained = [torch.cuda.Event() for _ in range(2)]   # buffer k has been decoded and may be overwritten
+    state = {"n": 0}
+
+    def encode_into(k, st):
+        r = lib.encode_rgba_batch(rgba.data_ptr(), F, RGBA_BYTES, W, H, codec, 1, CHUNKS, frames_buf[k].data_ptr(), cap,
+                                  used[k].data_ptr(), stream=st)
+        assert r == 0, r
+
+    def decode_from(k, st):
+        r = lib.decode_batch(frames_buf[k].data_ptr(), F, cap, used[k].data_ptr(), 0, CHUNKS, tex.data_ptr(), DXT_BYTES,
+                             tex_used.data_ptr(), fmts.data_ptr(), res.data_ptr(), stream=st)
+        assert r == 0, r
 
     def step():
-        r = lib.encode_rgba_batch(rgba.data_ptr(), F, RGBA_BYTES, W, H, codec, 1, CHUNKS, frames_buf.data_ptr(), cap,
-                                  used.data_ptr(), stream=sp)
-        assert r == 0, r
-        r = lib.decode_batch(frames_buf.data_ptr(), F, cap, used.data_ptr(), 0, CHUNKS, tex.data_ptr(), DXT_BYTES,
-                             tex_used.data_ptr(), fmts.data_ptr(), res.data_ptr(), stream=sp)
-        assert r == 0, r
+        n = state["n"]
+        k = n & 1
+        if not overlap:
+            encode_into(k, sp)
+            decode_from(k, sp)
+        else:
+            if n >= 2:
+                stream.wait_event(drained[k])          # the decode that read buffer k two steps ago is done
+            encode_into(k, sp)
+            encoded[k].record(stream)
+            if n >= 1:
+                stream_b.wait_event(encoded[k ^ 1])    # decode what the previous step encoded
+                decode_from(k ^ 1, spb)
+                drained[k ^ 1].record(stream_b)
+        state["n"] = n + 1
+
+    def drain():
+        # decode the batch the last step encoded (overlap mode leaves one in flight)
+        if overlap and state["n"] >= 1:
+            k = (state["n"] - 1) & 1
+            stream_b.wait_event(encoded[k])
+            decode_from(k, spb)
+        stream.wait_stream(stream_b)
 
     def barrier():
         if world > 1:
@@ -213,8 +249,10 @@ def run_gpu_arm(args, rank, local_rank, world):
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             step()
+        drain()
         barrier()
         assert res.tolist() == [0] * F and tex_used.tolist() == [DXT_BYTES] * F, "decode failed in warm-up"
+        state["n"] = 0
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
@@ -222,19 +260,23 @@ def run_gpu_arm(args, rank, local_rank, world):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        # K steps = K batches encoded AND K batches decoded: in overlap mode the first timed step has nothing of
+        # its own to decode yet, so the batch of the last step is decoded inside the timed region by drain()
         for _ in range(args.steps):
             step()
+        drain()
         e1.record(stream)
         barrier()
         launches = lib.launches() - launches0
         clocks = sampler.stop() if rank == 0 else None
+        assert res.tolist() == [0] * F and tex_used.tolist() == [DXT_BYTES] * F, "decode failed in the timed region"
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     ms_per_step = ms_total / args.steps
     value = world * F * RGBA_BYTES / (ms_per_step * 1e-3) / 1e9
-    mean_frame = float(used.double().mean().item())
+    mean_frame = float(used[0].double().mean().item())
 
     if rank != 0:
         if world > 1:
@@ -246,9 +288,11 @@ def run_gpu_arm(args, rank, local_rank, world):
     lib.set_stage_timing(True)
     lib.stage_times()
     lib.decode_phase_cycles(reset=True)
+    overlap_was, overlap = overlap, False   # stage timing needs the kernels one after another
     with torch.cuda.stream(stream):
         for _ in range(3):
             step()
+    overlap = overlap_was
     st = lib.stage_times()
     lib.set_stage_timing(False)
     ph = lib.decode_phase_cycles(reset=True)
@@ -339,7 +383,8 @@ def run_gpu_arm(args, rank, local_rank, world):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "l2": "inputs larger than L2 (%.2f GB RGBA per step per GPU)" % (F * RGBA_BYTES / 1e9),
-                   "compression_ratio": mean_frame / DXT_BYTES, "parallelism": f"frames sharded over {world} gpu(s), no collective"},
+                   "compression_ratio": mean_frame / DXT_BYTES, "parallelism": f"frames sharded over {world} gpu(s), no collective",
+                   "pipelining": "decode(batch i) on stream B overlaps encode(batch i+1) on stream A" if overlap else "none"},
         "fps": world * F / (ms_per_step * 1e-3),
         "encode_decode_split_ms": {"encode": per_step["bc_encode"] + per_step["snappy_encode"] + per_step["plan"] + per_step["place"],
                                    "decode": per_step["parse"] + per_step["snappy_decode"] + per_step["collect"]},
@@ -357,10 +402,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=32, help="device-resident frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=55, help="device-resident frames per GPU per step")
     ap.add_argument("--e2e-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: skip the e2e and CPU legs")
+    ap.add_argument("--no-overlap", action="store_true", help="encode and decode of a batch back to back on one stream")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

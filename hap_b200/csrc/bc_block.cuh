@@ -121,22 +121,25 @@ HAP_HD void snap_channel(float &a, float &b, float a2, float b2, float ab, float
 struct FitSums {
     float a2, b2, ab, axr, axg, axb, bxr, bxg, bxb;
 };
+template <bool HAS_B>
 HAP_HD bool cluster_sums(const float r[16], const float g[16], const float b[16], float ar, float ag, float ab_, float br,
                          float bg, float bb, FitSums &S)
 {
-    float dr = br - ar, dg = bg - ag, db = bb - ab_;
-    float dd = hap_fma(dr, dr, hap_fma(dg, dg, db * db));
+    float dr = br - ar, dg = bg - ag, db = HAS_B ? bb - ab_ : 0.0f;
+    float dd = HAS_B ? hap_fma(dr, dr, hap_fma(dg, dg, db * db)) : hap_fma(dr, dr, dg * dg);
     if (dd < 1e-6f) return false;
     float scale = 3.0f / dd;
     S.a2 = S.b2 = S.ab = S.axr = S.axg = S.axb = S.bxr = S.bxg = S.bxb = 0.f;
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        float s = hap_fma(r[t] - ar, dr, hap_fma(g[t] - ag, dg, (b[t] - ab_) * db)) * scale;
+        float s = (HAS_B ? hap_fma(r[t] - ar, dr, hap_fma(g[t] - ag, dg, (b[t] - ab_) * db))
+                         : hap_fma(r[t] - ar, dr, (g[t] - ag) * dg)) * scale;
         float q = fminf(fmaxf(floorf(s + 0.5f), 0.0f), 3.0f);
         float be = q * (1.0f / 3.0f), al = 1.0f - be;
         S.a2 = hap_fma(al, al, S.a2); S.b2 = hap_fma(be, be, S.b2); S.ab = hap_fma(al, be, S.ab);
-        S.axr = hap_fma(al, r[t], S.axr); S.axg = hap_fma(al, g[t], S.axg); S.axb = hap_fma(al, b[t], S.axb);
-        S.bxr = hap_fma(be, r[t], S.bxr); S.bxg = hap_fma(be, g[t], S.bxg); S.bxb = hap_fma(be, b[t], S.bxb);
+        S.axr = hap_fma(al, r[t], S.axr); S.axg = hap_fma(al, g[t], S.axg);
+        S.bxr = hap_fma(be, r[t], S.bxr); S.bxg = hap_fma(be, g[t], S.bxg);
+        if (HAS_B) { S.axb = hap_fma(al, b[t], S.axb); S.bxb = hap_fma(be, b[t], S.bxb); }
     }
     return S.a2 * S.b2 - S.ab * S.ab >= 1e-4f;
 }
@@ -146,7 +149,9 @@ HAP_HD bool cluster_sums(const float r[16], const float g[16], const float b[16]
 // r,g,b arrive PRE-MULTIPLIED by the metric (sr,sg,sb) so that plain Euclidean distance in that space
 // is the error to minimise (RGB: 1,1,1; scaled YCoCg: sqrt2, sqrt3 -- an error (dCo,dCg) costs
 // 2 dCo^2 + 3 dCg^2 in RGB); endpoints go back to storage units before they meet the 5:6:5 grid.
-template <int REFINE, int RESNAP, bool EXACT>
+// HAS_B = false: the third channel is constant over the block (scaled YCoCg carries its scale code there) and
+// drops out of every sum.
+template <int REFINE, int RESNAP, bool EXACT, bool HAS_B = true>
 HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const float b[16], int fixed_blue5 = -1,
                                   float sr = 1.0f, float sg = 1.0f, float sb = 1.0f)
 {
@@ -154,14 +159,17 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
     // mean and covariance
     float mr = 0.f, mg = 0.f, mb = 0.f;
 #pragma unroll
-    for (int t = 0; t < 16; t++) { mr += r[t]; mg += g[t]; mb += b[t]; }
-    mr *= 0.0625f; mg *= 0.0625f; mb *= 0.0625f;
+    for (int t = 0; t < 16; t++) { mr += r[t]; mg += g[t]; if (HAS_B) mb += b[t]; }
+    mr *= 0.0625f; mg *= 0.0625f; mb = HAS_B ? mb * 0.0625f : b[0];
     float crr = 0.f, crg = 0.f, crb = 0.f, cgg = 0.f, cgb = 0.f, cbb = 0.f;
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        float dr = r[t] - mr, dg = g[t] - mg, db = b[t] - mb;
-        crr = hap_fma(dr, dr, crr); crg = hap_fma(dr, dg, crg); crb = hap_fma(dr, db, crb);
-        cgg = hap_fma(dg, dg, cgg); cgb = hap_fma(dg, db, cgb); cbb = hap_fma(db, db, cbb);
+        float dr = r[t] - mr, dg = g[t] - mg;
+        crr = hap_fma(dr, dr, crr); crg = hap_fma(dr, dg, crg); cgg = hap_fma(dg, dg, cgg);
+        if (HAS_B) {
+            float db = b[t] - mb;
+            crb = hap_fma(dr, db, crb); cgb = hap_fma(dg, db, cgb); cbb = hap_fma(db, db, cbb);
+        }
     }
     float ar, ag, ab_, br, bg, bb;  // endpoints a (index 0 side) and b, in STORAGE units from here on
     const float var = crr + cgg + cbb;
@@ -180,20 +188,20 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
         else { vr = crb; vg = cgb; vb = cbb; }
 #pragma unroll
         for (int it = 0; it < 4; it++) {
-            float nr = hap_fma(crr, vr, hap_fma(crg, vg, crb * vb));
-            float ng = hap_fma(crg, vr, hap_fma(cgg, vg, cgb * vb));
-            float nb = hap_fma(crb, vr, hap_fma(cgb, vg, cbb * vb));
+            float nr = HAS_B ? hap_fma(crr, vr, hap_fma(crg, vg, crb * vb)) : hap_fma(crr, vr, crg * vg);
+            float ng = HAS_B ? hap_fma(crg, vr, hap_fma(cgg, vg, cgb * vb)) : hap_fma(crg, vr, cgg * vg);
+            float nb = HAS_B ? hap_fma(crb, vr, hap_fma(cgb, vg, cbb * vb)) : 0.0f;
             float m = fmaxf(fabsf(nr), fmaxf(fabsf(ng), fabsf(nb)));
             float inv = 1.0f / m;
             vr = nr * inv; vg = ng * inv; vb = nb * inv;
         }
         // extent along the axis -> first endpoints (metric space)
         float tmin = 1e30f, tmax = -1e30f;
-        const float vv = hap_fma(vr, vr, hap_fma(vg, vg, vb * vb));
+        const float vv = HAS_B ? hap_fma(vr, vr, hap_fma(vg, vg, vb * vb)) : hap_fma(vr, vr, vg * vg);
         const float ivv = 1.0f / vv;
 #pragma unroll
         for (int t = 0; t < 16; t++) {
-            float d = hap_fma(r[t] - mr, vr, hap_fma(g[t] - mg, vg, (b[t] - mb) * vb)) * ivv;
+            float d = (HAS_B ? hap_fma(r[t] - mr, vr, hap_fma(g[t] - mg, vg, (b[t] - mb) * vb)) : hap_fma(r[t] - mr, vr, (g[t] - mg) * vg)) * ivv;
             tmin = fminf(tmin, d);
             tmax = fmaxf(tmax, d);
         }
@@ -205,13 +213,13 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
 #pragma unroll 1
         for (int it = 0; it < REFINE; it++) {
             FitSums N;
-            if (!cluster_sums(r, g, b, mar, mag, mab, mbr, mbg, mbb, N)) break;
+            if (!cluster_sums<HAS_B>(r, g, b, mar, mag, mab, mbr, mbg, mbb, N)) break;
             S = N;
             have = true;
             float idet = 1.0f / (S.a2 * S.b2 - S.ab * S.ab);
             mar = (S.axr * S.b2 - S.bxr * S.ab) * idet; mbr = (S.bxr * S.a2 - S.axr * S.ab) * idet;
             mag = (S.axg * S.b2 - S.bxg * S.ab) * idet; mbg = (S.bxg * S.a2 - S.axg * S.ab) * idet;
-            mab = (S.axb * S.b2 - S.bxb * S.ab) * idet; mbb = (S.bxb * S.a2 - S.axb * S.ab) * idet;
+            if (HAS_B) { mab = (S.axb * S.b2 - S.bxb * S.ab) * idet; mbb = (S.bxb * S.a2 - S.axb * S.ab) * idet; }
         }
         ar = fminf(fmaxf(mar * isr, 0.f), 255.f); br = fminf(fmaxf(mbr * isr, 0.f), 255.f);
         ag = fminf(fmaxf(mag * isg, 0.f), 255.f); bg = fminf(fmaxf(mbg * isg, 0.f), 255.f);
@@ -222,12 +230,12 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
         if (have) {
             snap_channel(ar, br, S.a2, S.b2, S.ab, S.axr * isr, S.bxr * isr, 31.0f);
             snap_channel(ag, bg, S.a2, S.b2, S.ab, S.axg * isg, S.bxg * isg, 63.0f);
-            snap_channel(ab_, bb, S.a2, S.b2, S.ab, S.axb * isb, S.bxb * isb, 31.0f);
+            if (HAS_B) snap_channel(ab_, bb, S.a2, S.b2, S.ab, S.axb * isb, S.bxb * isb, 31.0f);
 #pragma unroll 1
             for (int it = 0; it < RESNAP; it++) {
                 // Lloyd on the quantised problem: re-cluster against the snapped segment, re-solve, re-snap
                 FitSums N;
-                if (!cluster_sums(r, g, b, ar * sr, ag * sg, ab_ * sb, br * sr, bg * sg, bb * sb, N)) break;
+                if (!cluster_sums<HAS_B>(r, g, b, ar * sr, ag * sg, ab_ * sb, br * sr, bg * sg, bb * sb, N)) break;
                 float idet = 1.0f / (N.a2 * N.b2 - N.ab * N.ab);
                 float car = fminf(fmaxf((N.axr * N.b2 - N.bxr * N.ab) * idet * isr, 0.f), 255.f);
                 float cbr = fminf(fmaxf((N.bxr * N.a2 - N.axr * N.ab) * idet * isr, 0.f), 255.f);
@@ -276,10 +284,14 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
         const float q2b = floorf((2.0f * e0b + e1b) * (1.0f / 3.0f) + 0.01f) * sb, q3b = floorf((e0b + 2.0f * e1b) * (1.0f / 3.0f) + 0.01f) * sb;
 #pragma unroll
         for (int t = 0; t < 16; t++) {
-            float d0 = hap_fma(r[t] - p0r, r[t] - p0r, hap_fma(g[t] - p0g, g[t] - p0g, (b[t] - p0b) * (b[t] - p0b)));
-            float d1 = hap_fma(r[t] - p1r, r[t] - p1r, hap_fma(g[t] - p1g, g[t] - p1g, (b[t] - p1b) * (b[t] - p1b)));
-            float d2 = hap_fma(r[t] - q2r, r[t] - q2r, hap_fma(g[t] - q2g, g[t] - q2g, (b[t] - q2b) * (b[t] - q2b)));
-            float d3 = hap_fma(r[t] - q3r, r[t] - q3r, hap_fma(g[t] - q3g, g[t] - q3g, (b[t] - q3b) * (b[t] - q3b)));
+            float d0 = hap_fma(r[t] - p0r, r[t] - p0r, (g[t] - p0g) * (g[t] - p0g));
+            float d1 = hap_fma(r[t] - p1r, r[t] - p1r, (g[t] - p1g) * (g[t] - p1g));
+            float d2 = hap_fma(r[t] - q2r, r[t] - q2r, (g[t] - q2g) * (g[t] - q2g));
+            float d3 = hap_fma(r[t] - q3r, r[t] - q3r, (g[t] - q3g) * (g[t] - q3g));
+            if (HAS_B) {
+                d0 = hap_fma(b[t] - p0b, b[t] - p0b, d0); d1 = hap_fma(b[t] - p1b, b[t] - p1b, d1);
+                d2 = hap_fma(b[t] - q2b, b[t] - q2b, d2); d3 = hap_fma(b[t] - q3b, b[t] - q3b, d3);
+            }
             uint32_t i01 = d1 < d0 ? 1u : 0u, i23 = d3 < d2 ? 3u : 2u;
             uint32_t idx = fminf(d2, d3) < fminf(d0, d1) ? i23 : i01;
             bits |= idx << (2 * t);
@@ -367,7 +379,7 @@ HAP_HD void encode_ycocg_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colo
     int y[16];
     const int code = ycocg_block(px, r, g, b, y);
     alpha = encode_bc4_block(y);
-    colour = encode_colour_block<HAP_YCOCG_FIT>(r, g, b, code, kYCoCgMetricCo, kYCoCgMetricCg, 1.0f);
+    colour = encode_colour_block<HAP_YCOCG_FIT, false>(r, g, b, code, kYCoCgMetricCo, kYCoCgMetricCg, 1.0f);
 }
 
 HAP_HD Block8 encode_rgtc1_alpha(const uint32_t px[16])

@@ -244,22 +244,34 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
     __syncthreads();
 
     while (wb < in_end) {
-        // ---- stage the window: a 16-byte aligned image of the input (chunks are byte-packed in a frame, so
-        //      the chunk itself is rarely aligned); cinp points at the byte that corresponds to `wb` ---------
+        // ---- stage the window.  Chunks are byte-packed in a frame, so the chunk is rarely aligned: read aligned
+        //      16-byte words and shift them so that S.cin[0] is the byte at `wb` (word loads stay aligned later) ---
         if (t == 0) S.n_long = 0;
-        const uintptr_t gaddr = (uintptr_t)(src + wb);
-        const uint32_t shift = (uint32_t)(gaddr & 15);
         {
+            const uintptr_t gaddr = (uintptr_t)(src + wb);
+            const uint32_t shift = (uint32_t)(gaddr & 15);           // uniform over the CTA
             const uint32_t avail = in_end - wb < (uint32_t)(kDecWin + 16) ? in_end - wb : (uint32_t)(kDecWin + 16);
-            const uint32_t n16 = (shift + avail + 15) >> 4;
+            const uint32_t n16 = (avail + 15) >> 4;
             const uint4 *g4 = reinterpret_cast<const uint4 *>(gaddr - shift);
             uint4 *s4 = reinterpret_cast<uint4 *>(S.cin);
-            for (uint32_t i = t; i < n16; i += kDecThreads) s4[i] = g4[i];
+            const uint32_t ws = shift >> 2, bs = (shift & 3) * 8;
+            for (uint32_t i = t; i < n16; i += kDecThreads) {
+                const uint4 a = g4[i];
+                uint4 b = make_uint4(0, 0, 0, 0);
+                if (shift != 0 && 16 * (i + 1) < shift + avail) b = g4[i + 1];  // never touch a word with no wanted byte
+                uint32_t w0, w1, w2, w3, w4;
+                if (ws == 0) { w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; }
+                else if (ws == 1) { w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; }
+                else if (ws == 2) { w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; }
+                else { w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; }
+                s4[i] = make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs),
+                                   __funnelshift_r(w3, w4, bs));
+            }
             // next window's lines on their way into L2 while this one is parsed and executed
             const uint64_t pf = (uint64_t)wb + kDecWin + (uint64_t)t * 128;
             if (pf < in_end) hap_prefetch_l2(src + pf);
         }
-        const uint8_t *cinp = S.cin + shift;
+        const uint8_t *cinp = S.cin;
         S.entry[t] = 0xFFFFu;
         __syncthreads();
 
@@ -270,50 +282,74 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
         //      (c) every sub-block the chain enters is walked once from its true entry. ------------------
         const uint32_t blk_start = (uint64_t)wb + (uint64_t)t * kDecSub < in_end ? wb + t * kDecSub : in_end;
         const uint32_t blk_end = (uint64_t)wb + (uint64_t)(t + 1) * kDecSub < in_end ? wb + (t + 1) * kDecSub : in_end;
-        {
+        if (blk_start < in_end) {
+            // the sub-block's 64 bytes (+ 4 bytes of header look-ahead) live in registers: the sweep is fully
+            // unrolled, so every tag byte is a compile-time extraction and only the table access touches memory
             const uint32_t blk_len = blk_end - blk_start;
-            for (int o = (int)blk_len - 1; o >= 0; o--) {
-                uint32_t len, aux, hdr, kind;
-                uint32_t x;
-                if (!read_element_header(cinp, wb, blk_start + o, in_end, len, aux, hdr, kind)) {
-                    x = kExitInvalid;
+            const uint32_t limit = in_end - blk_start;  // a chain position may not pass this
+            uint32_t w[18];
+            const uint32_t *c32 = reinterpret_cast<const uint32_t *>(S.cin + (size_t)t * kDecSub);
+#pragma unroll
+            for (int k = 0; k < 18; k++) w[k] = c32[k];
+#pragma unroll
+            for (int o = kDecSub - 1; o >= 0; o--) {
+                const uint32_t tag = (w[o >> 2] >> (8 * (o & 3))) & 0xFFu;
+                const uint32_t kind = tag & 3u;
+                uint64_t nxt;
+                if (kind != 0) {
+                    nxt = (uint32_t)o + ((0x5320u >> (4 * kind)) & 0xFu);  // copy headers: 2, 3 or 5 bytes
                 } else {
-                    const uint64_t nxt = (uint64_t)o + hdr + (kind == 0 ? len : 0);
-                    if (nxt < blk_len) x = S.tbl[(uint32_t)nxt * kDecThreads + t];
-                    else x = nxt - blk_len <= kExitMaxRel ? (uint32_t)(nxt - blk_len) : kExitFar;
+                    const uint32_t m = tag >> 2;
+                    if (m < 60) {
+                        nxt = (uint32_t)o + m + 2;                           // tag + (m+1) literal bytes
+                    } else {
+                        const uint32_t extra = m - 59;
+                        // the 4 bytes after the tag, assembled from registers
+                        const uint32_t lo_w = w[(o + 1) >> 2], hi_w = w[((o + 1) >> 2) + 1];
+                        const uint32_t v = __funnelshift_r(lo_w, hi_w, 8 * ((o + 1) & 3));
+                        const uint32_t mm = extra == 4 ? v : (v & ((1u << (8 * extra)) - 1u));
+                        nxt = mm == 0xFFFFFFFFu ? ~0ull : (uint64_t)o + 1 + extra + (uint64_t)mm + 1;
+                    }
                 }
+                uint32_t x;
+                if (nxt > limit) x = kExitInvalid;               // header or payload runs past the input
+                else if (nxt < blk_len) x = S.tbl[(uint32_t)nxt * kDecThreads + t];
+                else x = nxt - blk_len <= kExitMaxRel ? (uint32_t)(nxt - blk_len) : kExitFar;
                 S.tbl[(uint32_t)o * kDecThreads + t] = (uint8_t)x;
             }
         }
         __syncthreads();
+        PHASE_MARK(5);
         if (t == 0) {
-            uint32_t pos = wb;
-            while (pos < in_end) {
-                const uint32_t blk = (pos - wb) >> 6;
-                if (blk >= (uint32_t)kDecThreads) break;
-                const uint32_t o = (pos - wb) & 63;
-                S.entry[blk] = (uint16_t)o;
+            // window-relative positions: the dependent chain per hop is one table load plus a few ALU ops
+            const uint32_t rel_end = in_end - wb;
+            uint32_t rel = 0;
+            while (rel < rel_end && rel < (uint32_t)kDecWin) {
+                const uint32_t blk = rel >> 6, o = rel & 63;
                 const uint32_t x = S.tbl[o * kDecThreads + blk];
-                const uint32_t bend = (uint64_t)wb + (uint64_t)(blk + 1) * kDecSub < in_end ? wb + (blk + 1) * kDecSub : in_end;
+                S.entry[blk] = (uint16_t)o;
+                uint32_t bend = (blk + 1) << 6;
+                bend = bend < rel_end ? bend : rel_end;
                 if (x <= kExitMaxRel) {
-                    pos = bend + x;
+                    rel = bend + x;
                 } else if (x == kExitInvalid) {
                     S.fail = 1;
                     break;
                 } else {
                     // a long literal leaves this sub-block by more than a byte can hold: walk to it
-                    uint32_t p2 = pos;
+                    uint32_t p2 = wb + rel;
                     for (;;) {
                         uint32_t len, aux, hdr, kind;
                         if (!read_element_header(cinp, wb, p2, in_end, len, aux, hdr, kind)) { S.fail = 1; p2 = in_end; break; }
                         p2 += hdr + (kind == 0 ? len : 0);
-                        if (p2 >= bend) break;
+                        if (p2 - wb >= bend) break;
                     }
-                    pos = p2;
+                    rel = p2 - wb;
                 }
             }
         }
         __syncthreads();
+        PHASE_MARK(6);
         uint32_t entry = blk_end;
         WalkResult w;
         w.exit = 0; w.count = 0; w.out_bytes = 0; w.invalid = 0;
@@ -405,6 +441,7 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
         }
         __syncthreads();
 
+        PHASE_MARK(3);
         // ---- flatten copy-of-copy chains.  DXT payloads are full of "same as the previous block except a few
         //      bytes": a copy whose source is itself a copy, hundreds deep.  A plain copy whose source bytes lie
         //      inside ONE earlier element of this window takes over that element's source (pointer jumping on
@@ -440,7 +477,7 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
             __syncthreads();
         }
 
-        PHASE_MARK(3);
+        PHASE_MARK(7);
         // ---- 3. execute: round 1 = everything whose source is the input or earlier windows; later rounds =
         //         copies whose producers finished in an earlier round.  An element is owned by a group of
         //         8 lanes (4 bytes per lane per step), so a warp moves four elements at a time.

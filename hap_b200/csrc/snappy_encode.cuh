@@ -29,18 +29,20 @@ constexpr int kFragCap = kFragBytes + 32;   // element stream of a fragment neve
 constexpr int kEncHashBits = 13;
 constexpr uint32_t kFragStoredRaw = 0xFFFFFFFFu;  // fragment size marker: chunk must be stored raw
 
+// Shared memory of one fragment.  Thread t owns the 8 consecutive words [8t, 8t+8) and keeps them (and every
+// per-word quantity) in registers; shared memory only carries what OTHER threads read: the data (random
+// match verification), the hash table, and the strip-boundary values of the per-word arrays.
 struct EncodeSmem {
-    uint32_t data[kFragWords];
+    uint32_t data[kFragWords + 8];                  // input words; reused as the output byte stream at the end
     union {
-        uint32_t table[1 << kEncHashBits];          // steps 1-2
+        uint32_t table[1 << kEncHashBits];          // first occurrence of every hashed word
         struct {
-            uint16_t dist2[kFragWords];             // step 3+: distance in words after demotion, 0 = literal
-            uint16_t runend[kFragWords];            // indexed by run start: last word of the run
-        } r;
+            uint16_t a[kFragWords];                 // ping
+            uint16_t b[kFragWords];                 // pong
+        } h;
     } u;
-    uint16_t dist[kFragWords];                      // step 2: raw candidate; step 4+: run start of each word
-    uint16_t pos[kFragWords];                       // output offset of each word's contribution
-    uint8_t out[kFragCap];
+    uint16_t da[kFragWords];                        // candidate distances (ping)
+    uint16_t db[kFragWords];                        // candidate distances (pong); later: run end, stored at the run start
     uint32_t warp_tot[kEncWarps];
     uint32_t total;
 };
@@ -49,170 +51,221 @@ __device__ __forceinline__ uint32_t enc_hash(uint32_t w) { return (w * 0x9E3779B
 
 __device__ __forceinline__ uint32_t literal_header_bytes(uint32_t len) { return len <= 60 ? 1u : len <= 256 ? 2u : 3u; }
 
-// One fragment: `n` input bytes at `in` (n % 8 == 0, n <= kFragBytes) -> element stream in S.out,
-// returns its size (all threads).  period_words = DXT block size in words (2 or 4).
-__device__ __forceinline__ uint32_t compress_fragment(EncodeSmem &S, uint32_t W, uint32_t period_words)
-{
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    constexpr int kPerWarp = kFragWords / kEncWarps;  // 256 words per warp, 8 lane-strided iterations
-    constexpr int kIters = kPerWarp / 32;
+constexpr int kStrip = kFragWords / kEncThreads;  // 8 words per thread
+static_assert(kStrip == 8, "the strip code below moves 8 uint16 values per thread as one 16-byte access");
 
-    for (int i = t; i < (1 << kEncHashBits); i += kEncThreads) S.u.table[i] = 0xFFFFFFFFu;
+__device__ __forceinline__ void store_strip16(uint16_t *arr, uint32_t base, const uint32_t v[8])
+{
+    *reinterpret_cast<uint4 *>(arr + base) =
+        make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+}
+
+// Inclusive max / sum over the block of one value per thread; returns the exclusive prefix for this thread and
+// the block total.  Two barriers.
+__device__ __forceinline__ uint32_t enc_block_excl(uint32_t v, bool is_max, uint32_t *total, uint32_t *warp_tot)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(HAP_FULL_MASK, incl, d);
+        if (lane >= d) incl = is_max ? (incl > o ? incl : o) : incl + o;
+    }
+    uint32_t prev = __shfl_up_sync(HAP_FULL_MASK, incl, 1);
+    if (lane == 0) prev = 0;
+    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    // 1. first occurrence of every word
-    for (uint32_t i = t; i < W; i += kEncThreads) atomicMin(&S.u.table[enc_hash(S.data[i])], i);
-    __syncthreads();
-    // 2. candidate distance per word
-    for (uint32_t i = t; i < W; i += kEncThreads) {
-        uint32_t w = S.data[i];
-        uint32_t c = S.u.table[enc_hash(w)];
-        uint32_t d = (c < i && S.data[c] == w) ? i - c : 0;
-        uint32_t b0 = i - (i % period_words);
-        if (b0 >= period_words && b0 + period_words <= W) {
-            bool rep = true;
-            for (uint32_t k = 0; k < period_words; k++) rep = rep && (S.data[b0 + k] == S.data[b0 + k - period_words]);
-            if (rep) d = period_words;
-        }
-        S.dist[i] = (uint16_t)d;
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kEncWarps; w++) {
+        uint32_t x = warp_tot[w];
+        if (w < warp) base = is_max ? (base > x ? base : x) : base + x;
+        tot = is_max ? (tot > x ? tot : x) : tot + x;
     }
     __syncthreads();
-    // 2b. propagation: a word that is not yet part of a run adopts its left (else right) neighbour's distance
-    //     when its own data also matches there.  First occurrences of neighbouring words often point at
-    //     different earlier blocks; two rounds of this re-align them and recover most of what a greedy
-    //     match extension would find (0.92 -> 0.73 of the input on Hap Q picture content).
+    *total = tot;
+    return is_max ? (base > prev ? base : prev) : base + prev;
+}
+
+// One fragment: W words already in S.data AND in the caller's registers d[8] (words 8t..8t+7; W % 2 == 0,
+// W <= kFragWords) -> element stream written over S.data as bytes; returns its size (all threads).
+// period_words = DXT block size in words (2 or 4).
+__device__ __forceinline__ uint32_t compress_fragment(EncodeSmem &S, const uint32_t d[8], uint32_t W, uint32_t period_words)
+{
+    const uint32_t t = threadIdx.x;
+    const uint32_t i0 = t * kStrip;                  // first word of my strip
+    const uint32_t nv = i0 >= W ? 0u : (W - i0 < (uint32_t)kStrip ? W - i0 : (uint32_t)kStrip);  // my valid words
+
+    // 1. first occurrence of every word (the table was initialised by the caller, before the barrier)
+#pragma unroll
+    for (int k = 0; k < kStrip; k++)
+        if ((uint32_t)k < nv) atomicMin(&S.u.table[enc_hash(d[k])], i0 + k);
+    __syncthreads();
+
+    // 2. candidate distance per word: first earlier occurrence, or one block back when the whole block repeats
+    uint32_t dd[8];
+#pragma unroll
+    for (int k = 0; k < kStrip; k++) {
+        dd[k] = 0;
+        if ((uint32_t)k < nv) {
+            const uint32_t c = S.u.table[enc_hash(d[k])];
+            if (c < i0 + k && S.data[c] == d[k]) dd[k] = i0 + k - c;
+        }
+    }
+    if (period_words == 4) {
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const uint32_t w0 = i0 + 4 * b;
+            if (w0 >= 4 && w0 + 4 <= W) {
+                bool rep;
+                if (b == 0) rep = S.data[w0 - 4] == d[0] && S.data[w0 - 3] == d[1] && S.data[w0 - 2] == d[2] && S.data[w0 - 1] == d[3];
+                else rep = d[0] == d[4] && d[1] == d[5] && d[2] == d[6] && d[3] == d[7];
+                if (rep) { dd[4 * b] = dd[4 * b + 1] = dd[4 * b + 2] = dd[4 * b + 3] = 4; }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t w0 = i0 + 2 * b;
+            if (w0 >= 2 && w0 + 2 <= W) {
+                bool rep;
+                if (b == 0) rep = S.data[w0 - 2] == d[0] && S.data[w0 - 1] == d[1];
+                else rep = d[2 * b - 2] == d[2 * b] && d[2 * b - 1] == d[2 * b + 1];
+                if (rep) { dd[2 * b] = dd[2 * b + 1] = 2; }
+            }
+        }
+    }
+    store_strip16(S.da, i0, dd);
+    __syncthreads();
+
+    // 2b. propagation (two rounds): a word that is not yet part of a run adopts its left (else right) neighbour's
+    //     distance when its own data also matches there.  First occurrences of neighbouring words often point at
+    //     different earlier blocks; this re-aligns them and recovers most of what a greedy match extension finds.
     {
-        uint16_t *cur = S.dist, *nxt = S.u.r.dist2;  // the hash table is dead from here on
+        uint16_t *cur = S.da, *nxt = S.db;
 #pragma unroll 1
         for (int round = 0; round < 2; round++) {
-            for (uint32_t i = t; i < W; i += kEncThreads) {
-                const uint32_t d = cur[i];
-                const uint32_t l = i > 0 ? cur[i - 1] : 0u, r = i + 1 < W ? cur[i + 1] : 0u;
-                uint32_t nd = d;
-                if (!(d != 0 && (d == l || d == r))) {
-                    const uint32_t w = S.data[i];
-                    if (l != 0 && i >= l && S.data[i - l] == w) nd = l;
-                    else if (r != 0 && i >= r && S.data[i - r] == w) nd = r;
+            const uint32_t lb = i0 > 0 ? cur[i0 - 1] : 0u;
+            const uint32_t rb = i0 + kStrip < W ? cur[i0 + kStrip] : 0u;
+            uint32_t nd[8];
+#pragma unroll
+            for (int k = 0; k < kStrip; k++) {
+                const uint32_t l = k > 0 ? dd[k - 1] : lb, r = k < kStrip - 1 ? dd[k + 1] : rb;
+                const uint32_t cd = dd[k], i = i0 + k;
+                nd[k] = cd;
+                if ((uint32_t)k < nv && !(cd != 0 && (cd == l || cd == r))) {
+                    if (l != 0 && i >= l && S.data[i - l] == d[k]) nd[k] = l;
+                    else if (r != 0 && i >= r && S.data[i - r] == d[k]) nd[k] = r;
                 }
-                nxt[i] = (uint16_t)nd;
             }
+#pragma unroll
+            for (int k = 0; k < kStrip; k++) dd[k] = nd[k];
+            store_strip16(nxt, i0, dd);
             __syncthreads();
             uint16_t *tmp = cur; cur = nxt; nxt = tmp;
         }
+        // two rounds: the current values are back in S.da
     }
+
     // 3. demote matches that do not continue for at least two words (a 4-byte copy saves nothing)
-    for (uint32_t i = t; i < W; i += kEncThreads) {
-        uint32_t d = S.dist[i];
-        bool keep = d != 0 && ((i > 0 && S.dist[i - 1] == d) || (i + 1 < W && S.dist[i + 1] == d));
-        S.u.r.dist2[i] = keep ? (uint16_t)d : 0;
-    }
-    __syncthreads();
-    // 4. run start of every word: inclusive max-scan of (i+1 where a run starts)
+    uint32_t d2[8];
     {
-        uint32_t carry = 0;
-        const uint32_t wbase = warp * kPerWarp;
-#pragma unroll 1
-        for (int k = 0; k < kIters; k++) {
-            uint32_t i = wbase + k * 32 + lane;
-            uint32_t v = 0;
-            if (i < W && (i == 0 || S.u.r.dist2[i] != S.u.r.dist2[i - 1])) v = i + 1;
+        const uint32_t lb = i0 > 0 ? S.da[i0 - 1] : 0u;
+        const uint32_t rb = i0 + kStrip < W ? S.da[i0 + kStrip] : 0u;
 #pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                uint32_t o = __shfl_up_sync(HAP_FULL_MASK, v, dlt);
-                if (lane >= dlt) v = v > o ? v : o;
-            }
-            v = v > carry ? v : carry;
-            if (i < W) S.dist[i] = (uint16_t)v;  // 0 = no start seen inside this warp's span yet
-            carry = __shfl_sync(HAP_FULL_MASK, v, 31);
+        for (int k = 0; k < kStrip; k++) {
+            const uint32_t l = k > 0 ? dd[k - 1] : lb, r = k < kStrip - 1 ? dd[k + 1] : rb;
+            const bool has_l = i0 + k > 0, has_r = i0 + k + 1 < W;
+            d2[k] = ((uint32_t)k < nv && dd[k] != 0 && ((has_l && l == dd[k]) || (has_r && r == dd[k]))) ? dd[k] : 0u;
         }
-        if (lane == 0) S.warp_tot[warp] = carry;
-        __syncthreads();
-        uint32_t base = 0;
-        for (int w2 = 0; w2 < warp; w2++) base = base > S.warp_tot[w2] ? base : S.warp_tot[w2];
-#pragma unroll 1
-        for (int k = 0; k < kIters; k++) {
-            uint32_t i = wbase + k * 32 + lane;
-            if (i < W) {
-                uint32_t v = S.dist[i];
-                S.dist[i] = (uint16_t)((v ? v : base) - 1);
-            }
+    }
+    store_strip16(S.u.h.a, i0, d2);   // the hash table is dead: its space holds the demoted distances
+    __syncthreads();
+
+    // 4. run start of every word (max-scan of "i+1 where a run starts") and run ends (stored at the run start)
+    uint32_t rs[8];
+    {
+        const uint32_t lb = i0 > 0 ? S.u.h.a[i0 - 1] : 0u;
+        uint32_t last = 0;  // (index + 1) of the last run start inside my strip so far
+        uint32_t loc[8];
+#pragma unroll
+        for (int k = 0; k < kStrip; k++) {
+            const uint32_t prev = k > 0 ? d2[k - 1] : lb;
+            if ((uint32_t)k < nv && (i0 + k == 0 || d2[k] != prev)) last = i0 + k + 1;
+            loc[k] = last;
+        }
+        uint32_t unused;
+        const uint32_t carry = enc_block_excl(last, true, &unused, S.warp_tot);
+#pragma unroll
+        for (int k = 0; k < kStrip; k++) rs[k] = (loc[k] ? loc[k] : carry) - 1;
+        const uint32_t rb = i0 + kStrip < W ? S.u.h.a[i0 + kStrip] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < kStrip; k++) {
+            const uint32_t nxt = k < kStrip - 1 ? d2[k + 1] : rb;
+            if ((uint32_t)k < nv && (i0 + k + 1 == W || nxt != d2[k])) S.db[rs[k]] = (uint16_t)(i0 + k);
         }
     }
     __syncthreads();
-    // run ends, stored at the run's start index
-    for (uint32_t i = t; i < W; i += kEncThreads)
-        if (i + 1 == W || S.u.r.dist2[i + 1] != S.u.r.dist2[i]) S.u.r.runend[S.dist[i]] = (uint16_t)i;
-    __syncthreads();
-    // 5. bytes each word contributes, exclusive sum-scan -> S.pos
+
+    // 5. bytes each word contributes and their exclusive prefix sum
+    uint32_t pos[8];
     {
-        uint32_t carry = 0;
-        const uint32_t wbase = warp * kPerWarp;
-#pragma unroll 1
-        for (int k = 0; k < kIters; k++) {
-            uint32_t i = wbase + k * 32 + lane;
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < kStrip; k++) {
             uint32_t c = 0;
-            if (i < W) {
-                uint32_t rs = S.dist[i];
-                if (S.u.r.dist2[i] == 0) {
+            if ((uint32_t)k < nv) {
+                const uint32_t i = i0 + k;
+                if (d2[k] == 0) {
                     c = 4;
-                    if (i == rs) c += literal_header_bytes(4u * (S.u.r.runend[rs] - rs + 1));
-                } else if (((i - rs) & 15) == 0) {
+                    if (i == rs[k]) c += literal_header_bytes(4u * (S.db[i] - i + 1));
+                } else if (((i - rs[k]) & 15) == 0) {
                     c = 3;
                 }
             }
-            uint32_t v = c;
+            pos[k] = run;
+            run += c;
+        }
+        uint32_t tot;
+        const uint32_t base = enc_block_excl(run, false, &tot, S.warp_tot);  // ends with a barrier: S.data is free now
 #pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                uint32_t o = __shfl_up_sync(HAP_FULL_MASK, v, dlt);
-                if (lane >= dlt) v += o;
-            }
-            if (i < W) S.pos[i] = (uint16_t)(carry + v - c);
-            carry += __shfl_sync(HAP_FULL_MASK, v, 31);
-        }
-        if (lane == 0) S.warp_tot[warp] = carry;
-        __syncthreads();
-        uint32_t base = 0, tot = 0;
-        for (int w2 = 0; w2 < kEncWarps; w2++) {
-            uint32_t s = S.warp_tot[w2];
-            if (w2 < warp) base += s;
-            tot += s;
-        }
-#pragma unroll 1
-        for (int k = 0; k < kIters; k++) {
-            uint32_t i = wbase + k * 32 + lane;
-            if (i < W) S.pos[i] = (uint16_t)(S.pos[i] + base);
-        }
+        for (int k = 0; k < kStrip; k++) pos[k] += base;
         if (t == 0) S.total = tot;
     }
-    __syncthreads();
-    // 6. every word writes its own bytes
-    for (uint32_t i = t; i < W; i += kEncThreads) {
-        uint32_t rs = S.dist[i], d = S.u.r.dist2[i], p = S.pos[i];
-        if (d == 0) {
-            if (i == rs) {
-                uint32_t len = 4u * (S.u.r.runend[rs] - rs + 1);
+
+    // 6. every word writes its own bytes; the stream overwrites S.data (every thread holds its words in registers)
+    uint8_t *out = reinterpret_cast<uint8_t *>(S.data);
+#pragma unroll
+    for (int k = 0; k < kStrip; k++) {
+        if ((uint32_t)k >= nv) continue;
+        const uint32_t i = i0 + k;
+        uint32_t p = pos[k];
+        if (d2[k] == 0) {
+            if (i == rs[k]) {
+                const uint32_t len = 4u * (S.db[i] - i + 1);
                 if (len <= 60) {
-                    S.out[p++] = (uint8_t)((len - 1) << 2);
+                    out[p++] = (uint8_t)((len - 1) << 2);
                 } else if (len <= 256) {
-                    S.out[p++] = (uint8_t)(60 << 2);
-                    S.out[p++] = (uint8_t)(len - 1);
+                    out[p++] = (uint8_t)(60 << 2);
+                    out[p++] = (uint8_t)(len - 1);
                 } else {
-                    S.out[p++] = (uint8_t)(61 << 2);
-                    S.out[p++] = (uint8_t)(len - 1);
-                    S.out[p++] = (uint8_t)((len - 1) >> 8);
+                    out[p++] = (uint8_t)(61 << 2);
+                    out[p++] = (uint8_t)(len - 1);
+                    out[p++] = (uint8_t)((len - 1) >> 8);
                 }
             }
-            uint32_t w = S.data[i];
-            S.out[p] = (uint8_t)w;
-            S.out[p + 1] = (uint8_t)(w >> 8);
-            S.out[p + 2] = (uint8_t)(w >> 16);
-            S.out[p + 3] = (uint8_t)(w >> 24);
-        } else if (((i - rs) & 15) == 0) {
-            uint32_t left = S.u.r.runend[rs] - i + 1;       // words left in the run
-            uint32_t len = 4u * (left < 16 ? left : 16);    // 4..64 bytes
-            uint32_t off = 4u * d;
-            S.out[p] = (uint8_t)(2u | ((len - 1) << 2));     // copy with 2-byte offset
-            S.out[p + 1] = (uint8_t)off;
-            S.out[p + 2] = (uint8_t)(off >> 8);
+            const uint32_t w = d[k];
+            out[p] = (uint8_t)w;
+            out[p + 1] = (uint8_t)(w >> 8);
+            out[p + 2] = (uint8_t)(w >> 16);
+            out[p + 3] = (uint8_t)(w >> 24);
+        } else if (((i - rs[k]) & 15) == 0) {
+            const uint32_t left = S.db[rs[k]] - i + 1;        // words left in the run
+            const uint32_t len = 4u * (left < 16 ? left : 16);  // 4..64 bytes
+            const uint32_t off = 4u * d2[k];
+            out[p] = (uint8_t)(2u | ((len - 1) << 2));          // copy with 2-byte offset
+            out[p + 1] = (uint8_t)off;
+            out[p + 2] = (uint8_t)(off >> 8);
         }
     }
     __syncthreads();
@@ -267,17 +320,31 @@ __global__ void __launch_bounds__(kEncThreads) snappy_encode_fragments_kernel(
     const uint32_t n = left < (uint32_t)kFragBytes ? left : (uint32_t)kFragBytes;
     const uint32_t W = n >> 2;
     const uint8_t *in = dxt + in_off;
-    if ((((uintptr_t)in) & 3) == 0) {
-        const uint32_t *in32 = reinterpret_cast<const uint32_t *>(in);
-        for (uint32_t i = t; i < W; i += kEncThreads) S.data[i] = in32[i];
+    uint32_t d[8];
+    const uint32_t i0 = (uint32_t)t * kStrip;
+    if ((((uintptr_t)in) & 15) == 0 && i0 + kStrip <= W) {
+        const uint4 *in4 = reinterpret_cast<const uint4 *>(in) + 2 * t;
+        const uint4 a = in4[0], b = in4[1];
+        d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
     } else {
-        for (uint32_t i = t; i < W; i += kEncThreads)
-            S.data[i] = in[4 * i] | (in[4 * i + 1] << 8) | (in[4 * i + 2] << 16) | ((uint32_t)in[4 * i + 3] << 24);
+#pragma unroll
+        for (int k = 0; k < kStrip; k++) {
+            const uint32_t i = i0 + k;
+            d[k] = 0;
+            if (i < W) d[k] = in[4 * i] | (in[4 * i + 1] << 8) | (in[4 * i + 2] << 16) | ((uint32_t)in[4 * i + 3] << 24);
+        }
+    }
+    *reinterpret_cast<uint4 *>(&S.data[i0]) = make_uint4(d[0], d[1], d[2], d[3]);
+    *reinterpret_cast<uint4 *>(&S.data[i0 + 4]) = make_uint4(d[4], d[5], d[6], d[7]);
+    {
+        uint4 *tb = reinterpret_cast<uint4 *>(S.u.table);
+        const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        for (int q = t; q < (1 << kEncHashBits) / 4; q += kEncThreads) tb[q] = ones;
     }
     __syncthreads();
-    const uint32_t total = compress_fragment(S, W, sec.period_words);
+    const uint32_t total = compress_fragment(S, d, W, sec.period_words);
     uint8_t *o = scratch + (uint64_t)gfrag * kFragCap;
-    const uint32_t *o32s = reinterpret_cast<const uint32_t *>(S.out);
+    const uint32_t *o32s = reinterpret_cast<const uint32_t *>(S.data);
     uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
     for (uint32_t i = t; i < (total + 3) / 4; i += kEncThreads) o32[i] = o32s[i];
     if (t == 0) frag_size[gfrag] = total;

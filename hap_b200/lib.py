@@ -72,7 +72,9 @@ class HapB200(HapABI):
     def decode_phase_cycles(self, reset=True):
         out = (C.c_ulonglong * 8)()
         self.lib.HapB200DebugDecodePhaseCycles(out, 8, 1 if reset else 0)
-        return dict(zip(("stage", "parse", "scan", "describe", "execute"), [int(v) for v in out[:5]]))
+        # kernel marks: 0 stage, 5 exit tables, 6 chain hop, 1 walk, 2 scans, 3 descriptors+runs, 7 flatten, 4 execute
+        names = {0: "stage", 5: "exit_tables", 6: "chain_hop", 1: "walk", 2: "scan", 3: "describe", 7: "flatten", 4: "execute"}
+        return {names[i]: int(out[i]) for i in (0, 5, 6, 1, 2, 3, 7, 4)}
 
     def max_encoded_length_rgba(self, w, h, codec, chunks) -> int:
         return int(self.lib.HapB200MaxEncodedLengthRGBA(w, h, codec, chunks))
