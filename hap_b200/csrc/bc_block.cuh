@@ -327,10 +327,14 @@ constexpr float kYCoCgMetricCo = 1.41421356f, kYCoCgMetricCg = 1.73205081f;
 HAP_HD int ycocg_block(const uint32_t px[16], float cr[16], float cg_[16], float cb[16], int yv[16])
 {
     int m2 = 0, m4 = 0;
+    int co2v[16], cg4v[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) {
         int R = px[t] & 0xFF, G = (px[t] >> 8) & 0xFF, B = (px[t] >> 16) & 0xFF;
         int co2 = R - B, cg4 = -R + 2 * G - B;
+        co2v[t] = co2;
+        cg4v[t] = cg4;
+        yv[t] = (R + 2 * G + B + 2) >> 2;
         int a2 = co2 < 0 ? -co2 : co2, a4 = cg4 < 0 ? -cg4 : cg4;
         m2 = a2 > m2 ? a2 : m2;
         m4 = a4 > m4 ? a4 : m4;
@@ -341,21 +345,70 @@ HAP_HD int ycocg_block(const uint32_t px[16], float cr[16], float cg_[16], float
     const float sb = (float)((scale - 1) << 3);
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        int R = px[t] & 0xFF, G = (px[t] >> 8) & 0xFF, B = (px[t] >> 16) & 0xFF;
         // round half up of co2*scale/2 and cg4*scale/4 (arithmetic shift floors)
-        int co = ((R - B) * scale + 1) >> 1;
-        int cg = ((-R + 2 * G - B) * scale + 2) >> 2;
+        int co = (co2v[t] * scale + 1) >> 1;
+        int cg = (cg4v[t] * scale + 2) >> 2;
         cr[t] = (float)hap_clampi(co + 128, 0, 255) * kYCoCgMetricCo;
         cg_[t] = (float)hap_clampi(cg + 128, 0, 255) * kYCoCgMetricCg;
         cb[t] = sb;
-        yv[t] = (R + 2 * G + B + 2) >> 2;
     }
     return scale - 1;  // 5-bit blue code 0, 1 or 3: expands to B' = 0, 8, 24
 }
 
+// A block whose 16 texels are one colour (letterbox bars, graphics, clipped highlights -- common in real
+// footage): no statistics needed.  Endpoints bracket the colour on the 5:6:5 grid, the single index is the
+// nearest of the four decoder palette entries under the metric (wr,wg,wb = squared channel weights).
+HAP_HD Block8 encode_flat_colour(int R, int G, int B, int fixed_blue5, float wr, float wg, float wb)
+{
+    uint32_t a5r = (uint32_t)(R * 31) / 255u, a6g = (uint32_t)(G * 63) / 255u, a5b = (uint32_t)(B * 31) / 255u;
+    uint32_t b5r = a5r + (expand5(a5r) != (uint32_t)R && a5r < 31 ? 1u : 0u);
+    uint32_t b6g = a6g + (expand6(a6g) != (uint32_t)G && a6g < 63 ? 1u : 0u);
+    uint32_t b5b = a5b + (expand5(a5b) != (uint32_t)B && a5b < 31 ? 1u : 0u);
+    if (fixed_blue5 >= 0) a5b = b5b = (uint32_t)fixed_blue5;
+    // c0 > c1 required for 4-colour mode: the "ceil" triple is the larger 565 word unless they are equal
+    const uint32_t c0 = (b5r << 11) | (b6g << 5) | b5b, c1 = (a5r << 11) | (a6g << 5) | a5b;
+    Block8 out;
+    out.lo = c0 | (c1 << 16);
+    out.hi = 0;
+    if (c0 == c1) return out;
+    if (c0 < c1) {
+        // cannot happen (each field of c0 is >= the field of c1), kept for safety: index 0 still decodes to c0
+        return out;
+    }
+    const int p0[3] = {(int)expand5(b5r), (int)expand6(b6g), (int)expand5(b5b)};
+    const int p1[3] = {(int)expand5(a5r), (int)expand6(a6g), (int)expand5(a5b)};
+    const int px3[3] = {R, G, B};
+    const float wv[3] = {wr, wg, wb};
+    float best = 1e30f;
+    uint32_t bi = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+        float e = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            int v = k == 0 ? p0[c] : k == 1 ? p1[c] : k == 2 ? (2 * p0[c] + p1[c]) / 3 : (p0[c] + 2 * p1[c]) / 3;
+            float dlt = (float)(px3[c] - v);
+            e = hap_fma(dlt * wv[c], dlt, e);
+        }
+        if (e < best) { best = e; bi = k; }
+    }
+    out.hi = bi * 0x55555555u;
+    return out;
+}
+
 // ---- whole-block encoders: px = 16 RGBA8 texels, row-major inside the block, little-endian ------
+HAP_HD bool block_is_flat_rgb(const uint32_t px[16])
+{
+    uint32_t diff = 0;
+#pragma unroll
+    for (int t = 1; t < 16; t++) diff |= px[t] ^ px[0];
+    return (diff & 0x00FFFFFFu) == 0;
+}
+
 HAP_HD Block8 encode_dxt1(const uint32_t px[16])
 {
+    if (block_is_flat_rgb(px))
+        return encode_flat_colour((int)(px[0] & 0xFF), (int)((px[0] >> 8) & 0xFF), (int)((px[0] >> 16) & 0xFF), -1, 1.f, 1.f, 1.f);
     float r[16], g[16], b[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) {
@@ -375,6 +428,18 @@ HAP_HD void encode_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colour)
 
 HAP_HD void encode_ycocg_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colour)
 {
+    if (block_is_flat_rgb(px)) {
+        const int R = (int)(px[0] & 0xFF), G = (int)((px[0] >> 8) & 0xFF), B = (int)((px[0] >> 16) & 0xFF);
+        const int co2 = R - B, cg4 = -R + 2 * G - B;
+        const int a2 = co2 < 0 ? -co2 : co2, a4 = cg4 < 0 ? -cg4 : cg4;
+        const int scale = (a2 * 4 <= 254 && a4 * 4 <= 508) ? 4 : (a2 * 2 <= 254 && a4 * 2 <= 508) ? 2 : 1;
+        const int co = hap_clampi(((co2 * scale + 1) >> 1) + 128, 0, 255), cg = hap_clampi(((cg4 * scale + 2) >> 2) + 128, 0, 255);
+        const uint32_t Y = (uint32_t)((R + 2 * G + B + 2) >> 2);
+        alpha.lo = Y | (Y << 8);
+        alpha.hi = 0;
+        colour = encode_flat_colour(co, cg, (scale - 1) << 3, scale - 1, 2.0f, 3.0f, 1.0f);
+        return;
+    }
     float r[16], g[16], b[16];
     int y[16];
     const int code = ycocg_block(px, r, g, b, y);
