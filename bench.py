@@ -176,6 +176,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     from hap_b200 import synth
     from hap_b200.lib import HapB200Codec_HapY
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -324,7 +325,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes[dominant], "ms_per_launch": dom_ms,
-                "stage_ms_per_step": per_step, "decode_phase_share": decode_phase_share}
+                "stage_ms_per_step": per_step, "decode_phase_share": decode_phase_share, "decode_counts": getattr(lib, "last_decode_counts", None)}
     if args.profile:
         print(json.dumps({"profile_only": True, "ms_per_step": ms_per_step, "value": value, "roofline": roofline}))
         return

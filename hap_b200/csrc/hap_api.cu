@@ -269,9 +269,12 @@ int HapB200DebugDecodePhaseCycles(unsigned long long *out, int n, int reset)
     unsigned long long h[8] = {0};
     if (cudaMemcpyFromSymbol(h, g_decode_phase_cycles, sizeof h) != cudaSuccess) { cudaGetLastError(); return -1; }
     for (int i = 0; i < n && i < 8; i++) out[i] = h[i];
+    if (n >= 16 && cudaMemcpyFromSymbol(h, g_decode_counts, sizeof h) == cudaSuccess)
+        for (int i = 0; i < 8; i++) out[8 + i] = h[i];
     if (reset) {
         unsigned long long z[8] = {0};
         cudaMemcpyToSymbol(g_decode_phase_cycles, z, sizeof z);
+        cudaMemcpyToSymbol(g_decode_counts, z, sizeof z);
     }
     return 8;
 }

@@ -162,6 +162,44 @@ __device__ __forceinline__ void lanes_copy(uint8_t *dst, const uint8_t *src, uin
     const uint32_t done = head + (nw << 2);
     for (uint32_t i = done + lane; i < len; i += N_LANES) dst[i] = src[i];
 }
+// Up to kSmallElem (64) bytes by one thread.  Word path: every load is issued before the first store, so the
+// loads overlap instead of each waiting behind the store before it (the compiler must assume they alias).
+constexpr uint32_t kSmallElem = 64;
+__device__ __forceinline__ void small_copy(uint8_t *d, const uint8_t *s, uint32_t len)
+{
+    if ((((uintptr_t)d | (uintptr_t)s | len) & 3) == 0) {
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s);
+        uint32_t *d32 = reinterpret_cast<uint32_t *>(d);
+        const uint32_t nw = len >> 2;
+        uint32_t v[kSmallElem / 4];
+#pragma unroll
+        for (uint32_t k = 0; k < kSmallElem / 4; k++)
+            if (k < nw) v[k] = s32[k];
+#pragma unroll
+        for (uint32_t k = 0; k < kSmallElem / 4; k++)
+            if (k < nw) d32[k] = v[k];
+    } else if ((((uintptr_t)d | len) & 3) == 0) {
+        // destination aligned, source not: each word from two aligned source words
+        const uint32_t mis = (uint32_t)((uintptr_t)s & 3);
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s - mis);
+        uint32_t *d32 = reinterpret_cast<uint32_t *>(d);
+        const uint32_t nw = len >> 2;
+        uint32_t v[kSmallElem / 4 + 1];
+#pragma unroll
+        for (uint32_t k = 0; k < kSmallElem / 4; k++)
+            if (k < nw) v[k] = s32[k];
+        // the last source word may hold only bytes before the element's end: assemble it bytewise
+        uint32_t last = 0;
+        for (uint32_t q = 0; q < mis; q++) last |= (uint32_t)s[len - mis + q] << (8 * q);
+        v[kSmallElem / 4] = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < kSmallElem / 4; k++)
+            if (k < nw) d32[k] = __funnelshift_r(v[k], k + 1 < nw ? v[k + 1] : last, 8 * mis);
+    } else {
+        for (uint32_t i = 0; i < len; i++) d[i] = s[i];
+    }
+}
+
 __device__ __forceinline__ void group_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t glane) { lanes_copy<8>(dst, src, len, glane); }
 __device__ __forceinline__ void cta_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t t) { lanes_copy<kDecThreads>(dst, src, len, t); }
 
@@ -173,11 +211,14 @@ __device__ __forceinline__ void hap_prefetch_l2(const void *p) { asm volatile("p
 
 #ifdef HAPB200_DECODE_PHASE_CYCLES
 __device__ unsigned long long g_decode_phase_cycles[8];
+__device__ unsigned long long g_decode_counts[8];  // windows, elements, execute rounds, pending-after-round-1, flatten changes
+#define COUNT_ADD(i, v) do { if (t == 0) atomicAdd(&g_decode_counts[i], (unsigned long long)(v)); } while (0)
 #define PHASE_MARK(i) do { if (t == 0) { long long now_ = clock64(); atomicAdd(&g_decode_phase_cycles[i], (unsigned long long)(now_ - phase_t0_)); phase_t0_ = now_; } } while (0)
 #define PHASE_INIT long long phase_t0_ = clock64()
 #else
 #define PHASE_MARK(i) do { } while (0)
 #define PHASE_INIT do { } while (0)
+#define COUNT_ADD(i, v) do { } while (0)
 #endif
 
 __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(ChunkJob *jobs, int njobs)
@@ -185,7 +226,7 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
     HAP_DYN_SMEM(smem_raw);
     DecodeSmem &S = *reinterpret_cast<DecodeSmem *>(smem_raw);
     const int t = threadIdx.x;
-    const uint32_t grp = t >> 3, glane = t & 7;
+    const uint32_t wrp = t >> 5;
     if ((int)blockIdx.x >= njobs) return;
     PHASE_INIT;
     ChunkJob &job = jobs[blockIdx.x];
@@ -479,32 +520,31 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
 
         PHASE_MARK(7);
         // ---- 3. execute: round 1 = everything whose source is the input or earlier windows; later rounds =
-        //         copies whose producers finished in an earlier round.  An element is owned by a group of
-        //         8 lanes (4 bytes per lane per step), so a warp moves four elements at a time.
+        //         copies whose producers finished in an earlier round.  Elements of at most 64 bytes (every copy,
+        //         most literals) are moved by ONE THREAD each, staged through registers so that all its loads are
+        //         in flight together; longer literals by a warp each; the longest by the whole CTA.
         for (uint32_t round = 1;; round++) {
             int pending = 0;
-            for (uint32_t e = grp; e < total_e; e += kGroups) {
-                const uint32_t dn = S.e_done[e];
-                if (dn != 0 && dn != round) continue;          // finished in an earlier round
-                const uint32_t len = S.e_len[e], a = S.e_a[e], o = S.e_dst[e];
+            for (uint32_t e = t; e < total_e; e += kDecThreads) {
+                if (S.e_done[e] != 0) continue;
+                const uint32_t len = S.e_len[e];
+                if (len > kSmallElem) continue;
+                const uint32_t a = S.e_a[e], o = S.e_dst[e];
                 const uint32_t kind = a & kSrcMask, ap = a & kPosMask;
                 uint8_t *d = dst + o;
                 if (kind == kSrcIn) {
-                    if (len >= kLongLiteral) continue;           // moved by the whole CTA below
-                    // bytes inside the staged window -> shared memory, else straight from the input
                     const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= (uint64_t)wb + kDecWin + 16) ? cinp + (ap - wb) : src + ap;
-                    group_copy(d, sl, len, glane);
-                    if (glane == 0) S.e_done[e] = (uint16_t)round;
+                    small_copy(d, sl, len);
+                    S.e_done[e] = (uint16_t)round;
                     continue;
                 }
                 const uint32_t base = S.e_b[e];
                 const uint32_t rel = o - base;  // position of this element inside its same-offset run
-                // bytes this element reads
-                uint32_t need_lo, need_hi;
+                uint32_t need_lo, need_hi;      // bytes this element reads
                 if (kind == kSrcOut) { need_lo = ap; need_hi = ap + len; }
                 else if (rel + len <= ap) { need_lo = o - ap; need_hi = need_lo + len; }
                 else { need_lo = base - ap; need_hi = base; }
-                if (dn == 0 && need_hi > d0) {
+                if (need_hi > d0) {
                     bool ready = true;
                     uint32_t x = need_lo > d0 ? need_lo : d0;
                     uint32_t lo2 = 0, hi2 = e;  // last element with e_dst <= x; the producer is before e
@@ -519,22 +559,41 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
                     if (!ready) { pending = 1; continue; }
                 }
                 if (kind == kSrcOut) {
-                    group_copy(d, dst + ap, len, glane);
+                    small_copy(d, dst + ap, len);
                 } else if (rel + len <= ap) {
-                    group_copy(d, dst + (o - ap), len, glane);
+                    small_copy(d, dst + (o - ap), len);
                 } else {
                     const uint32_t off = ap;
                     const uint8_t *period = dst + (base - off);
                     if (((off | rel | len) & 3) == 0 && (((uintptr_t)d | (uintptr_t)period) & 3) == 0) {
                         const uint32_t *p32 = reinterpret_cast<const uint32_t *>(period);
                         uint32_t *d32 = reinterpret_cast<uint32_t *>(d);
-                        const uint32_t pw = off >> 2, rw = rel >> 2;
-                        for (uint32_t k = glane; k < (len >> 2); k += 8) d32[k] = p32[(rw + k) % pw];
+                        const uint32_t pw = off >> 2, nw = len >> 2;
+                        uint32_t idx = (rel >> 2) % pw;
+                        uint32_t v[kSmallElem / 4];
+#pragma unroll
+                        for (uint32_t k = 0; k < kSmallElem / 4; k++)
+                            if (k < nw) { v[k] = p32[idx]; idx = idx + 1 == pw ? 0 : idx + 1; }
+#pragma unroll
+                        for (uint32_t k = 0; k < kSmallElem / 4; k++)
+                            if (k < nw) d32[k] = v[k];
                     } else {
-                        for (uint32_t i = glane; i < len; i += 8) d[i] = period[(rel + i) % off];
+                        uint32_t idx = rel % off;
+                        for (uint32_t i = 0; i < len; i++) { d[i] = period[idx]; idx = idx + 1 == off ? 0 : idx + 1; }
                     }
                 }
-                if (glane == 0) S.e_done[e] = (uint16_t)round;
+                S.e_done[e] = (uint16_t)round;
+            }
+            if (round == 1) {
+                // literals of 65..1023 bytes: one warp each
+                for (uint32_t e = wrp; e < total_e; e += kDecThreads / 32) {
+                    const uint32_t len = S.e_len[e];
+                    if (len <= kSmallElem || len >= kLongLiteral) continue;
+                    const uint32_t ap = S.e_a[e] & kPosMask;  // only literals are this long
+                    const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= (uint64_t)wb + kDecWin + 16) ? cinp + (ap - wb) : src + ap;
+                    lanes_copy<32>(dst + S.e_dst[e], sl, len, t & 31);
+                    if ((t & 31) == 0) S.e_done[e] = 1;
+                }
             }
             if (round == 1) {
                 // long literals: the whole CTA moves each one
@@ -554,8 +613,11 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
                         }
                 }
             }
+            COUNT_ADD(2, 1);
             if (!__syncthreads_or(pending)) break;
         }
+        COUNT_ADD(0, 1);
+        COUNT_ADD(1, total_e);
         PHASE_MARK(4);
 
         d0 += total_o;

@@ -22,17 +22,19 @@ static std::vector<uint8_t> compress(const std::vector<uint8_t> &in)
     return out;
 }
 
-static void check_stream(const std::string &name, const std::vector<uint8_t> &stream, int mode)
+static void check_stream(const std::string &name, const std::vector<uint8_t> &stream, int mode, int dmis = 0, int smis = 0)
 {
     size_t want = 0;
     int pre = orc_snappy_uncompressed_length(stream.data(), stream.size(), &want);
-    std::vector<uint8_t> ref(pre == ORC_SNAPPY_OK ? want + 1 : 1), got(ref.size() + 64, 0xCD);
+    std::vector<uint8_t> ref(pre == ORC_SNAPPY_OK ? want + 1 : 1), got_store(ref.size() + 64 + 8, 0xCD);
+    uint8_t *got = got_store.data() + dmis;  // destination misaligned by dmis bytes
     size_t rn = ref.size() - 1;
     int rs = pre == ORC_SNAPPY_OK ? orc_snappy_uncompress(stream.data(), stream.size(), ref.data(), &rn) : pre;
     ChunkJob job;
-    std::vector<uint8_t> padded(stream);  // exact size: reads past the end must not happen
-    job.src = padded.data();
-    job.dst = got.data() + 32;
+    std::vector<uint8_t> padded(stream.size() + 8);  // source misaligned by smis bytes
+    memcpy(padded.data() + smis, stream.data(), stream.size());
+    job.src = padded.data() + smis;
+    job.dst = got + 32;
     job.src_bytes = (uint32_t)stream.size();
     job.dst_bytes = (uint32_t)(pre == ORC_SNAPPY_OK ? want : 0);
     job.compressor = kHapChunkSnappy;
@@ -42,7 +44,7 @@ static void check_stream(const std::string &name, const std::vector<uint8_t> &st
     bool ok = true;
     if (rs == ORC_SNAPPY_OK) {
         if (job.status != HapResult_No_Error) ok = false;
-        else if (memcmp(got.data() + 32, ref.data(), want) != 0) ok = false;
+        else if (memcmp(got + 32, ref.data(), want) != 0) ok = false;
     } else {
         if (job.status != HapResult_Bad_Frame) ok = false;
     }
@@ -148,6 +150,10 @@ int main(int argc, char **argv)
     }
     for (int mode = 0; mode < modes; mode++)
         for (auto &c : cases) check_stream(c.first, c.second, mode);
+    // every destination / source alignment (the kernel has word, funnel and byte paths)
+    for (int dm = 0; dm < 4; dm++)
+        for (int sm = 0; sm < 4; sm++)
+            for (auto &c : cases) check_stream(c.first + "@d" + std::to_string(dm) + "s" + std::to_string(sm), c.second, 2, dm, sm);
     printf("%zu cases x %d modes, %d failures, %llu barriers\n", cases.size(), modes, g_fail,
            (unsigned long long)emu::g_barriers());
     return g_fail ? 1 : 0;
