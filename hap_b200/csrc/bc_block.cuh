@@ -36,6 +36,22 @@ HAP_HD float hap_fma(float a, float b, float c) { return fmaf(a, b, c); }
 
 struct Block8 { uint32_t lo, hi; };
 
+// sum over the four bytes of a (unsigned) times the four bytes of b (signed), plus c: one DP4A instruction
+#if defined(HAPB200_EMU) || !defined(__CUDA_ARCH__)
+HAP_HD int hap_dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    for (int k = 0; k < 4; k++) c += (int)((a >> (8 * k)) & 0xFF) * (int)(int8_t)((b >> (8 * k)) & 0xFF);
+    return c;
+}
+#else
+__device__ __forceinline__ int hap_dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+#endif
+
 HAP_HD int hap_clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
 
 // ---- BC4 / RGTC1: 16 values -> 8 bytes ------------------------------------------------------------
@@ -46,32 +62,35 @@ HAP_HD int hap_clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi 
 // floor(q/7) == (q*9363)>>16 exactly (checked exhaustively)
 HAP_HD int bc4_level_value(int L, int a0, int a1) { return a1 + (int)(((uint32_t)(L * (a0 - a1)) * 9363u) >> 16); }
 
-HAP_HD int bc4_error_and_indices(const int v[16], int a0, int a1, uint32_t &bits_lo, uint32_t &bits_hi)
+// a0 > a1.  level L in 0..7 counted from a1 (min) upwards.  The eight palette values are computed once; a texel's
+// nearest level is the number of mid-points (p[L] + p[L+1]) / 2 it reaches -- seven compare-and-add per texel, no
+// division, no indexed array.
+// vq = the values in QUARTER units (4*v for plain 8-bit input; R+2G+B for luma, which keeps the two bits
+// that rounding Y to 8 bits throws away and so picks the level nearest to the true luma).
+HAP_HD void bc4_indices(const int vq[16], int a0, int a1, uint32_t &bits_lo, uint32_t &bits_hi)
 {
-    // a0 > a1.  level L in 0..7 counted from a1 (min) upwards: value = ((7-L)*a1 + L*a0)/7.
-    // No per-texel integer division and no indexed palette array (both are slow on the GPU): the level is
-    // guessed with one multiply, then the guess and its two neighbours are scored against exact values.
-    const float inv = 7.0f / (float)(a0 - a1);
+    int p[8], s2[7];
+#pragma unroll
+    for (int L = 0; L < 8; L++) p[L] = bc4_level_value(L, a0, a1);
+#pragma unroll
+    for (int L = 0; L < 7; L++) s2[L] = 4 * (p[L] + p[L + 1]);  // mid-point in eighths (v2 below is 8 * value)
+    // DXT index by level: 0 -> 1 (a1), 1..6 -> 7..2, 7 -> 0 (a0); packed 3 bits per level
+    const uint32_t kIndexOfLevel = 1u | (7u << 3) | (6u << 6) | (5u << 9) | (4u << 12) | (3u << 15) | (2u << 18) | (0u << 21);
     uint64_t bits = 0;
-    int err = 0;
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        int L = hap_clampi((int)floorf(hap_fma((float)(v[t] - a1), inv, 0.5f)), 0, 7);
-        int d = v[t] - bc4_level_value(L, a0, a1);
-        int best = d * d, bl = L;
-        if (L > 0) { int e = v[t] - bc4_level_value(L - 1, a0, a1); if (e * e < best) { best = e * e; bl = L - 1; } }
-        if (L < 7) { int e = v[t] - bc4_level_value(L + 1, a0, a1); if (e * e < best) { best = e * e; bl = L + 1; } }
-        err += best;
-        // DXT index: 0 = a0, 1 = a1, 2..7 = interpolants from a0 towards a1
-        uint32_t idx = bl == 7 ? 0u : bl == 0 ? 1u : (uint32_t)(8 - bl);
-        bits |= (uint64_t)idx << (3 * t);
+        const int v2 = 2 * vq[t];
+        int L = 0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) L += v2 > s2[k] ? 1 : 0;  // a tie goes to the lower level: the palette values are truncated, so its exact value is the nearer one
+        bits |= (uint64_t)((kIndexOfLevel >> (3 * L)) & 7u) << (3 * t);
     }
     bits_lo = (uint32_t)bits;
     bits_hi = (uint32_t)(bits >> 32);
-    return err;
 }
 
-HAP_HD Block8 encode_bc4_block(const int v[16])
+// v: the 8-bit values (endpoints = their min/max); vq: the same in quarter units, see bc4_indices
+HAP_HD Block8 encode_bc4_block(const int v[16], const int vq[16])
 {
     int mn = 255, mx = 0;
 #pragma unroll
@@ -87,9 +106,8 @@ HAP_HD Block8 encode_bc4_block(const int v[16])
         return out;
     }
     uint32_t lo, hi;
-    int a0 = mx, a1 = mn;
-    int err = bc4_error_and_indices(v, a0, a1, lo, hi);
-    out.lo = (uint32_t)a0 | ((uint32_t)a1 << 8) | (lo << 16);
+    bc4_indices(vq, mx, mn, lo, hi);
+    out.lo = (uint32_t)mx | ((uint32_t)mn << 8) | (lo << 16);
     out.hi = (lo >> 16) | (hi << 16);
     return out;
 }
@@ -324,17 +342,18 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
 constexpr float kYCoCgMetricCo = 1.41421356f, kYCoCgMetricCg = 1.73205081f;
 
 // Returns the 5-bit scale code; cr/cg_ come back pre-multiplied by the metric above.
-HAP_HD int ycocg_block(const uint32_t px[16], float cr[16], float cg_[16], float cb[16], int yv[16])
+HAP_HD int ycocg_block(const uint32_t px[16], float cr[16], float cg_[16], float cb[16], int yv[16], int yq[16])
 {
     int m2 = 0, m4 = 0;
     int co2v[16], cg4v[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        int R = px[t] & 0xFF, G = (px[t] >> 8) & 0xFF, B = (px[t] >> 16) & 0xFF;
-        int co2 = R - B, cg4 = -R + 2 * G - B;
+        // texel bytes are R,G,B,A: weights (1,0,-1,0), (-1,2,-1,0) and (1,2,1,0) as signed bytes
+        int co2 = hap_dp4a_us(px[t], 0x00FF0001u, 0), cg4 = hap_dp4a_us(px[t], 0x00FF02FFu, 0);
         co2v[t] = co2;
         cg4v[t] = cg4;
-        yv[t] = (R + 2 * G + B + 2) >> 2;
+        yq[t] = hap_dp4a_us(px[t], 0x00010201u, 0);  // R + 2G + B = 4 * luma
+        yv[t] = (yq[t] + 2) >> 2;
         int a2 = co2 < 0 ? -co2 : co2, a4 = cg4 < 0 ? -cg4 : cg4;
         m2 = a2 > m2 ? a2 : m2;
         m4 = a4 > m4 ? a4 : m4;
@@ -422,7 +441,10 @@ HAP_HD void encode_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colour)
     int a[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) a[t] = (int)(px[t] >> 24);
-    alpha = encode_bc4_block(a);
+    int aq[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) aq[t] = 4 * a[t];
+    alpha = encode_bc4_block(a, aq);
     colour = encode_dxt1(px);
 }
 
@@ -442,8 +464,9 @@ HAP_HD void encode_ycocg_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colo
     }
     float r[16], g[16], b[16];
     int y[16];
-    const int code = ycocg_block(px, r, g, b, y);
-    alpha = encode_bc4_block(y);
+    int yq[16];
+    const int code = ycocg_block(px, r, g, b, y, yq);
+    alpha = encode_bc4_block(y, yq);
     colour = encode_colour_block<HAP_YCOCG_FIT, false>(r, g, b, code, kYCoCgMetricCo, kYCoCgMetricCg, 1.0f);
 }
 
@@ -452,7 +475,10 @@ HAP_HD Block8 encode_rgtc1_alpha(const uint32_t px[16])
     int a[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) a[t] = (int)(px[t] >> 24);
-    return encode_bc4_block(a);
+    int aq[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) aq[t] = 4 * a[t];
+    return encode_bc4_block(a, aq);
 }
 
 }  // namespace hapb200

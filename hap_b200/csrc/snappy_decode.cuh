@@ -165,36 +165,43 @@ __device__ __forceinline__ void lanes_copy(uint8_t *dst, const uint8_t *src, uin
 // Up to kSmallElem (64) bytes by one thread.  Word path: every load is issued before the first store, so the
 // loads overlap instead of each waiting behind the store before it (the compiler must assume they alias).
 constexpr uint32_t kSmallElem = 64;
+constexpr uint32_t kThreadElem = 256;  // literals up to this long are also moved by one thread (their source is shared memory)
+constexpr uint32_t kStageWords = 8;  // words held in registers at a time (two passes cover 64 bytes)
 __device__ __forceinline__ void small_copy(uint8_t *d, const uint8_t *s, uint32_t len)
 {
     if ((((uintptr_t)d | (uintptr_t)s | len) & 3) == 0) {
         const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s);
         uint32_t *d32 = reinterpret_cast<uint32_t *>(d);
         const uint32_t nw = len >> 2;
-        uint32_t v[kSmallElem / 4];
+#pragma unroll 1
+        for (uint32_t b = 0; b < nw; b += kStageWords) {
+            uint32_t v[kStageWords];
 #pragma unroll
-        for (uint32_t k = 0; k < kSmallElem / 4; k++)
-            if (k < nw) v[k] = s32[k];
+            for (uint32_t k = 0; k < kStageWords; k++)
+                if (b + k < nw) v[k] = s32[b + k];
 #pragma unroll
-        for (uint32_t k = 0; k < kSmallElem / 4; k++)
-            if (k < nw) d32[k] = v[k];
+            for (uint32_t k = 0; k < kStageWords; k++)
+                if (b + k < nw) d32[b + k] = v[k];
+        }
     } else if ((((uintptr_t)d | len) & 3) == 0) {
         // destination aligned, source not: each word from two aligned source words
         const uint32_t mis = (uint32_t)((uintptr_t)s & 3);
         const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s - mis);
         uint32_t *d32 = reinterpret_cast<uint32_t *>(d);
         const uint32_t nw = len >> 2;
-        uint32_t v[kSmallElem / 4 + 1];
-#pragma unroll
-        for (uint32_t k = 0; k < kSmallElem / 4; k++)
-            if (k < nw) v[k] = s32[k];
-        // the last source word may hold only bytes before the element's end: assemble it bytewise
+        // the word after the last whole source word may hold only bytes before the element's end: bytewise
         uint32_t last = 0;
         for (uint32_t q = 0; q < mis; q++) last |= (uint32_t)s[len - mis + q] << (8 * q);
-        v[kSmallElem / 4] = 0;
+#pragma unroll 1
+        for (uint32_t b = 0; b < nw; b += kStageWords) {
+            uint32_t v[kStageWords + 1];
 #pragma unroll
-        for (uint32_t k = 0; k < kSmallElem / 4; k++)
-            if (k < nw) d32[k] = __funnelshift_r(v[k], k + 1 < nw ? v[k + 1] : last, 8 * mis);
+            for (uint32_t k = 0; k <= kStageWords; k++)
+                v[k] = b + k < nw ? s32[b + k] : last;
+#pragma unroll
+            for (uint32_t k = 0; k < kStageWords; k++)
+                if (b + k < nw) d32[b + k] = __funnelshift_r(v[k], v[k + 1], 8 * mis);
+        }
     } else {
         for (uint32_t i = 0; i < len; i++) d[i] = s[i];
     }
@@ -221,7 +228,7 @@ __device__ unsigned long long g_decode_counts[8];  // windows, elements, execute
 #define COUNT_ADD(i, v) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(ChunkJob *jobs, int njobs)
+__global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(ChunkJob *jobs, int njobs)
 {
     HAP_DYN_SMEM(smem_raw);
     DecodeSmem &S = *reinterpret_cast<DecodeSmem *>(smem_raw);
@@ -528,7 +535,7 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
             for (uint32_t e = t; e < total_e; e += kDecThreads) {
                 if (S.e_done[e] != 0) continue;
                 const uint32_t len = S.e_len[e];
-                if (len > kSmallElem) continue;
+                if (len > kThreadElem) continue;                 // (copies are at most 64 bytes)
                 const uint32_t a = S.e_a[e], o = S.e_dst[e];
                 const uint32_t kind = a & kSrcMask, ap = a & kPosMask;
                 uint8_t *d = dst + o;
@@ -570,13 +577,16 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
                         uint32_t *d32 = reinterpret_cast<uint32_t *>(d);
                         const uint32_t pw = off >> 2, nw = len >> 2;
                         uint32_t idx = (rel >> 2) % pw;
-                        uint32_t v[kSmallElem / 4];
+#pragma unroll 1
+                        for (uint32_t b = 0; b < nw; b += kStageWords) {
+                            uint32_t v[kStageWords];
 #pragma unroll
-                        for (uint32_t k = 0; k < kSmallElem / 4; k++)
-                            if (k < nw) { v[k] = p32[idx]; idx = idx + 1 == pw ? 0 : idx + 1; }
+                            for (uint32_t k = 0; k < kStageWords; k++)
+                                if (b + k < nw) { v[k] = p32[idx]; idx = idx + 1 == pw ? 0 : idx + 1; }
 #pragma unroll
-                        for (uint32_t k = 0; k < kSmallElem / 4; k++)
-                            if (k < nw) d32[k] = v[k];
+                            for (uint32_t k = 0; k < kStageWords; k++)
+                                if (b + k < nw) d32[b + k] = v[k];
+                        }
                     } else {
                         uint32_t idx = rel % off;
                         for (uint32_t i = 0; i < len; i++) { d[i] = period[idx]; idx = idx + 1 == off ? 0 : idx + 1; }
@@ -585,10 +595,10 @@ __global__ void __launch_bounds__(kDecThreads) snappy_decode_chunks_kernel(Chunk
                 S.e_done[e] = (uint16_t)round;
             }
             if (round == 1) {
-                // literals of 65..1023 bytes: one warp each
+                // literals of kThreadElem+1 .. 1023 bytes: one warp each
                 for (uint32_t e = wrp; e < total_e; e += kDecThreads / 32) {
                     const uint32_t len = S.e_len[e];
-                    if (len <= kSmallElem || len >= kLongLiteral) continue;
+                    if (len <= kThreadElem || len >= kLongLiteral) continue;
                     const uint32_t ap = S.e_a[e] & kPosMask;  // only literals are this long
                     const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= (uint64_t)wb + kDecWin + 16) ? cinp + (ap - wb) : src + ap;
                     lanes_copy<32>(dst + S.e_dst[e], sl, len, t & 31);
