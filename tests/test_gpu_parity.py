@@ -201,3 +201,77 @@ def test_full_size_roundtrip_properties(lib, w, h, codec_name, k):
     src = img.cpu().numpy()
     ch = (0, 1, 2, 3) if codec_name == "HapM" else (0, 1, 2)
     assert oracles.psnr(src, dec, ch) > 38.0
+
+
+def test_decode_rgba_batch_matches_oracle_block_decoder(lib):
+    """Frames -> RGBA in one batched call (Snappy decode + block decode + YCoCg / alpha merge on the GPU)
+    equals the oracle's block decoder applied to the reference-decoded texture bytes."""
+    import hap_b200.lib as L
+    w, h, frames, k = 256, 128, 5, 4
+    for codec_name, kinds in (("HapY", ["ycocg"]), ("HapM", ["ycocg", "bc4"]), ("Hap1", ["bc1"]), ("Hap5", ["bc3"])):
+        codec = getattr(L, "HapB200Codec_" + codec_name)
+        imgs = torch.stack([synth.frame(w, h, i, alpha="ramp", device="cuda") for i in range(frames)])
+        cap = (lib.max_encoded_length_rgba(w, h, codec, k) + 15) // 16 * 16
+        out = torch.zeros(frames * cap, dtype=torch.uint8, device="cuda")
+        used = torch.zeros(frames, dtype=torch.int64, device="cuda")
+        assert lib.encode_rgba_batch(imgs.data_ptr(), frames, w * h * 4, w, h, codec, 1, k, out.data_ptr(), cap, used.data_ptr()) == 0
+        rgba = torch.zeros((frames, h, w, 4), dtype=torch.uint8, device="cuda")
+        res = torch.full((frames,), 9, dtype=torch.int32, device="cuda")
+        assert lib.decode_rgba_batch(out.data_ptr(), frames, cap, used.data_ptr(), k, codec, w, h, rgba.data_ptr(), w * h * 4,
+                                     res.data_ptr()) == 0
+        assert res.tolist() == [0] * frames
+        ref = oracles.ref_abi() or oracles.oracle_abi()
+        host = out.cpu().numpy()
+        for f in range(frames):
+            fr = host[f * cap: f * cap + int(used[f])].tobytes()
+            t0 = ref.decode(fr, 0, lib.texture_bytes(w, h, codec, 0))[1]
+            want = oracles.bc_decode(kinds[0], t0, w, h)
+            if kinds[0] == "bc4":
+                want = np.stack([want, want, want, np.full_like(want, 255)], -1)
+            if len(kinds) == 2:
+                t1 = ref.decode(fr, 1, lib.texture_bytes(w, h, codec, 1))[1]
+                want = want.copy()
+                want[..., 3] = oracles.bc_decode("bc4", t1, w, h)
+            assert np.array_equal(rgba[f].cpu().numpy(), want), (codec_name, f)
+        # a frame of another flavour is reported per frame, not decoded
+        other = L.HapB200Codec_Hap1 if codec_name != "Hap1" else L.HapB200Codec_HapY
+        assert lib.decode_rgba_batch(out.data_ptr(), frames, cap, used.data_ptr(), k, other, w, h, rgba.data_ptr(), w * h * 4,
+                                     res.data_ptr()) == 0
+        assert all(r in (2, 3) for r in res.tolist())  # wrong size for the claimed flavour, or wrong format
+
+
+def test_16k_frame_roundtrip(lib):
+    """BASELINE.json config 5's frame size: one 16384 x 16384 RGBA frame (1 GiB) -> Hap Q, 64 chunks -> decoded on
+    the GPU; the decoded texture must equal the block encoder's output (kept on the device, 256 MiB)."""
+    import hap_b200.lib as L
+    w = h = 16384
+    codec, k = L.HapB200Codec_HapY, 64
+    free, _ = torch.cuda.mem_get_info()
+    if free < 6 * 2 ** 30:
+        pytest.skip("not enough free device memory")
+    img = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda")
+    tile = synth.frame(2048, 2048, 0, device="cuda")
+    for y in range(0, h, 2048):
+        for x in range(0, w, 2048):
+            img[y:y + 2048, x:x + 2048] = tile
+    n = lib.texture_bytes(w, h, codec)
+    blocks = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    assert lib.block_encode_batch(img.data_ptr(), 1, img.numel(), w, h, codec, blocks.data_ptr(), n) == 0
+    cap = (lib.max_encoded_length_rgba(w, h, codec, k) + 15) // 16 * 16
+    out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    used = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert lib.encode_rgba_batch(img.data_ptr(), 1, img.numel(), w, h, codec, 1, k, out.data_ptr(), cap, used.data_ptr()) == 0
+    nbytes = int(used[0])
+    assert out[:4].tolist() == [0, 0, 0, 0xCF]          # 8-byte header, complex, YCoCg
+    assert nbytes < n
+    back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    bused = torch.zeros(1, dtype=torch.int64, device="cuda")
+    fmts = torch.zeros(1, dtype=torch.int32, device="cuda")
+    res = torch.full((1,), 9, dtype=torch.int32, device="cuda")
+    assert lib.decode_batch(out.data_ptr(), 1, cap, used.data_ptr(), 0, k, back.data_ptr(), n, bused.data_ptr(), fmts.data_ptr(),
+                            res.data_ptr()) == 0
+    assert res.tolist() == [0] and bused.tolist() == [n] and fmts.tolist() == [1]
+    assert torch.equal(back, blocks)
+    # the host-side header walk agrees (chunk count as the reference limits it)
+    head = out[: 4096].cpu().numpy().tobytes()
+    assert head[8:12] == (5 * 64 + 8).to_bytes(3, "little") + b"\x01"
