@@ -63,10 +63,8 @@ struct DecodeSmem {
     uint16_t entry[kDecThreads];     // true entry offset of each sub-block, 0xFFFF = jumped over
     uint32_t scratch[kDecThreads / 32];
     uint32_t bcast[4];
-    uint32_t n_long;                 // long literals of the window being described
+    uint32_t n_long;                 // long literals of the current window
     uint32_t long_list[kMaxLong];
-    uint32_t n_long_prev;            // ... of the window being executed
-    uint32_t long_prev[kMaxLong];
     int fail;        // preamble / parse stage
     int fail_desc;   // descriptor stage (separate word: it is written while slow threads may still read `fail`)
 };
@@ -212,78 +210,6 @@ __device__ __forceinline__ void small_copy(uint8_t *d, const uint8_t *s, uint32_
 __device__ __forceinline__ void group_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t glane) { lanes_copy<8>(dst, src, len, glane); }
 __device__ __forceinline__ void cta_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t t) { lanes_copy<kDecThreads>(dst, src, len, t); }
 
-// One pass over the elements of at most kThreadElem bytes that are still pending: thread `first`, `first+step`, ...
-// Literal bytes are read from the input in global memory (the staged window may already hold the next window).
-// Returns 1 when some element had to be left for a later round.
-__device__ __forceinline__ int exec_small_elements(DecodeSmem &S, uint32_t first, uint32_t step, uint32_t total_e,
-                                                   uint32_t round, uint32_t d0, uint8_t *__restrict__ dst,
-                                                   const uint8_t *__restrict__ src)
-{
-    int pending = 0;
-    for (uint32_t e = first; e < total_e; e += step) {
-        if (S.e_done[e] != 0) continue;
-        const uint32_t len = S.e_len[e];
-        if (len > kThreadElem) continue;                 // (copies are at most 64 bytes)
-        const uint32_t a = S.e_a[e], o = S.e_dst[e];
-        const uint32_t kind = a & kSrcMask, ap = a & kPosMask;
-        uint8_t *d = dst + o;
-        if (kind == kSrcIn) {
-            small_copy(d, src + ap, len);
-            S.e_done[e] = (uint16_t)round;
-            continue;
-        }
-        const uint32_t base = S.e_b[e];
-        const uint32_t rel = o - base;  // position of this element inside its same-offset run
-        uint32_t need_lo, need_hi;      // bytes this element reads
-        if (kind == kSrcOut) { need_lo = ap; need_hi = ap + len; }
-        else if (rel + len <= ap) { need_lo = o - ap; need_hi = need_lo + len; }
-        else { need_lo = base - ap; need_hi = base; }
-        if (need_hi > d0) {
-            bool ready = true;
-            uint32_t x = need_lo > d0 ? need_lo : d0;
-            uint32_t lo2 = 0, hi2 = e;  // last element with e_dst <= x; the producer is before e
-            while (hi2 - lo2 > 1) {
-                uint32_t m = (lo2 + hi2) >> 1;
-                if (S.e_dst[m] <= x) lo2 = m; else hi2 = m;
-            }
-            for (uint32_t f = lo2; f < e && S.e_dst[f] < need_hi; f++) {
-                uint32_t df = S.e_done[f];
-                if (df == 0 || df >= round) { ready = false; break; }
-            }
-            if (!ready) { pending = 1; continue; }
-        }
-        if (kind == kSrcOut) {
-            small_copy(d, dst + ap, len);
-        } else if (rel + len <= ap) {
-            small_copy(d, dst + (o - ap), len);
-        } else {
-            const uint32_t off = ap;
-            const uint8_t *period = dst + (base - off);
-            if (((off | rel | len) & 3) == 0 && (((uintptr_t)d | (uintptr_t)period) & 3) == 0) {
-                const uint32_t *p32 = reinterpret_cast<const uint32_t *>(period);
-                uint32_t *d32 = reinterpret_cast<uint32_t *>(d);
-                const uint32_t pw = off >> 2, nw = len >> 2;
-                uint32_t idx = (rel >> 2) % pw;
-#pragma unroll 1
-                for (uint32_t b = 0; b < nw; b += kStageWords) {
-                    uint32_t v[kStageWords];
-#pragma unroll
-                    for (uint32_t k = 0; k < kStageWords; k++)
-                        if (b + k < nw) { v[k] = p32[idx]; idx = idx + 1 == pw ? 0 : idx + 1; }
-#pragma unroll
-                    for (uint32_t k = 0; k < kStageWords; k++)
-                        if (b + k < nw) d32[b + k] = v[k];
-                }
-            } else {
-                uint32_t idx = rel % off;
-                for (uint32_t i = 0; i < len; i++) { d[i] = period[idx]; idx = idx + 1 == off ? 0 : idx + 1; }
-            }
-        }
-        S.e_done[e] = (uint16_t)round;
-    }
-    return pending;
-}
-
 #ifdef HAPB200_EMU
 __device__ __forceinline__ void hap_prefetch_l2(const void *) {}
 #else
@@ -365,16 +291,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
     uint32_t d0 = 0;           // output bytes produced by earlier windows
     __syncthreads();
 
-    // Software pipeline over windows: while ONE thread follows the element chain of window k (a serial walk over
-    // the exit table), the other seven warps already move the bytes of window k-1.
-    uint32_t p_total_e = 0, p_total_o = 0;  // descriptors of the previous window, not executed yet
-    bool have_prev = false;
-    for (;;) {
-        const bool have_win = wb < in_end;
-        if (!have_win && !have_prev) break;
-        const uint8_t *cinp = S.cin;
-        uint32_t blk_start = in_end, blk_end = in_end;
-        if (have_win) {
+    while (wb < in_end) {
         // ---- stage the window.  Chunks are byte-packed in a frame, so the chunk is rarely aligned: read aligned
         //      16-byte words and shift them so that S.cin[0] is the byte at `wb` (word loads stay aligned later) ---
         if (t == 0) S.n_long = 0;
@@ -402,6 +319,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
             const uint64_t pf = (uint64_t)wb + kDecWin + (uint64_t)t * 128;
             if (pf < in_end) hap_prefetch_l2(src + pf);
         }
+        const uint8_t *cinp = S.cin;
         S.entry[t] = 0xFFFFu;
         __syncthreads();
 
@@ -410,8 +328,8 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
         //      chain entering there leave the sub-block?  One backward sweep: x[o] = x[o + length(o)].
         //      (b) one thread hops sub-block to sub-block along the true chain using that table.
         //      (c) every sub-block the chain enters is walked once from its true entry. ------------------
-        blk_start = (uint64_t)wb + (uint64_t)t * kDecSub < in_end ? wb + t * kDecSub : in_end;
-        blk_end = (uint64_t)wb + (uint64_t)(t + 1) * kDecSub < in_end ? wb + (t + 1) * kDecSub : in_end;
+        const uint32_t blk_start = (uint64_t)wb + (uint64_t)t * kDecSub < in_end ? wb + t * kDecSub : in_end;
+        const uint32_t blk_end = (uint64_t)wb + (uint64_t)(t + 1) * kDecSub < in_end ? wb + (t + 1) * kDecSub : in_end;
         if (blk_start < in_end) {
             // the sub-block's 64 bytes (+ 4 bytes of header look-ahead) live in registers: the sweep is fully
             // unrolled, so every tag byte is a compile-time extraction and only the table access touches memory
@@ -448,22 +366,9 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                 S.tbl[(uint32_t)o * kDecThreads + t] = (uint8_t)x;
             }
         }
-        }  // have_win: staging + exit tables
         __syncthreads();
         PHASE_MARK(5);
-        if (wrp != 0) {
-            // ---- execute, round 1 of the PREVIOUS window: everything whose source is the input or finished output
-            if (have_prev) {
-                exec_small_elements(S, t - 32, kDecThreads - 32, p_total_e, 1, d0, dst, src);
-                // literals of kThreadElem+1 .. 1023 bytes: one warp each
-                for (uint32_t e = wrp - 1; e < p_total_e; e += kDecThreads / 32 - 1) {
-                    const uint32_t len = S.e_len[e];
-                    if (len <= kThreadElem || len >= kLongLiteral) continue;
-                    lanes_copy<32>(dst + S.e_dst[e], src + (S.e_a[e] & kPosMask), len, t & 31);
-                    if ((t & 31) == 0) S.e_done[e] = 1;
-                }
-            }
-        } else if (t == 0 && have_win) {
+        if (t == 0) {
             // window-relative positions: the dependent chain per hop is one table load plus a few ALU ops
             const uint32_t rel_end = in_end - wb;
             uint32_t rel = 0;
@@ -493,38 +398,6 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
         }
         __syncthreads();
         PHASE_MARK(6);
-        if (have_prev) {
-            // ---- execute, rest of the previous window: the longest literals by the whole CTA, then the copies
-            //      that had to wait for a producer, in dependency rounds
-            const uint32_t nlong = S.n_long_prev < (uint32_t)kMaxLong ? S.n_long_prev : (uint32_t)kMaxLong;
-            for (uint32_t q = 0; q < nlong; q++) {
-                const uint32_t e = S.long_prev[q];
-                cta_copy(dst + S.e_dst[e], src + (S.e_a[e] & kPosMask), S.e_len[e], t);
-                if (t == 0) S.e_done[e] = 1;
-            }
-            if (S.n_long_prev > (uint32_t)kMaxLong) {
-                // overflow of the list (pathological): sweep the descriptors instead
-                for (uint32_t e = 0; e < p_total_e; e++)
-                    if ((S.e_a[e] & kSrcMask) == kSrcIn && S.e_len[e] >= kLongLiteral && S.e_done[e] == 0) {
-                        cta_copy(dst + S.e_dst[e], src + (S.e_a[e] & kPosMask), S.e_len[e], t);
-                        __syncthreads();
-                        if (t == 0) S.e_done[e] = 1;
-                    }
-            }
-            // round 1 ran above (by warps 1-7, all elements); what waited for a producer goes in rounds 2, 3, ...
-            for (uint32_t round = 2;; round++) {
-                const int pending = exec_small_elements(S, t, kDecThreads, p_total_e, round, d0, dst, src);
-                COUNT_ADD(2, 1);
-                if (!__syncthreads_or(pending)) break;
-            }
-            COUNT_ADD(0, 1);
-            COUNT_ADD(1, p_total_e);
-            d0 += p_total_o;
-            have_prev = false;
-        }
-        PHASE_MARK(4);
-        if (S.fail) break;
-        if (!have_win) break;
         uint32_t entry = blk_end;
         WalkResult w;
         w.exit = 0; w.count = 0; w.out_bytes = 0; w.invalid = 0;
@@ -653,14 +526,111 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
         }
 
         PHASE_MARK(7);
-        // the bytes of this window move while the next window's chain is being followed (top of the loop)
-        p_total_e = total_e;
-        p_total_o = total_o;
-        have_prev = true;
-        if (t == 0) {
-            S.n_long_prev = S.n_long;
+        // ---- 3. execute: round 1 = everything whose source is the input or earlier windows; later rounds =
+        //         copies whose producers finished in an earlier round.  Elements of at most 64 bytes (every copy,
+        //         most literals) are moved by ONE THREAD each, staged through registers so that all its loads are
+        //         in flight together; longer literals by a warp each; the longest by the whole CTA.
+        for (uint32_t round = 1;; round++) {
+            int pending = 0;
+            for (uint32_t e = t; e < total_e; e += kDecThreads) {
+                if (S.e_done[e] != 0) continue;
+                const uint32_t len = S.e_len[e];
+                if (len > kThreadElem) continue;                 // (copies are at most 64 bytes)
+                const uint32_t a = S.e_a[e], o = S.e_dst[e];
+                const uint32_t kind = a & kSrcMask, ap = a & kPosMask;
+                uint8_t *d = dst + o;
+                if (kind == kSrcIn) {
+                    const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= (uint64_t)wb + kDecWin + 16) ? cinp + (ap - wb) : src + ap;
+                    small_copy(d, sl, len);
+                    S.e_done[e] = (uint16_t)round;
+                    continue;
+                }
+                const uint32_t base = S.e_b[e];
+                const uint32_t rel = o - base;  // position of this element inside its same-offset run
+                uint32_t need_lo, need_hi;      // bytes this element reads
+                if (kind == kSrcOut) { need_lo = ap; need_hi = ap + len; }
+                else if (rel + len <= ap) { need_lo = o - ap; need_hi = need_lo + len; }
+                else { need_lo = base - ap; need_hi = base; }
+                if (need_hi > d0) {
+                    bool ready = true;
+                    uint32_t x = need_lo > d0 ? need_lo : d0;
+                    uint32_t lo2 = 0, hi2 = e;  // last element with e_dst <= x; the producer is before e
+                    while (hi2 - lo2 > 1) {
+                        uint32_t m = (lo2 + hi2) >> 1;
+                        if (S.e_dst[m] <= x) lo2 = m; else hi2 = m;
+                    }
+                    for (uint32_t f = lo2; f < e && S.e_dst[f] < need_hi; f++) {
+                        uint32_t df = S.e_done[f];
+                        if (df == 0 || df >= round) { ready = false; break; }
+                    }
+                    if (!ready) { pending = 1; continue; }
+                }
+                if (kind == kSrcOut) {
+                    small_copy(d, dst + ap, len);
+                } else if (rel + len <= ap) {
+                    small_copy(d, dst + (o - ap), len);
+                } else {
+                    const uint32_t off = ap;
+                    const uint8_t *period = dst + (base - off);
+                    if (((off | rel | len) & 3) == 0 && (((uintptr_t)d | (uintptr_t)period) & 3) == 0) {
+                        const uint32_t *p32 = reinterpret_cast<const uint32_t *>(period);
+                        uint32_t *d32 = reinterpret_cast<uint32_t *>(d);
+                        const uint32_t pw = off >> 2, nw = len >> 2;
+                        uint32_t idx = (rel >> 2) % pw;
+#pragma unroll 1
+                        for (uint32_t b = 0; b < nw; b += kStageWords) {
+                            uint32_t v[kStageWords];
+#pragma unroll
+                            for (uint32_t k = 0; k < kStageWords; k++)
+                                if (b + k < nw) { v[k] = p32[idx]; idx = idx + 1 == pw ? 0 : idx + 1; }
+#pragma unroll
+                            for (uint32_t k = 0; k < kStageWords; k++)
+                                if (b + k < nw) d32[b + k] = v[k];
+                        }
+                    } else {
+                        uint32_t idx = rel % off;
+                        for (uint32_t i = 0; i < len; i++) { d[i] = period[idx]; idx = idx + 1 == off ? 0 : idx + 1; }
+                    }
+                }
+                S.e_done[e] = (uint16_t)round;
+            }
+            if (round == 1) {
+                // literals of kThreadElem+1 .. 1023 bytes: one warp each
+                for (uint32_t e = wrp; e < total_e; e += kDecThreads / 32) {
+                    const uint32_t len = S.e_len[e];
+                    if (len <= kThreadElem || len >= kLongLiteral) continue;
+                    const uint32_t ap = S.e_a[e] & kPosMask;  // only literals are this long
+                    const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= (uint64_t)wb + kDecWin + 16) ? cinp + (ap - wb) : src + ap;
+                    lanes_copy<32>(dst + S.e_dst[e], sl, len, t & 31);
+                    if ((t & 31) == 0) S.e_done[e] = 1;
+                }
+            }
+            if (round == 1) {
+                // long literals: the whole CTA moves each one
+                const uint32_t nlong = S.n_long < (uint32_t)kMaxLong ? S.n_long : (uint32_t)kMaxLong;
+                for (uint32_t q = 0; q < nlong; q++) {
+                    const uint32_t e = S.long_list[q];
+                    cta_copy(dst + S.e_dst[e], src + (S.e_a[e] & kPosMask), S.e_len[e], t);
+                    if (t == 0) S.e_done[e] = 1;
+                }
+                if (S.n_long > (uint32_t)kMaxLong) {
+                    // overflow of the list (pathological): sweep the descriptors instead
+                    for (uint32_t e = 0; e < total_e; e++)
+                        if ((S.e_a[e] & kSrcMask) == kSrcIn && S.e_len[e] >= kLongLiteral && S.e_done[e] == 0) {
+                            cta_copy(dst + S.e_dst[e], src + (S.e_a[e] & kPosMask), S.e_len[e], t);
+                            __syncthreads();
+                            if (t == 0) S.e_done[e] = 1;
+                        }
+                }
+            }
+            COUNT_ADD(2, 1);
+            if (!__syncthreads_or(pending)) break;
         }
-        for (uint32_t q = t; q < (uint32_t)kMaxLong; q += kDecThreads) S.long_prev[q] = S.long_list[q];
+        COUNT_ADD(0, 1);
+        COUNT_ADD(1, total_e);
+        PHASE_MARK(4);
+
+        d0 += total_o;
         wb = next_wb;
         __syncthreads();
     }
