@@ -90,11 +90,15 @@ __device__ __forceinline__ uint32_t enc_block_excl(uint32_t v, bool is_max, uint
 // One fragment: W words already in S.data AND in the caller's registers d[8] (words 8t..8t+7; W % 2 == 0,
 // W <= kFragWords) -> element stream written over S.data as bytes; returns its size (all threads).
 // period_words = DXT block size in words (2 or 4).
-__device__ __forceinline__ uint32_t compress_fragment(EncodeSmem &S, const uint32_t d[8], uint32_t W, uint32_t period_words)
+// FULL = the fragment has all kFragWords words (31 of 32 fragments of a 1 MiB chunk): every per-word bounds test
+// folds away at compile time.
+template <bool FULL>
+__device__ __forceinline__ uint32_t compress_fragment(EncodeSmem &S, const uint32_t d[8], uint32_t Wdyn, uint32_t period_words)
 {
     const uint32_t t = threadIdx.x;
+    const uint32_t W = FULL ? (uint32_t)kFragWords : Wdyn;
     const uint32_t i0 = t * kStrip;                  // first word of my strip
-    const uint32_t nv = i0 >= W ? 0u : (W - i0 < (uint32_t)kStrip ? W - i0 : (uint32_t)kStrip);  // my valid words
+    const uint32_t nv = FULL ? (uint32_t)kStrip : (i0 >= W ? 0u : (W - i0 < (uint32_t)kStrip ? W - i0 : (uint32_t)kStrip));  // my valid words
 
     // 1. first occurrence of every word (the table was initialised by the caller, before the barrier)
 #pragma unroll
@@ -342,7 +346,8 @@ __global__ void __launch_bounds__(kEncThreads) snappy_encode_fragments_kernel(
         for (int q = t; q < (1 << kEncHashBits) / 4; q += kEncThreads) tb[q] = ones;
     }
     __syncthreads();
-    const uint32_t total = compress_fragment(S, d, W, sec.period_words);
+    const uint32_t total = W == (uint32_t)kFragWords ? compress_fragment<true>(S, d, W, sec.period_words)
+                                                     : compress_fragment<false>(S, d, W, sec.period_words);
     uint8_t *o = scratch + (uint64_t)gfrag * kFragCap;
     const uint32_t *o32s = reinterpret_cast<const uint32_t *>(S.data);
     uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
