@@ -118,7 +118,7 @@ HAP_HD uint32_t expand6(uint32_t c) { return (c << 2) | (c >> 4); }
 
 // Picks, for one channel, the pair of grid values around the float endpoints (a,b) that minimises the
 // cluster-weighted squared error.  levels = 31 or 63; values stay in 0..255 units.
-HAP_HD void snap_channel(float &a, float &b, float a2, float b2, float ab, float ax, float bx, float levels)
+HAP_HD float snap_channel(float &a, float &b, float a2, float b2, float ab, float ax, float bx, float levels)
 {
     const float to_grid = levels * (1.0f / 255.0f), from_grid = 255.0f / levels;
     float a_lo = floorf(a * to_grid), b_lo = floorf(b * to_grid);
@@ -133,6 +133,7 @@ HAP_HD void snap_channel(float &a, float &b, float a2, float b2, float ab, float
     }
     a = best_a;
     b = best_b;
+    return best;  // error of the chosen pair, up to the constant sum of squares of the channel
 }
 
 // One round of [project texels onto the segment a-b -> 4 clusters] + accumulate the normal-equation sums.
@@ -169,7 +170,7 @@ HAP_HD bool cluster_sums(const float r[16], const float g[16], const float b[16]
 // 2 dCo^2 + 3 dCg^2 in RGB); endpoints go back to storage units before they meet the 5:6:5 grid.
 // HAS_B = false: the third channel is constant over the block (scaled YCoCg carries its scale code there) and
 // drops out of every sum.
-template <int REFINE, int RESNAP, bool EXACT, bool HAS_B = true>
+template <int REFINE, int RESNAP, bool EXACT, bool HAS_B = true, int STARTS = 1>
 HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const float b[16], int fixed_blue5 = -1,
                                   float sr = 1.0f, float sg = 1.0f, float sb = 1.0f)
 {
@@ -223,21 +224,51 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
             tmin = fminf(tmin, d);
             tmax = fmaxf(tmax, d);
         }
-        float mar = hap_fma(vr, tmin, mr), mag = hap_fma(vg, tmin, mg), mab = hap_fma(vb, tmin, mb);
-        float mbr = hap_fma(vr, tmax, mr), mbg = hap_fma(vg, tmax, mg), mbb = hap_fma(vb, tmax, mb);
-        // refinement: clusters implied by the current segment, then least squares for the endpoints
+        // STARTS = 9 (the RGB formats): the Lloyd iteration only finds the local optimum next to its start, so it is
+        // run from 3 x 3 placements of the two ends and the start with the lowest error AFTER grid snapping wins --
+        // a cheap stand-in for cluster fit's search over all 969 ordered partitions (measured: +0.03 dB against it,
+        // where a single start was -0.39 dB).
         FitSums S;
         bool have = false;
+        float mar = 0.f, mag = 0.f, mab = 0.f, mbr = 0.f, mbg = 0.f, mbb = 0.f;
+        float best_e = 1e30f;
 #pragma unroll 1
-        for (int it = 0; it < REFINE; it++) {
-            FitSums N;
-            if (!cluster_sums<HAS_B>(r, g, b, mar, mag, mab, mbr, mbg, mbb, N)) break;
-            S = N;
-            have = true;
-            float idet = 1.0f / (S.a2 * S.b2 - S.ab * S.ab);
-            mar = (S.axr * S.b2 - S.bxr * S.ab) * idet; mbr = (S.bxr * S.a2 - S.axr * S.ab) * idet;
-            mag = (S.axg * S.b2 - S.bxg * S.ab) * idet; mbg = (S.bxg * S.a2 - S.axg * S.ab) * idet;
-            if (HAS_B) { mab = (S.axb * S.b2 - S.bxb * S.ab) * idet; mbb = (S.bxb * S.a2 - S.axb * S.ab) * idet; }
+        for (int st = 0; st < STARTS; st++) {
+            // starts: both ends of the extent moved independently by -1/5, +1/5 or +3/5 of its length (3 x 3)
+            const float step = 0.2f * (tmax - tmin);
+            const float lo_t = STARTS == 1 ? tmin : tmin + ((float)(st % 3) * 2.0f - 1.0f) * step;
+            const float hi_t = STARTS == 1 ? tmax : tmax - ((float)(st / 3) * 2.0f - 1.0f) * step;
+            float car = hap_fma(vr, lo_t, mr), cag = hap_fma(vg, lo_t, mg), cab = hap_fma(vb, lo_t, mb);
+            float cbr = hap_fma(vr, hi_t, mr), cbg = hap_fma(vg, hi_t, mg), cbb = hap_fma(vb, hi_t, mb);
+            FitSums C;
+            bool chave = false;
+#pragma unroll 1
+            for (int it = 0; it < REFINE; it++) {
+                FitSums N;
+                if (!cluster_sums<HAS_B>(r, g, b, car, cag, cab, cbr, cbg, cbb, N)) break;
+                C = N;
+                chave = true;
+                float idet = 1.0f / (C.a2 * C.b2 - C.ab * C.ab);
+                car = (C.axr * C.b2 - C.bxr * C.ab) * idet; cbr = (C.bxr * C.a2 - C.axr * C.ab) * idet;
+                cag = (C.axg * C.b2 - C.bxg * C.ab) * idet; cbg = (C.bxg * C.a2 - C.axg * C.ab) * idet;
+                if (HAS_B) { cab = (C.axb * C.b2 - C.bxb * C.ab) * idet; cbb = (C.bxb * C.a2 - C.axb * C.ab) * idet; }
+            }
+            if (STARTS == 1) {
+                S = C; have = chave;
+                mar = car; mag = cag; mab = cab; mbr = cbr; mbg = cbg; mbb = cbb;
+            } else if (chave) {
+                // error of this start after snapping (storage units; the metric is 1,1,1 for the RGB formats)
+                float tr = fminf(fmaxf(car * isr, 0.f), 255.f), ur = fminf(fmaxf(cbr * isr, 0.f), 255.f);
+                float tg = fminf(fmaxf(cag * isg, 0.f), 255.f), ug = fminf(fmaxf(cbg * isg, 0.f), 255.f);
+                float tb = fminf(fmaxf(cab * isb, 0.f), 255.f), ub = fminf(fmaxf(cbb * isb, 0.f), 255.f);
+                float e = snap_channel(tr, ur, C.a2, C.b2, C.ab, C.axr * isr, C.bxr * isr, 31.0f) * (sr * sr);
+                e += snap_channel(tg, ug, C.a2, C.b2, C.ab, C.axg * isg, C.bxg * isg, 63.0f) * (sg * sg);
+                if (HAS_B) e += snap_channel(tb, ub, C.a2, C.b2, C.ab, C.axb * isb, C.bxb * isb, 31.0f) * (sb * sb);
+                if (e < best_e) {
+                    best_e = e; S = C; have = true;
+                    mar = car; mag = cag; mab = cab; mbr = cbr; mbg = cbg; mbb = cbb;
+                }
+            }
         }
         ar = fminf(fmaxf(mar * isr, 0.f), 255.f); br = fminf(fmaxf(mbr * isr, 0.f), 255.f);
         ag = fminf(fmaxf(mag * isg, 0.f), 255.f); bg = fminf(fmaxf(mbg * isg, 0.f), 255.f);
@@ -433,7 +464,10 @@ HAP_HD Block8 encode_dxt1(const uint32_t px[16])
     for (int t = 0; t < 16; t++) {
         r[t] = (float)(px[t] & 0xFF); g[t] = (float)((px[t] >> 8) & 0xFF); b[t] = (float)((px[t] >> 16) & 0xFF);
     }
-    return encode_colour_block<2, 1, true>(r, g, b);
+#ifndef HAP_RGB_FIT
+#define HAP_RGB_FIT 1, 1, true, true, 9
+#endif
+    return encode_colour_block<HAP_RGB_FIT>(r, g, b);
 }
 
 HAP_HD void encode_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colour)

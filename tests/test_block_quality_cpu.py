@@ -1,6 +1,5 @@
 """Quality of the block-encoder algorithm (the source the CUDA kernels compile, run on the host) against
-the oracle's squish-HIGH-class cluster fit.  north_star bar: PSNR within 0.1 dB.  Where the bar is not
-met yet the test pins the measured gap so that it can only shrink."""
+the oracle's squish-HIGH-class cluster fit.  north_star bar: PSNR within 0.1 dB.  All four formats are held to it."""
 import numpy as np
 import pytest
 
@@ -9,7 +8,7 @@ import twin
 from hap_b200 import synth
 
 # (kind, allowed deficit in dB versus the oracle on the 512x512 synthetic video frame)
-BARS = [("ycocg", 0.10), ("bc4", 0.10), ("bc1", 0.20), ("bc3", 0.20)]
+BARS = [("ycocg", 0.10), ("bc4", 0.10), ("bc1", 0.10), ("bc3", 0.10)]
 
 
 @pytest.mark.parametrize("kind,deficit", BARS)

@@ -56,7 +56,7 @@ def test_psnr_bar_on_1080p(lib, name, codec):
     tb = twin.encode(name, crop)
     po = oracles.psnr(crop, oracles.bc_decode(name, ob, 512, 256))
     pt = oracles.psnr(crop, oracles.bc_decode(name, tb, 512, 256))
-    assert ours > 38 and pt >= po - (0.10 if name == "ycocg" else 0.40), (name, ours, pt, po)
+    assert ours > 38 and pt >= po - 0.10, (name, ours, pt, po)
 
 
 @pytest.mark.parametrize("name,codec", KINDS)
