@@ -100,6 +100,41 @@ bool runtime_ok()
     return g_rt.ready;
 }
 
+// Stream of one host-pointer call.  When every buffer of the call is host memory nothing outside the call can
+// be ordered against it, so it takes a private non-blocking stream from a pool and concurrent calls from
+// different host threads overlap their copies and kernels (the reference is re-entrant, hap.c has no globals).
+// With any device pointer among the arguments the call uses the legacy default stream under a mutex, which
+// orders it after whatever produced those buffers on the caller's (blocking) streams.
+struct CallStream {
+    cudaStream_t st = nullptr;
+    bool pooled = false;
+    std::unique_lock<std::mutex> serial;
+    static std::mutex &pool_mu() { static std::mutex m; return m; }
+    static std::vector<cudaStream_t> &pool() { static std::vector<cudaStream_t> v; return v; }
+    explicit CallStream(bool all_host)
+    {
+        if (all_host) {
+            {
+                std::lock_guard<std::mutex> l(pool_mu());
+                if (!pool().empty()) { st = pool().back(); pool().pop_back(); }
+            }
+            if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); st = nullptr; }
+            pooled = st != nullptr;
+        }
+        if (!pooled) {
+            serial = std::unique_lock<std::mutex>(g_rt.mu);
+            st = g_rt.stream;
+        }
+    }
+    ~CallStream()
+    {
+        if (pooled) {
+            std::lock_guard<std::mutex> l(pool_mu());
+            pool().push_back(st);
+        }
+    }
+};
+
 bool is_device_pointer(const void *p)
 {
     cudaPointerAttributes a;
@@ -447,8 +482,10 @@ unsigned int HapEncode(unsigned int count, const void **inputBuffers, unsigned l
     }
 
     if (!runtime_ok()) return HapResult_Internal_Error;
-    std::lock_guard<std::mutex> lock(g_rt.mu);
-    cudaStream_t st = g_rt.stream;
+    bool enc_all_host = !is_device_pointer(outputBuffer);
+    for (unsigned i = 0; i < count; i++) enc_all_host = enc_all_host && !is_device_pointer(inputBuffers[i]);
+    CallStream call(enc_all_host);
+    cudaStream_t st = call.st;
 
     // worst-case frame in device scratch; textures staged into 16-byte aligned device memory
     unsigned long lens[2] = {ta[0].bytes, count == 2 ? ta[1].bytes : 0};
@@ -563,8 +600,8 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
 
     if (!hj.empty()) {
         if (!runtime_ok()) return HapResult_Internal_Error;
-        std::lock_guard<std::mutex> lock(g_rt.mu);
-        cudaStream_t st = g_rt.stream;
+        CallStream call(!in_dev && !out_dev);
+        cudaStream_t st = call.st;
         DevBuf din(st), dout(st), djobs(st);
         const uint8_t *dsec;
         if (in_dev) {
@@ -739,8 +776,8 @@ unsigned int HapB200EncodeRGBA(const void *rgba, unsigned int width, unsigned in
     const unsigned long cap = HapB200MaxEncodedLengthRGBA(width, height, codec, chunkCount);
     if (outputBufferBytes < cap) return HapResult_Buffer_Too_Small;
     if (!runtime_ok()) return HapResult_Internal_Error;
-    std::lock_guard<std::mutex> lock(g_rt.mu);
-    cudaStream_t st = g_rt.stream;
+    CallStream call(!is_device_pointer(rgba) && !is_device_pointer(outputBuffer));
+    cudaStream_t st = call.st;
     DevBuf img(st), frame(st), used(st);
     const uint64_t tight = 4ull * width;
     if (!img.alloc(tight * height) || !frame.alloc(cap) || !used.alloc(32)) { cudaGetLastError(); return HapResult_Internal_Error; }
@@ -847,8 +884,8 @@ unsigned int HapB200DecodeRGBA(const void *inputBuffer, unsigned long inputBuffe
         if (r == HapResult_No_Error && used != t1) r = HapResult_Bad_Frame;
     }
     if (r == HapResult_No_Error) {
-        std::lock_guard<std::mutex> lock(g_rt.mu);
-        cudaStream_t st = g_rt.stream;
+        CallStream call(false);  // dxt / img are device buffers filled on the legacy stream by HapDecode above
+        cudaStream_t st = call.st;
         r = launch_block_decode((const uint8_t *)dxt, (const uint8_t *)dxt + align16(t0), 1, 0, 0, width, height, ci, (uint8_t *)img,
                                 0, tight, st);
         if (r == HapResult_No_Error &&

@@ -275,3 +275,23 @@ def test_16k_frame_roundtrip(lib):
     # the host-side header walk agrees (chunk count as the reference limits it)
     head = out[: 4096].cpu().numpy().tobytes()
     assert head[8:12] == (5 * 64 + 8).to_bytes(3, "little") + b"\x01"
+
+
+def test_concurrent_host_calls_are_reentrant(lib):
+    """The reference is re-entrant (no globals in hap.c); so are the host-pointer entry points here: calls from
+    many host threads run on pooled streams at the same time and must not mix their buffers."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(21)
+    payloads = [dxt_like(rng, int(rng.integers(2000, 9000)), 16) for _ in range(24)]
+    orc = oracles.oracle_abi()
+
+    def work(i):
+        p = payloads[i]
+        k = 1 + i % 7
+        r, f = lib.encode([p], [YCOCG], [HapCompressorSnappy], [k])
+        assert r == 0
+        r2, back, fmt, calls = lib.decode(f, 0, len(p))
+        return r2 == 0 and back == p and fmt == YCOCG and orc.decode(f, 0, len(p))[1] == p
+
+    with ThreadPoolExecutor(8) as pool:
+        assert all(pool.map(work, range(len(payloads))))
