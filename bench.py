@@ -161,7 +161,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # =====================================================================================================
@@ -176,7 +176,6 @@ def run_gpu_arm(args, rank, local_rank, world):
     from hap_b200 import synth
     from hap_b200.lib import HapB200Codec_HapY
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -327,7 +326,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                 "algorithmic_bytes_per_launch": alg_bytes[dominant], "ms_per_launch": dom_ms,
                 "stage_ms_per_step": per_step, "decode_phase_share": decode_phase_share, "decode_counts": getattr(lib, "last_decode_counts", None)}
     if args.profile:
-        print(json.dumps({"profile_only": True, "ms_per_step": ms_per_step, "value": value, "roofline": roofline}))
+        emit({"profile_only": True, "ms_per_step": ms_per_step, "value": value, "roofline": roofline})
         return
 
     # ---- end-to-end leg: the host-pointer C-ABI (one frame per call, pinned host buffers), PCIe copies inside
@@ -403,13 +402,31 @@ def run_gpu_arm(args, rank, local_rank, world):
                                    "decode": per_step["parse"] + per_step["snappy_decode"] + per_step["collect"]},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line, on the process's real stdout (see main(): fd 1 itself is pointed at stderr while the
+    run lasts, because NCCL prints its version banner straight to fd 1 when the first communicator is made)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
