@@ -210,6 +210,18 @@ __device__ __forceinline__ void small_copy(uint8_t *d, const uint8_t *s, uint32_
 __device__ __forceinline__ void group_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t glane) { lanes_copy<8>(dst, src, len, glane); }
 __device__ __forceinline__ void cta_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t t) { lanes_copy<kDecThreads>(dst, src, len, t); }
 
+// 16 aligned bytes at p, but only the bytes inside [lo, hi) are read (the others come back as zero)
+__device__ __forceinline__ uint4 load16_inside(const uint4 *p, uintptr_t lo, uintptr_t hi)
+{
+    const uintptr_t a = (uintptr_t)p;
+    if (a >= lo && a + 16 <= hi) return *p;
+    uint32_t w[4] = {0, 0, 0, 0};
+    const uint8_t *b = reinterpret_cast<const uint8_t *>(p);
+    for (int k = 0; k < 16; k++)
+        if (a + k >= lo && a + k < hi) w[k >> 2] |= (uint32_t)b[k] << (8 * (k & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 #ifdef HAPB200_EMU
 __device__ __forceinline__ void hap_prefetch_l2(const void *) {}
 #else
@@ -303,10 +315,13 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
             const uint4 *g4 = reinterpret_cast<const uint4 *>(gaddr - shift);
             uint4 *s4 = reinterpret_cast<uint4 *>(S.cin);
             const uint32_t ws = shift >> 2, bs = (shift & 3) * 8;
+            // aligned words are only read whole when every byte of them belongs to the chunk; the (at most two) words
+            // that stick out at the chunk's ends are gathered bytewise, so nothing outside [src, src + in_end) is touched
+            const uintptr_t c_lo = (uintptr_t)src, c_hi = (uintptr_t)src + in_end;
             for (uint32_t i = t; i < n16; i += kDecThreads) {
-                const uint4 a = g4[i];
+                const uint4 a = load16_inside(g4 + i, c_lo, c_hi);
                 uint4 b = make_uint4(0, 0, 0, 0);
-                if (shift != 0 && 16 * (i + 1) < shift + avail) b = g4[i + 1];  // never touch a word with no wanted byte
+                if (shift != 0 && 16 * (i + 1) < shift + avail) b = load16_inside(g4 + i + 1, c_lo, c_hi);
                 uint32_t w0, w1, w2, w3, w4;
                 if (ws == 0) { w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; }
                 else if (ws == 1) { w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; }

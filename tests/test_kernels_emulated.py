@@ -37,3 +37,15 @@ def test_encode_path_emulated_and_decoded_by_reference():
     assert p.returncode == 0, p.stdout + p.stderr
     if ref:
         assert "reference decoder: loaded" in p.stdout
+
+
+def test_kernels_under_address_sanitizer():
+    """The same kernel sources under ASan with exact-size buffers: no read or write outside the chunk / frame."""
+    for name, extra in (("test_decode_emu", ORC[:1]), ("test_encode_emu", ORC)):
+        exe = os.path.join(BUILD, name + "_asan")
+        src = os.path.join(ROOT, "tests", "emu", name + ".cc")
+        subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-w", "-fsanitize=address"] + INC + [src] + extra + ["-ldl", "-lm", "-o", exe],
+                       check=True)
+        env = dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0:detect_leaks=0")
+        p = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=900, env=env)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
