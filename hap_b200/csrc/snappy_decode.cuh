@@ -303,14 +303,21 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
     uint32_t d0 = 0;           // output bytes produced by earlier windows
     __syncthreads();
 
+    // Sub-blocks covered per window.  Dense streams (a few bytes per element, e.g. Google Snappy on DXT5) fill the
+    // descriptor arrays long before 256 sub-blocks are used; the span then shrinks so that no exit table is computed
+    // for bytes this window never reaches, and grows back when windows stop being cut short.
+    uint32_t span = kDecThreads;
     while (wb < in_end) {
         // ---- stage the window.  Chunks are byte-packed in a frame, so the chunk is rarely aligned: read aligned
         //      16-byte words and shift them so that S.cin[0] is the byte at `wb` (word loads stay aligned later) ---
         if (t == 0) S.n_long = 0;
+        uint32_t staged_end;  // input position up to which S.cin holds this window's bytes
         {
             const uintptr_t gaddr = (uintptr_t)(src + wb);
             const uint32_t shift = (uint32_t)(gaddr & 15);           // uniform over the CTA
-            const uint32_t avail = in_end - wb < (uint32_t)(kDecWin + 16) ? in_end - wb : (uint32_t)(kDecWin + 16);
+            const uint32_t want = span * kDecSub + 16;
+            const uint32_t avail = in_end - wb < want ? in_end - wb : want;
+            staged_end = wb + avail;
             const uint32_t n16 = (avail + 15) >> 4;
             const uint4 *g4 = reinterpret_cast<const uint4 *>(gaddr - shift);
             uint4 *s4 = reinterpret_cast<uint4 *>(S.cin);
@@ -343,8 +350,9 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
         //      chain entering there leave the sub-block?  One backward sweep: x[o] = x[o + length(o)].
         //      (b) one thread hops sub-block to sub-block along the true chain using that table.
         //      (c) every sub-block the chain enters is walked once from its true entry. ------------------
-        const uint32_t blk_start = (uint64_t)wb + (uint64_t)t * kDecSub < in_end ? wb + t * kDecSub : in_end;
-        const uint32_t blk_end = (uint64_t)wb + (uint64_t)(t + 1) * kDecSub < in_end ? wb + (t + 1) * kDecSub : in_end;
+        // threads beyond the span own nothing in this window
+        const uint32_t blk_start = (uint32_t)t < span && (uint64_t)wb + (uint64_t)t * kDecSub < in_end ? wb + t * kDecSub : in_end;
+        const uint32_t blk_end = (uint32_t)t < span && (uint64_t)wb + (uint64_t)(t + 1) * kDecSub < in_end ? wb + (t + 1) * kDecSub : in_end;
         if (blk_start < in_end) {
             // the sub-block's 64 bytes (+ 4 bytes of header look-ahead) live in registers: the sweep is fully
             // unrolled, so every tag byte is a compile-time extraction and only the table access touches memory
@@ -387,7 +395,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
             // window-relative positions: the dependent chain per hop is one table load plus a few ALU ops
             const uint32_t rel_end = in_end - wb;
             uint32_t rel = 0;
-            while (rel < rel_end && rel < (uint32_t)kDecWin) {
+            while (rel < rel_end && rel < span * kDecSub) {
                 const uint32_t blk = rel >> 6, o = rel & 63;
                 const uint32_t x = S.tbl[o * kDecThreads + blk];
                 S.entry[blk] = (uint16_t)o;
@@ -425,6 +433,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
         // ---- 2. scans: element slots and output offsets; window truncation -------------------
         uint32_t total_e, total_o;
         uint32_t ebase = block_excl_sum<kDecThreads>(w.count, &total_e, S.scratch);
+        const uint32_t total_e_all = total_e;
         const bool keep = ebase + w.count <= (uint32_t)kDecMaxElems;
         uint32_t kept_cnt = keep ? w.count : 0;
         uint32_t kept_out = keep ? w.out_bytes : 0;
@@ -437,6 +446,11 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
         if (t == 0 && (uint64_t)d0 + total_o > expected) S.fail = 1;
         __syncthreads();
         if (S.fail) break;
+        {
+            const uint32_t used_sub = (next_wb - wb + kDecSub - 1) / kDecSub;   // uniform: both come from block-wide scans
+            if (total_e_all > (uint32_t)kDecMaxElems) span = used_sub + used_sub / 4 < 16u ? 16u : (used_sub + used_sub / 4 > (uint32_t)kDecThreads ? (uint32_t)kDecThreads : used_sub + used_sub / 4);
+            else if (total_e_all < (uint32_t)kDecMaxElems / 2) span = span * 2 > (uint32_t)kDecThreads ? (uint32_t)kDecThreads : span * 2;
+        }
 
         PHASE_MARK(2);
         // ---- descriptors.  e_a packs the SOURCE of an element as (kind << 30) | position:
@@ -555,7 +569,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                 const uint32_t kind = a & kSrcMask, ap = a & kPosMask;
                 uint8_t *d = dst + o;
                 if (kind == kSrcIn) {
-                    const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= (uint64_t)wb + kDecWin + 16) ? cinp + (ap - wb) : src + ap;
+                    const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= staged_end) ? cinp + (ap - wb) : src + ap;
                     small_copy(d, sl, len);
                     S.e_done[e] = (uint16_t)round;
                     continue;
@@ -615,7 +629,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                     const uint32_t len = S.e_len[e];
                     if (len <= kThreadElem || len >= kLongLiteral) continue;
                     const uint32_t ap = S.e_a[e] & kPosMask;  // only literals are this long
-                    const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= (uint64_t)wb + kDecWin + 16) ? cinp + (ap - wb) : src + ap;
+                    const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= staged_end) ? cinp + (ap - wb) : src + ap;
                     lanes_copy<32>(dst + S.e_dst[e], sl, len, t & 31);
                     if ((t & 31) == 0) S.e_done[e] = 1;
                 }

@@ -116,6 +116,19 @@ int main(int argc, char **argv)
             for (int k = 0; k < 16; k++) v[b * 16 + k] = (k < 8 && b > 0) ? v[(b - 1) * 16 + k] : (uint8_t)rng();
         add("chain_depth", v);
     }
+    {
+        // dense stream: thousands of 4..7-byte copies out of a small dictionary -> far more elements per window than
+        // descriptor slots, so windows are cut short and the adaptive span shrinks and grows again
+        std::vector<uint8_t> dict(4096), v;
+        for (auto &b : dict) b = (uint8_t)rng();
+        v.insert(v.end(), dict.begin(), dict.end());
+        for (int r = 0; r < 30000; r++) {
+            int n = 4 + rng() % 4, at = rng() % (4096 - 8);
+            for (int i = 0; i < n; i++) v.push_back(dict[at + i]);
+        }
+        for (int r = 0; r < 20000; r++) v.push_back((uint8_t)rng());  // then literal-heavy again
+        add("dense_copies", v);
+    }
     // hand-made stream with every element kind (same bytes as tests/golden "all_kinds")
     {
         std::vector<uint8_t> s;
