@@ -203,7 +203,49 @@ __device__ __forceinline__ void small_copy(uint8_t *d, const uint8_t *s, uint32_
                 if (b + k < nw) d32[b + k] = __funnelshift_r(v[k], v[k + 1], 8 * mis);
         }
     } else {
-        for (uint32_t i = 0; i < len; i++) d[i] = s[i];
+        // any alignment (every stream a byte-granular encoder such as Google's produces): 32 bytes per pass; all
+        // source bytes are fetched first -- whole aligned words, plus single bytes for the two words that stick out
+        // at the ends -- then written; a byte-by-byte copy would wait for each load behind the store before it
+#pragma unroll 1
+        for (uint32_t base = 0; base < len; base += 32) {
+            const uint32_t n = len - base < 32u ? len - base : 32u;
+            const uint8_t *sp = s + base;
+            const uint32_t mis = (uint32_t)((uintptr_t)sp & 3);
+            const uint32_t *s32 = reinterpret_cast<const uint32_t *>(sp - mis);
+            const uint32_t nwords = (mis + n + 3) >> 2;           // aligned words touched, <= 9
+            uint32_t v[10];
+#pragma unroll
+            for (uint32_t k = 0; k < 9; k++) {
+                v[k] = 0;
+                if (k < nwords) {
+                    const bool inner = (k > 0 || mis == 0) && (4 * (k + 1) <= mis + n);  // every byte of the word is wanted
+                    if (inner) {
+                        v[k] = s32[k];
+                    } else {
+#pragma unroll
+                        for (uint32_t q = 0; q < 4; q++) {
+                            const uint32_t pos = 4 * k + q;  // byte position relative to the aligned base
+                            if (pos >= mis && pos < mis + n) v[k] |= (uint32_t)sp[pos - mis] << (8 * q);
+                        }
+                    }
+                }
+            }
+            v[9] = 0;
+            uint32_t u[8];
+#pragma unroll
+            for (uint32_t k = 0; k < 8; k++) u[k] = __funnelshift_r(v[k], v[k + 1], 8 * mis);
+            uint8_t *dp = d + base;
+            if ((((uintptr_t)dp | n) & 3) == 0) {
+                uint32_t *d32 = reinterpret_cast<uint32_t *>(dp);
+#pragma unroll
+                for (uint32_t k = 0; k < 8; k++)
+                    if (4 * k < n) d32[k] = u[k];
+            } else {
+#pragma unroll
+                for (uint32_t i = 0; i < 32; i++)
+                    if (i < n) dp[i] = (uint8_t)(u[i >> 2] >> (8 * (i & 3)));
+            }
+        }
     }
 }
 

@@ -76,9 +76,13 @@ def main():
         e1.record(st)
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
+    ph = lib.decode_phase_cycles(reset=True)
+    tot = max(sum(ph.values()), 1)
+    phase_share = {k: round(v / tot, 4) for k, v in ph.items()}
+    counts = getattr(lib, 'last_decode_counts', None)
     print(json.dumps({"what": "K7 on reference-encoded 4K Hap Q frames (Google Snappy), device-resident batch",
                       "frames": F, "chunks": K, "ms_per_batch": ms, "ratio": float(used.double().mean()) / n,
-                      "texture_GBps": F * n / ms / 1e6, "rgba_equiv_GBps": F * 4 * W * H / ms / 1e6, "stream_stats_chunk3": stats}))
+                      "texture_GBps": F * n / ms / 1e6, "rgba_equiv_GBps": F * 4 * W * H / ms / 1e6, "phase_share": phase_share, "counts_over_8_batches": counts}))
 
 
 if __name__ == "__main__":
