@@ -616,11 +616,48 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                     S.e_done[e] = (uint16_t)round;
                     continue;
                 }
+                if (kind == kSrcOut) {
+                    // A plain copy.  Its source bytes either lie in earlier windows (final), or they are the output of
+                    // producers of this window.  It does not have to wait for those producers to RUN: a literal's
+                    // bytes are in the input, a resolved copy's bytes are wherever that copy reads them -- so the
+                    // source range is walked producer by producer and each piece is pulled from where it really is.
+                    // Only a piece whose producer is itself unresolved (or periodic) has to wait for a later round.
+                    bool ok = true;
+                    uint32_t x = ap;
+                    const uint32_t x_end = ap + len;
+                    if (x < d0) {
+                        const uint32_t n0 = x_end <= d0 ? len : d0 - x;
+                        small_copy(d, dst + x, n0);
+                        x += n0;
+                    }
+                    if (x < x_end) {
+                        uint32_t lo2 = 0, hi2 = e;  // last element with e_dst <= x; the producer is before e
+                        while (hi2 - lo2 > 1) {
+                            uint32_t m = (lo2 + hi2) >> 1;
+                            if (S.e_dst[m] <= x) lo2 = m; else hi2 = m;
+                        }
+                        for (uint32_t f = lo2; x < x_end; f++) {
+                            const uint32_t fd = S.e_dst[f], fl = S.e_len[f];
+                            const uint32_t x1 = x_end < fd + fl ? x_end : fd + fl;
+                            const uint32_t fa = S.e_a[f], fk = fa & kSrcMask, fp = (fa & kPosMask) + (x - fd);
+                            const uint32_t df = S.e_done[f];
+                            const uint8_t *from;
+                            if (df != 0 && df < round) from = dst + x;                      // producer already ran
+                            else if (fk == kSrcIn) from = src + fp;                          // literal bytes: the input
+                            else if (fk == kSrcOut && fp + (x1 - x) <= d0) from = dst + fp;  // resolved copy: its source
+                            else { ok = false; break; }
+                            small_copy(d + (x - ap), from, x1 - x);
+                            x = x1;
+                        }
+                    }
+                    if (!ok) { pending = 1; continue; }
+                    S.e_done[e] = (uint16_t)round;
+                    continue;
+                }
                 const uint32_t base = S.e_b[e];
                 const uint32_t rel = o - base;  // position of this element inside its same-offset run
                 uint32_t need_lo, need_hi;      // bytes this element reads
-                if (kind == kSrcOut) { need_lo = ap; need_hi = ap + len; }
-                else if (rel + len <= ap) { need_lo = o - ap; need_hi = need_lo + len; }
+                if (rel + len <= ap) { need_lo = o - ap; need_hi = need_lo + len; }
                 else { need_lo = base - ap; need_hi = base; }
                 if (need_hi > d0) {
                     bool ready = true;
@@ -636,9 +673,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                     }
                     if (!ready) { pending = 1; continue; }
                 }
-                if (kind == kSrcOut) {
-                    small_copy(d, dst + ap, len);
-                } else if (rel + len <= ap) {
+                if (rel + len <= ap) {
                     small_copy(d, dst + (o - ap), len);
                 } else {
                     const uint32_t off = ap;
