@@ -54,6 +54,28 @@ __device__ __forceinline__ int hap_dp4a_us(uint32_t a, uint32_t b, int c)
 
 HAP_HD int hap_clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
 
+// Three-input min/max, clamp(a+b, 0, c) and saturate: single instructions on sm_100a (VIMNMX3, FMNMX3,
+// VIADDMNMX.RELU, FFMA.SAT); plain C++ on the host so that the CPU twin computes the same values.
+#if defined(HAPB200_EMU) || !defined(__CUDA_ARCH__)
+HAP_HD int hap_max3(int a, int b, int c) { int m = a > b ? a : b; return m > c ? m : c; }
+HAP_HD int hap_min3(int a, int b, int c) { int m = a < b ? a : b; return m < c ? m : c; }
+HAP_HD int hap_addmin_relu(int a, int b, int c) { int s = a + b; s = s < c ? s : c; return s < 0 ? 0 : s; }
+#else
+__device__ __forceinline__ int hap_max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
+__device__ __forceinline__ int hap_min3(int a, int b, int c) { return __vimin3_s32(a, b, c); }
+__device__ __forceinline__ int hap_addmin_relu(int a, int b, int c) { return __viaddmin_s32_relu(a, b, c); }
+#endif
+HAP_HD float hap_fmax3(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }
+HAP_HD float hap_fmin3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
+HAP_HD float hap_sat(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+#if defined(HAPB200_EMU) || !defined(__CUDA_ARCH__)
+HAP_HD uint32_t hap_float_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+#else
+__device__ __forceinline__ uint32_t hap_float_bits(float f) { return __float_as_uint(f); }
+#endif
+constexpr float kRoundMagic = 12582912.0f;      // 1.5 * 2^23: x + magic rounds x to the nearest integer (ties to even) ...
+constexpr uint32_t kRoundMagicBits = 0x4B400000u;  // ... which then sits in the low mantissa bits
+
 // ---- BC4 / RGTC1: 16 values -> 8 bytes ------------------------------------------------------------
 // 8-value mode (a0 > a1): palette a0, a1, then 6 interpolants (decoder: ((8-i)a0 + (i-1)a1)/7).
 // Endpoints are the block's max/min (a least-squares refinement of them was measured to change nothing);
@@ -62,53 +84,55 @@ HAP_HD int hap_clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi 
 // floor(q/7) == (q*9363)>>16 exactly (checked exhaustively)
 HAP_HD int bc4_level_value(int L, int a0, int a1) { return a1 + (int)(((uint32_t)(L * (a0 - a1)) * 9363u) >> 16); }
 
-// a0 > a1.  level L in 0..7 counted from a1 (min) upwards.  The eight palette values are computed once; a texel's
-// nearest level is the number of mid-points (p[L] + p[L+1]) / 2 it reaches -- seven compare-and-add per texel, no
-// division, no indexed array.
-// vq = the values in QUARTER units (4*v for plain 8-bit input; R+2G+B for luma, which keeps the two bits
-// that rounding Y to 8 bits throws away and so picks the level nearest to the true luma).
-HAP_HD void bc4_indices(const int vq[16], int a0, int a1, uint32_t &bits_lo, uint32_t &bits_hi)
+// ---- BC4 ------------------------------------------------------------------------------------------
+// v[t] = the value in 1/UNIT steps, UNIT a multiple of 7 (UNIT = 7: 7 * alpha; UNIT = 28: 7 * (R + 2G + B), luma
+// with the two bits kept that rounding Y to 8 bits throws away -- the factors ride for free in the DP4A weights);
+// vmax / vmin = max / min of v.  Endpoints = the rounded max and min of the block (a least-squares refinement of
+// them was measured to change nothing).
+// A texel's level L (0 = the min end ... 7 = the max end) is the nearest of the 8 palette values.  The decoder's
+// palette truncates: value(L) = min + floor(L d / 7), i.e. the ideal ramp minus 0/7 .. 6/7 of a grey level, 3/7 on
+// average -- so the texel is moved UP by 3/7 (exactly 3 UNIT/7 here) before it is rounded onto the ideal ramp.
+// That is one VIADDMNMX (clamp(v - UNIT min + 3 UNIT/7, 0, range)), one fixed-point multiply and one shift per
+// texel instead of seven threshold compares (measured against the exhaustive choice: see test_block_quality_cpu).
+// Levels are packed 8 to a word and turned into DXT index numbering on all eight 3-bit fields at once.
+HAP_HD uint32_t bc4_levels_to_indices8(uint32_t levels)
 {
-    int p[8], s2[7];
-#pragma unroll
-    for (int L = 0; L < 8; L++) p[L] = bc4_level_value(L, a0, a1);
-#pragma unroll
-    for (int L = 0; L < 7; L++) s2[L] = 4 * (p[L] + p[L + 1]);  // mid-point in eighths (v2 below is 8 * value)
-    // DXT index by level: 0 -> 1 (a1), 1..6 -> 7..2, 7 -> 0 (a0); packed 3 bits per level
-    const uint32_t kIndexOfLevel = 1u | (7u << 3) | (6u << 6) | (5u << 9) | (4u << 12) | (3u << 15) | (2u << 18) | (0u << 21);
-    uint64_t bits = 0;
-#pragma unroll
-    for (int t = 0; t < 16; t++) {
-        const int v2 = 2 * vq[t];
-        int L = 0;
-#pragma unroll
-        for (int k = 0; k < 7; k++) L += v2 > s2[k] ? 1 : 0;  // a tie goes to the lower level: the palette values are truncated, so its exact value is the nearer one
-        bits |= (uint64_t)((kIndexOfLevel >> (3 * L)) & 7u) << (3 * t);
-    }
-    bits_lo = (uint32_t)bits;
-    bits_hi = (uint32_t)(bits >> 32);
+    const uint32_t x = levels ^ 0xFFFFFFu;                            // M = 7 - L: 0 = the max end (a0)
+    const uint32_t m0 = 0x249249u;                                     // bit 0 of each of the eight fields
+    const uint32_t x1 = x >> 1, x2 = x >> 2;
+    const uint32_t sevens = x & x1 & x2 & m0, zeros = ~(x | x1 | x2) & m0;
+    return (x & ~(sevens * 7u)) + m0 - zeros;                         // M: 0 -> 0, 7 -> 1, else M + 1
 }
 
-// v: the 8-bit values (endpoints = their min/max); vq: the same in quarter units, see bc4_indices
-HAP_HD Block8 encode_bc4_block(const int v[16], const int vq[16])
+template <int UNIT>
+HAP_HD Block8 encode_bc4_scaled(const int v[16], int vmax, int vmin)
 {
-    int mn = 255, mx = 0;
-#pragma unroll
-    for (int t = 0; t < 16; t++) {
-        mn = v[t] < mn ? v[t] : mn;
-        mx = v[t] > mx ? v[t] : mx;
-    }
+    static_assert(UNIT % 7 == 0, "UNIT carries the factor 7");
+    const int mx = (int)((uint32_t)(vmax + UNIT / 2) / (uint32_t)UNIT), mn = (int)((uint32_t)(vmin + UNIT / 2) / (uint32_t)UNIT);
     Block8 out;
-    if (mx == mn) {
-        // a0 == a1 selects the 6-value mode; index 0 decodes to a0 in both modes
-        out.lo = (uint32_t)mx | ((uint32_t)mn << 8);
-        out.hi = 0;
-        return out;
+    out.lo = (uint32_t)mx | ((uint32_t)mn << 8);
+    out.hi = 0;
+    if (mx == mn) return out;  // a0 == a1 selects the 6-value mode; index 0 decodes to a0 in both modes
+    const int d = mx - mn, range = UNIT * d;
+    const int r7 = d - 7 * (int)(((uint32_t)d * 9363u) >> 16);                       // d mod 7 (d <= 255)
+    // integer inputs (UNIT = 7): 3/7 is exact for every d.  Quarter-step inputs: the best constant per d mod 7,
+    // 0, 8, 9, 11, 11, 9, 8 twenty-eighths (0 when d is a multiple of 7: nothing is truncated then)
+    const int bias = UNIT % 28 == 0 ? (int)((0x89BB980u >> (4 * r7)) & 15u) * (UNIT / 28) : 3 * (UNIT / 7);
+    const int c0 = bias - UNIT * mn;
+    // 7 * 2^20 / range, rounded: (t * mul + 2^19) >> 20 is round(7 t / range) for every t <= range (<= 7140)
+    const int mul = (int)(7340032.0f * (1.0f / (float)range) + 0.5f);
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const uint32_t La = (uint32_t)(hap_addmin_relu(v[t], c0, range) * mul + (1 << 19)) >> 20;
+        const uint32_t Lb = (uint32_t)(hap_addmin_relu(v[t + 8], c0, range) * mul + (1 << 19)) >> 20;
+        a += La << (3 * t);
+        b += Lb << (3 * t);
     }
-    uint32_t lo, hi;
-    bc4_indices(vq, mx, mn, lo, hi);
-    out.lo = (uint32_t)mx | ((uint32_t)mn << 8) | (lo << 16);
-    out.hi = (lo >> 16) | (hi << 16);
+    a = bc4_levels_to_indices8(a);
+    b = bc4_levels_to_indices8(b);
+    out.lo |= a << 16;
+    out.hi = (a >> 16) | (b << 8);
     return out;
 }
 
@@ -372,37 +396,157 @@ HAP_HD Block8 encode_colour_block(const float r[16], const float g[16], const fl
 #endif
 constexpr float kYCoCgMetricCo = 1.41421356f, kYCoCgMetricCg = 1.73205081f;
 
-// Returns the 5-bit scale code; cr/cg_ come back pre-multiplied by the metric above.
-HAP_HD int ycocg_block(const uint32_t px[16], float cr[16], float cg_[16], float cb[16], int yv[16], int yq[16])
+// One channel of the endpoint pair onto its 5- or 6-bit grid.  For fixed clusters the squared error separates per
+// channel, E(a,b) = a^2 A2 + b^2 B2 + 2ab AB - 2a AX - 2b BX, so floor/ceil of both ends are tried (4 candidates)
+// with the values the DECODER expands them to.  a, b: storage units 0..255; the sums are taken about `off`.
+HAP_HD void snap_pair(float a, float b, float off, float A2, float B2, float AB, float AX, float BX, float levels,
+                      uint32_t &ga_out, uint32_t &gb_out)
 {
-    int m2 = 0, m4 = 0;
-    int co2v[16], cg4v[16];
-#pragma unroll
-    for (int t = 0; t < 16; t++) {
-        // texel bytes are R,G,B,A: weights (1,0,-1,0), (-1,2,-1,0) and (1,2,1,0) as signed bytes
-        int co2 = hap_dp4a_us(px[t], 0x00FF0001u, 0), cg4 = hap_dp4a_us(px[t], 0x00FF02FFu, 0);
-        co2v[t] = co2;
-        cg4v[t] = cg4;
-        yq[t] = hap_dp4a_us(px[t], 0x00010201u, 0);  // R + 2G + B = 4 * luma
-        yv[t] = (yq[t] + 2) >> 2;
-        int a2 = co2 < 0 ? -co2 : co2, a4 = cg4 < 0 ? -cg4 : cg4;
-        m2 = a2 > m2 ? a2 : m2;
-        m4 = a4 > m4 ? a4 : m4;
-    }
+    const float to_grid = levels * (1.0f / 255.0f), from_grid = 255.0f / levels;
+    const float ga0 = floorf(a * to_grid), gb0 = floorf(b * to_grid);
+    const float ga1 = fminf(ga0 + 1.0f, levels), gb1 = fminf(gb0 + 1.0f, levels);
+    // the decoder expands by bit replication, which equals round(g * 255 / levels) for 5 and 6 bits
+    const float ca0 = floorf(hap_fma(ga0, from_grid, 0.5f)) - off, ca1 = floorf(hap_fma(ga1, from_grid, 0.5f)) - off;
+    const float cb0 = floorf(hap_fma(gb0, from_grid, 0.5f)) - off, cb1 = floorf(hap_fma(gb1, from_grid, 0.5f)) - off;
+    const float m2AX = -2.0f * AX, m2BX = -2.0f * BX, AB2 = 2.0f * AB;
+    const float ua0 = ca0 * hap_fma(ca0, A2, m2AX), ua1 = ca1 * hap_fma(ca1, A2, m2AX);
+    const float ub0 = cb0 * hap_fma(cb0, B2, m2BX), ub1 = cb1 * hap_fma(cb1, B2, m2BX);
+    const float e00 = hap_fma(AB2 * ca0, cb0, ua0 + ub0), e10 = hap_fma(AB2 * ca1, cb0, ua1 + ub0);
+    const float e01 = hap_fma(AB2 * ca0, cb1, ua0 + ub1), e11 = hap_fma(AB2 * ca1, cb1, ua1 + ub1);
+    float best = e00, ga = ga0, gb = gb0;
+    if (e10 < best) { best = e10; ga = ga1; gb = gb0; }
+    if (e01 < best) { best = e01; ga = ga0; gb = gb1; }
+    if (e11 < best) { ga = ga1; gb = gb1; }
+    ga_out = (uint32_t)(int)ga;
+    gb_out = (uint32_t)(int)gb;
+}
+
+// The chroma half of a scaled-YCoCg block: 16 (Co, Cg) pairs -> BC1 colour block (R' = Co', G' = Cg', B' = scale
+// code).  co2 = R - B (half units), cg4 = -R + 2G - B (quarter units), with their max / min over the block.
+//
+// Everything is a fit in the 2-D plane of (Co', Cg') weighted by the metric above, done on the UNROUNDED chroma
+// (the stored texel would be its rounding; the fit is against what the decoder should reproduce) and about the
+// centre of the block's bounding box, which keeps the fp32 moment sums exact enough for a one-pass covariance:
+//   moments -> 2x2 covariance -> principal axis in closed form -> extent along it -> 4 clusters by projection
+//   -> the 2x2 least-squares system for the two endpoints given those clusters (the normal equations cluster
+//   fit solves, for the partition the axis implies) -> per-channel grid search (snap_pair) -> indices by
+//   projection onto the decoder's palette segment.
+// Cluster sums are kept in terms of q = 0..3 (the cluster number): with beta = q/3, alpha = 1 - beta all nine
+// sums of the normal equations follow from sum(q), sum(q^2), sum(q x), sum(q y) and the plain moments.
+HAP_HD Block8 encode_ycocg_chroma(const int co2[16], const int cg4[16], int co_hi, int co_lo, int cg_hi, int cg_lo)
+{
+    const int m2 = co_hi > -co_lo ? co_hi : -co_lo, m4 = cg_hi > -cg_lo ? cg_hi : -cg_lo;
     int scale = 1;
     if (m2 * 4 <= 254 && m4 * 4 <= 508) scale = 4;
     else if (m2 * 2 <= 254 && m4 * 2 <= 508) scale = 2;
-    const float sb = (float)((scale - 1) << 3);
+    const uint32_t blue5 = (uint32_t)(scale - 1);  // 5-bit code 0, 1 or 3: expands to B' = 0, 8, 24
+    const float fs = (float)scale;
+    // x = (Co' - offx) * metric, Co' = co2 * scale / 2 + 128
+    const float cx = 0.5f * (float)(co_hi + co_lo), cy = 0.5f * (float)(cg_hi + cg_lo);
+    const float kx = fs * (0.5f * kYCoCgMetricCo), ky = fs * (0.25f * kYCoCgMetricCg);
+    const float bx0 = -cx * kx, by0 = -cy * ky;
+    const float offx = hap_fma(cx, 0.5f * fs, 128.0f), offy = hap_fma(cy, 0.25f * fs, 128.0f);
+    const float imx = 1.0f / kYCoCgMetricCo, imy = 1.0f / kYCoCgMetricCg;
+    float x[16], y[16];
+    float Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f;
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        // round half up of co2*scale/2 and cg4*scale/4 (arithmetic shift floors)
-        int co = (co2v[t] * scale + 1) >> 1;
-        int cg = (cg4v[t] * scale + 2) >> 2;
-        cr[t] = (float)hap_clampi(co + 128, 0, 255) * kYCoCgMetricCo;
-        cg_[t] = (float)hap_clampi(cg + 128, 0, 255) * kYCoCgMetricCg;
-        cb[t] = sb;
+        x[t] = hap_fma((float)co2[t], kx, bx0);
+        y[t] = hap_fma((float)cg4[t], ky, by0);
+        Sx += x[t]; Sy += y[t];
+        Sxx = hap_fma(x[t], x[t], Sxx); Sxy = hap_fma(x[t], y[t], Sxy); Syy = hap_fma(y[t], y[t], Syy);
     }
-    return scale - 1;  // 5-bit blue code 0, 1 or 3: expands to B' = 0, 8, 24
+    const float cxx = hap_fma(-0.0625f * Sx, Sx, Sxx), cxy = hap_fma(-0.0625f * Sx, Sy, Sxy), cyy = hap_fma(-0.0625f * Sy, Sy, Syy);
+
+    uint32_t a5r, a6g, b5r, b6g;
+    bool fitted = false;
+    if (cxx + cyy >= 0.5f) {
+        // principal axis of [[cxx, cxy], [cxy, cyy]]: eigenvector of the larger eigenvalue, closed form
+        const float hd = 0.5f * (cxx - cyy);
+        const float rad = sqrtf(hap_fma(hd, hd, cxy * cxy));
+        float vx = hd >= 0.f ? hd + rad : cxy, vy = hd >= 0.f ? cxy : rad - hd;
+        const float vv0 = hap_fma(vx, vx, vy * vy);
+        if (vv0 < 1e-12f) { vx = 1.0f; vy = 0.0f; }  // isotropic spread: any axis
+        // extent along the axis
+        float d[16];
+#pragma unroll
+        for (int t = 0; t < 16; t++) d[t] = hap_fma(x[t], vx, y[t] * vy);
+        float tmin = d[0], tmax = d[0];
+#pragma unroll
+        for (int t = 1; t < 15; t += 2) { tmin = hap_fmin3(tmin, d[t], d[t + 1]); tmax = hap_fmax3(tmax, d[t], d[t + 1]); }
+        tmin = fminf(tmin, d[15]); tmax = fmaxf(tmax, d[15]);
+        const float ext = tmax - tmin;
+        if (ext > 1e-6f) {
+            // clusters: q = round(3 (d - tmin) / ext) is 0..3 by construction, no clamp
+            const float sc = 3.0f * (1.0f / ext);
+            const float c0 = -tmin * sc;
+            float Sq = 0.f, Sqq = 0.f, Sqx = 0.f, Sqy = 0.f;
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+                const float q = rintf(hap_fma(d[t], sc, c0));
+                Sq += q; Sqq = hap_fma(q, q, Sqq); Sqx = hap_fma(q, x[t], Sqx); Sqy = hap_fma(q, y[t], Sqy);
+            }
+            const float B2 = Sqq * (1.0f / 9.0f), AB = hap_fma(Sq, 1.0f / 3.0f, -B2), A2 = 16.0f - hap_fma(Sq, 2.0f / 3.0f, -B2);
+            const float BXx = Sqx * (1.0f / 3.0f), BXy = Sqy * (1.0f / 3.0f), AXx = Sx - BXx, AXy = Sy - BXy;
+            const float det = hap_fma(A2, B2, -(AB * AB));
+            float eax, eay, ebx, eby;  // endpoints, metric space about the centre
+            if (det >= 1e-4f) {
+                const float idet = 1.0f / det;
+                eax = hap_fma(AXx, B2, -(BXx * AB)) * idet; ebx = hap_fma(BXx, A2, -(AXx * AB)) * idet;
+                eay = hap_fma(AXy, B2, -(BXy * AB)) * idet; eby = hap_fma(BXy, A2, -(AXy * AB)) * idet;
+            } else {
+                const float ivv = 1.0f / hap_fma(vx, vx, vy * vy);
+                eax = vx * (tmin * ivv); eay = vy * (tmin * ivv); ebx = vx * (tmax * ivv); eby = vy * (tmax * ivv);
+            }
+            // storage units, then the grid
+            const float ar = fminf(fmaxf(hap_fma(eax, imx, offx), 0.f), 255.f), br = fminf(fmaxf(hap_fma(ebx, imx, offx), 0.f), 255.f);
+            const float ag = fminf(fmaxf(hap_fma(eay, imy, offy), 0.f), 255.f), bg = fminf(fmaxf(hap_fma(eby, imy, offy), 0.f), 255.f);
+            if (det >= 1e-4f) {
+                snap_pair(ar, br, offx, A2, B2, AB, AXx * imx, BXx * imx, 31.0f, a5r, b5r);
+                snap_pair(ag, bg, offy, A2, B2, AB, AXy * imy, BXy * imy, 63.0f, a6g, b6g);
+            } else {
+                a5r = (uint32_t)(int)floorf(hap_fma(ar, 31.0f / 255.0f, 0.5f)); b5r = (uint32_t)(int)floorf(hap_fma(br, 31.0f / 255.0f, 0.5f));
+                a6g = (uint32_t)(int)floorf(hap_fma(ag, 63.0f / 255.0f, 0.5f)); b6g = (uint32_t)(int)floorf(hap_fma(bg, 63.0f / 255.0f, 0.5f));
+            }
+            fitted = true;
+        }
+    }
+    if (!fitted) {
+        // (nearly) one chroma: bracket it with its grid neighbours so the 4 palette entries straddle it
+        const float fr = fminf(fmaxf(hap_fma(Sx * 0.0625f, imx, offx), 0.f), 255.f), fg = fminf(fmaxf(hap_fma(Sy * 0.0625f, imy, offy), 0.f), 255.f);
+        a5r = (uint32_t)(int)floorf(fr * (31.0f / 255.0f)); b5r = (uint32_t)(int)ceilf(fr * (31.0f / 255.0f));
+        a6g = (uint32_t)(int)floorf(fg * (63.0f / 255.0f)); b6g = (uint32_t)(int)ceilf(fg * (63.0f / 255.0f));
+    }
+    uint32_t c0 = (a5r << 11) | (a6g << 5) | blue5, c1 = (b5r << 11) | (b6g << 5) | blue5;
+    Block8 out;
+    out.lo = c0 | (c1 << 16);
+    out.hi = 0;  // index 0 = c0 in either mode
+    if (c0 == c1) return out;
+    if (c0 < c1) {
+        uint32_t tmp;
+        tmp = c0; c0 = c1; c1 = tmp;
+        tmp = a5r; a5r = b5r; b5r = tmp;
+        tmp = a6g; a6g = b6g; b6g = tmp;
+        out.lo = c0 | (c1 << 16);
+    }
+    // indices: position along the decoder's palette segment P0 -> P1, saturated to its ends, rounded to thirds.
+    // The rounded level k = 0..3 sits in the low mantissa bits of (3w + magic); all sixteen are summed into one word
+    // as k << 2t (the magic's own bits add up to a constant that is taken off once).
+    const float p0x = ((float)expand5(a5r) - offx) * kYCoCgMetricCo, p0y = ((float)expand6(a6g) - offy) * kYCoCgMetricCg;
+    const float p1x = ((float)expand5(b5r) - offx) * kYCoCgMetricCo, p1y = ((float)expand6(b6g) - offy) * kYCoCgMetricCg;
+    const float ex = p1x - p0x, ey = p1y - p0y;
+    const float iee = 1.0f / hap_fma(ex, ex, ey * ey);
+    const float wx = ex * iee, wy = ey * iee, w0 = -hap_fma(p0x, wx, p0y * wy);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        const float w = hap_sat(hap_fma(x[t], wx, hap_fma(y[t], wy, w0)));
+        acc += hap_float_bits(hap_fma(w, 3.0f, kRoundMagic)) << (2 * t);
+    }
+    const uint32_t k = acc - kRoundMagicBits * 0x55555555u;
+    // level along the segment -> DXT numbering (0 = c0, 1 = c1, 2, 3 in between): 0,1,2,3 -> 0,2,3,1
+    out.hi = (((k ^ (k >> 1)) & 0x55555555u) << 1) | ((k >> 1) & 0x55555555u);
+    return out;
 }
 
 // A block whose 16 texels are one colour (letterbox bars, graphics, clipped highlights -- common in real
@@ -470,15 +614,21 @@ HAP_HD Block8 encode_dxt1(const uint32_t px[16])
     return encode_colour_block<HAP_RGB_FIT>(r, g, b);
 }
 
+HAP_HD Block8 encode_rgtc1_alpha(const uint32_t px[16])
+{
+    int a7[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) a7[t] = hap_dp4a_us(px[t], 0x07000000u, 0);  // 7 * alpha
+    int hi = a7[0], lo = a7[0];
+#pragma unroll
+    for (int t = 1; t < 15; t += 2) { hi = hap_max3(hi, a7[t], a7[t + 1]); lo = hap_min3(lo, a7[t], a7[t + 1]); }
+    hi = hap_max3(hi, a7[15], a7[15]); lo = hap_min3(lo, a7[15], a7[15]);
+    return encode_bc4_scaled<7>(a7, hi, lo);
+}
+
 HAP_HD void encode_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colour)
 {
-    int a[16];
-#pragma unroll
-    for (int t = 0; t < 16; t++) a[t] = (int)(px[t] >> 24);
-    int aq[16];
-#pragma unroll
-    for (int t = 0; t < 16; t++) aq[t] = 4 * a[t];
-    alpha = encode_bc4_block(a, aq);
+    alpha = encode_rgtc1_alpha(px);
     colour = encode_dxt1(px);
 }
 
@@ -496,23 +646,26 @@ HAP_HD void encode_ycocg_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colo
         colour = encode_flat_colour(co, cg, (scale - 1) << 3, scale - 1, 2.0f, 3.0f, 1.0f);
         return;
     }
-    float r[16], g[16], b[16];
-    int y[16];
-    int yq[16];
-    const int code = ycocg_block(px, r, g, b, y, yq);
-    alpha = encode_bc4_block(y, yq);
-    colour = encode_colour_block<HAP_YCOCG_FIT, false>(r, g, b, code, kYCoCgMetricCo, kYCoCgMetricCg, 1.0f);
-}
-
-HAP_HD Block8 encode_rgtc1_alpha(const uint32_t px[16])
-{
-    int a[16];
+    // texel bytes are R,G,B,A: weights (1,0,-1,0), (-1,2,-1,0) and 7 * (1,2,1,0) as signed bytes, one DP4A each
+    int co2[16], cg4[16], y28[16];
 #pragma unroll
-    for (int t = 0; t < 16; t++) a[t] = (int)(px[t] >> 24);
-    int aq[16];
+    for (int t = 0; t < 16; t++) {
+        co2[t] = hap_dp4a_us(px[t], 0x00FF0001u, 0);
+        cg4[t] = hap_dp4a_us(px[t], 0x00FF02FFu, 0);
+        y28[t] = hap_dp4a_us(px[t], 0x00070E07u, 0);  // 7 (R + 2G + B) = 28 * luma
+    }
+    int co_hi = co2[0], co_lo = co2[0], cg_hi = cg4[0], cg_lo = cg4[0], y_hi = y28[0], y_lo = y28[0];
 #pragma unroll
-    for (int t = 0; t < 16; t++) aq[t] = 4 * a[t];
-    return encode_bc4_block(a, aq);
+    for (int t = 1; t < 15; t += 2) {
+        co_hi = hap_max3(co_hi, co2[t], co2[t + 1]); co_lo = hap_min3(co_lo, co2[t], co2[t + 1]);
+        cg_hi = hap_max3(cg_hi, cg4[t], cg4[t + 1]); cg_lo = hap_min3(cg_lo, cg4[t], cg4[t + 1]);
+        y_hi = hap_max3(y_hi, y28[t], y28[t + 1]); y_lo = hap_min3(y_lo, y28[t], y28[t + 1]);
+    }
+    co_hi = hap_max3(co_hi, co2[15], co2[15]); co_lo = hap_min3(co_lo, co2[15], co2[15]);
+    cg_hi = hap_max3(cg_hi, cg4[15], cg4[15]); cg_lo = hap_min3(cg_lo, cg4[15], cg4[15]);
+    y_hi = hap_max3(y_hi, y28[15], y28[15]); y_lo = hap_min3(y_lo, y28[15], y28[15]);
+    alpha = encode_bc4_scaled<28>(y28, y_hi, y_lo);
+    colour = encode_ycocg_chroma(co2, cg4, co_hi, co_lo, cg_hi, cg_lo);
 }
 
 }  // namespace hapb200
