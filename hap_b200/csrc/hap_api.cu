@@ -301,6 +301,10 @@ unsigned long long HapB200KernelLaunchCount(void) { return g_launches.load(); }
 // CTAs by thread 0 of each; a profiling aid for kernel work, not part of the stable API.
 int HapB200DebugDecodePhaseCycles(unsigned long long *out, int n, int reset)
 {
+#ifndef HAPB200_DECODE_PHASE_CYCLES
+    (void)out; (void)n; (void)reset;
+    return -1;  // built without the counters
+#else
     unsigned long long h[8] = {0};
     if (cudaMemcpyFromSymbol(h, g_decode_phase_cycles, sizeof h) != cudaSuccess) { cudaGetLastError(); return -1; }
     for (int i = 0; i < n && i < 8; i++) out[i] = h[i];
@@ -312,6 +316,7 @@ int HapB200DebugDecodePhaseCycles(unsigned long long *out, int n, int reset)
         cudaMemcpyToSymbol(g_decode_counts, z, sizeof z);
     }
     return 8;
+#endif
 }
 
 void HapB200SetStageTiming(int enabled)

@@ -31,9 +31,10 @@ constexpr uint32_t kFragStoredRaw = 0xFFFFFFFFu;  // fragment size marker: chunk
 
 // Shared memory of one fragment.  Thread t owns the 8 consecutive words [8t, 8t+8) and keeps them (and every
 // per-word quantity) in registers; shared memory only carries what OTHER threads read: the data (random
-// match verification), the hash table, and the strip-boundary values of the per-word arrays.
+// match verification), the hash table, the strip-boundary values of the per-word arrays, and -- for the last
+// step, which re-distributes the words over the threads -- positions, run starts and distances.
 struct EncodeSmem {
-    uint32_t data[kFragWords + 8];                  // input words; reused as the output byte stream at the end
+    uint32_t data[kFragWords + 8];                  // input words
     union {
         uint32_t table[1 << kEncHashBits];          // first occurrence of every hashed word
         struct {
@@ -45,6 +46,7 @@ struct EncodeSmem {
     uint16_t db[kFragWords];                        // candidate distances (pong); later: run end, stored at the run start
     uint32_t warp_tot[kEncWarps];
     uint32_t total;
+    uint32_t out[(kFragCap + 3) / 4 + 2];           // the element stream
 };
 
 __device__ __forceinline__ uint32_t enc_hash(uint32_t w) { return (w * 0x9E3779B1u) >> (32 - kEncHashBits); }
@@ -61,9 +63,11 @@ __device__ __forceinline__ void store_strip16(uint16_t *arr, uint32_t base, cons
 }
 
 // Inclusive max / sum over the block of one value per thread; returns the exclusive prefix for this thread and
-// the block total.  Two barriers.
+// the block total.  Two barriers.  The 32 warp totals are scanned by every warp with shuffles (lane w holds the
+// total of warp w) instead of a 32-step loop over shared memory.
 __device__ __forceinline__ uint32_t enc_block_excl(uint32_t v, bool is_max, uint32_t *total, uint32_t *warp_tot)
 {
+    static_assert(kEncWarps == 32, "one warp total per lane");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t incl = v;
 #pragma unroll
@@ -75,20 +79,22 @@ __device__ __forceinline__ uint32_t enc_block_excl(uint32_t v, bool is_max, uint
     if (lane == 0) prev = 0;
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    uint32_t base = 0, tot = 0;
+    uint32_t wi = warp_tot[lane];
 #pragma unroll
-    for (int w = 0; w < kEncWarps; w++) {
-        uint32_t x = warp_tot[w];
-        if (w < warp) base = is_max ? (base > x ? base : x) : base + x;
-        tot = is_max ? (tot > x ? tot : x) : tot + x;
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(HAP_FULL_MASK, wi, d);
+        if (lane >= d) wi = is_max ? (wi > o ? wi : o) : wi + o;
     }
+    const uint32_t tot = __shfl_sync(HAP_FULL_MASK, wi, 31);
+    uint32_t base = __shfl_sync(HAP_FULL_MASK, wi, warp > 0 ? warp - 1 : 0);
+    if (warp == 0) base = 0;
     __syncthreads();
     *total = tot;
     return is_max ? (base > prev ? base : prev) : base + prev;
 }
 
 // One fragment: W words already in S.data AND in the caller's registers d[8] (words 8t..8t+7; W % 2 == 0,
-// W <= kFragWords) -> element stream written over S.data as bytes; returns its size (all threads).
+// W <= kFragWords) -> element stream written to S.out as bytes; returns its size (all threads).
 // period_words = DXT block size in words (2 or 4).
 // FULL = the fragment has all kFragWords words (31 of 32 fragments of a 1 MiB chunk): every per-word bounds test
 // folds away at compile time.
@@ -122,7 +128,10 @@ __device__ __forceinline__ uint32_t compress_fragment(EncodeSmem &S, const uint3
             const uint32_t w0 = i0 + 4 * b;
             if (w0 >= 4 && w0 + 4 <= W) {
                 bool rep;
-                if (b == 0) rep = S.data[w0 - 4] == d[0] && S.data[w0 - 3] == d[1] && S.data[w0 - 2] == d[2] && S.data[w0 - 1] == d[3];
+                if (b == 0) {
+                    const uint4 pv = *reinterpret_cast<const uint4 *>(&S.data[w0 - 4]);  // one 16-byte load: no bank conflict
+                    rep = pv.x == d[0] && pv.y == d[1] && pv.z == d[2] && pv.w == d[3];
+                }
                 else rep = d[0] == d[4] && d[1] == d[5] && d[2] == d[6] && d[3] == d[7];
                 if (rep) { dd[4 * b] = dd[4 * b + 1] = dd[4 * b + 2] = dd[4 * b + 3] = 4; }
             }
@@ -133,7 +142,10 @@ __device__ __forceinline__ uint32_t compress_fragment(EncodeSmem &S, const uint3
             const uint32_t w0 = i0 + 2 * b;
             if (w0 >= 2 && w0 + 2 <= W) {
                 bool rep;
-                if (b == 0) rep = S.data[w0 - 2] == d[0] && S.data[w0 - 1] == d[1];
+                if (b == 0) {
+                    const uint2 pv = *reinterpret_cast<const uint2 *>(&S.data[w0 - 2]);
+                    rep = pv.x == d[0] && pv.y == d[1];
+                }
                 else rep = d[2 * b - 2] == d[2 * b] && d[2 * b - 1] == d[2 * b + 1];
                 if (rep) { dd[2 * b] = dd[2 * b + 1] = 2; }
             }
@@ -237,16 +249,27 @@ __device__ __forceinline__ uint32_t compress_fragment(EncodeSmem &S, const uint3
         if (t == 0) S.total = tot;
     }
 
-    // 6. every word writes its own bytes; the stream overwrites S.data (every thread holds its words in registers)
-    uint8_t *out = reinterpret_cast<uint8_t *>(S.data);
+    // 6. every word writes its own bytes.  Ownership changes for this step: thread t takes words t, t + 1024, ...
+    //    so that the lanes of a warp write neighbouring bytes of the stream (with the strip layout they sit 32 bytes
+    //    apart, an 8-way bank conflict on each of four byte stores per word).  Positions, run starts and distances
+    //    travel through shared memory as 16-bit strips.  Inside a literal run the stream is the input words shifted
+    //    by (p & 3) bytes, so a word writes ONE aligned 32-bit word made of its last bytes and the next word's first
+    //    bytes; only the two ends of a run, headers and copy elements are written bytewise.
+    store_strip16(S.da, i0, pos);
+    store_strip16(S.u.h.b, i0, rs);
+    __syncthreads();
+    uint8_t *out = reinterpret_cast<uint8_t *>(S.out);
 #pragma unroll
-    for (int k = 0; k < kStrip; k++) {
-        if ((uint32_t)k >= nv) continue;
-        const uint32_t i = i0 + k;
-        uint32_t p = pos[k];
-        if (d2[k] == 0) {
-            if (i == rs[k]) {
-                const uint32_t len = 4u * (S.db[i] - i + 1);
+    for (int j = 0; j < kStrip; j++) {
+        const uint32_t i = t + (uint32_t)j * kEncThreads;
+        if (!FULL && i >= W) continue;
+        const uint32_t dist = S.u.h.a[i], rs_i = S.u.h.b[i];
+        uint32_t p = S.da[i];
+        if (dist == 0) {
+            const uint32_t w = S.data[i];
+            const uint32_t e = S.db[rs_i];   // last word of this literal run
+            if (i == rs_i) {
+                const uint32_t len = 4u * (e - i + 1);
                 if (len <= 60) {
                     out[p++] = (uint8_t)((len - 1) << 2);
                 } else if (len <= 256) {
@@ -258,15 +281,23 @@ __device__ __forceinline__ uint32_t compress_fragment(EncodeSmem &S, const uint3
                     out[p++] = (uint8_t)((len - 1) >> 8);
                 }
             }
-            const uint32_t w = d[k];
-            out[p] = (uint8_t)w;
-            out[p + 1] = (uint8_t)(w >> 8);
-            out[p + 2] = (uint8_t)(w >> 16);
-            out[p + 3] = (uint8_t)(w >> 24);
-        } else if (((i - rs[k]) & 15) == 0) {
-            const uint32_t left = S.db[rs[k]] - i + 1;        // words left in the run
+            const uint32_t sh = p & 3u;
+            if (sh == 0) {
+                *reinterpret_cast<uint32_t *>(out + p) = w;
+            } else {
+                const uint32_t a1 = (p & ~3u) + 4u;   // the aligned word that holds my last `sh` bytes
+                if (i == rs_i)
+                    for (uint32_t q = 0; q < 4u - sh; q++) out[p + q] = (uint8_t)(w >> (8 * q));
+                if (i < e) {
+                    *reinterpret_cast<uint32_t *>(out + a1) = __funnelshift_r(w, S.data[i + 1], 8 * (4u - sh));
+                } else {
+                    for (uint32_t q = 0; q < sh; q++) out[a1 + q] = (uint8_t)(w >> (8 * (4u - sh + q)));
+                }
+            }
+        } else if (((i - rs_i) & 15) == 0) {
+            const uint32_t left = S.db[rs_i] - i + 1;          // words left in the run
             const uint32_t len = 4u * (left < 16 ? left : 16);  // 4..64 bytes
-            const uint32_t off = 4u * d2[k];
+            const uint32_t off = 4u * dist;
             out[p] = (uint8_t)(2u | ((len - 1) << 2));          // copy with 2-byte offset
             out[p + 1] = (uint8_t)off;
             out[p + 2] = (uint8_t)(off >> 8);
@@ -349,7 +380,7 @@ __global__ void __launch_bounds__(kEncThreads) snappy_encode_fragments_kernel(
     const uint32_t total = W == (uint32_t)kFragWords ? compress_fragment<true>(S, d, W, sec.period_words)
                                                      : compress_fragment<false>(S, d, W, sec.period_words);
     uint8_t *o = scratch + (uint64_t)gfrag * kFragCap;
-    const uint32_t *o32s = reinterpret_cast<const uint32_t *>(S.data);
+    const uint32_t *o32s = S.out;
     uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
     for (uint32_t i = t; i < (total + 3) / 4; i += kEncThreads) o32[i] = o32s[i];
     if (t == 0) frag_size[gfrag] = total;

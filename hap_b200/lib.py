@@ -13,7 +13,8 @@ HapB200Codec_Hap1, HapB200Codec_Hap5, HapB200Codec_HapY, HapB200Codec_HapM, HapB
 
 
 def library_path() -> str:
-    return os.path.join(HERE, "libhap_b200.so")
+    # HAPB200_LIBRARY: another build of the same library (A/B measurements of kernel variants)
+    return os.environ.get("HAPB200_LIBRARY") or os.path.join(HERE, "libhap_b200.so")
 
 
 class HapB200(HapABI):
