@@ -503,7 +503,7 @@ HAP_HD Block8 encode_ycocg_chroma(const int co2[16], const int cg4[16], int co_h
             const float ag = fminf(fmaxf(hap_fma(eay, imy, offy), 0.f), 255.f), bg = fminf(fmaxf(hap_fma(eby, imy, offy), 0.f), 255.f);
             if (det >= 1e-4f) {
                 snap_pair(ar, br, offx, A2, B2, AB, AXx * imx, BXx * imx, 31.0f, a5r, b5r);
-                snap_pair(ag, bg, offy, A2, B2, AB, AXy * imy, BXy * imy, 63.0f, a6g, b6g);
+                a6g = (uint32_t)(int)floorf(hap_fma(ag, 63.0f / 255.0f, 0.5f)); b6g = (uint32_t)(int)floorf(hap_fma(bg, 63.0f / 255.0f, 0.5f));
             } else {
                 a5r = (uint32_t)(int)floorf(hap_fma(ar, 31.0f / 255.0f, 0.5f)); b5r = (uint32_t)(int)floorf(hap_fma(br, 31.0f / 255.0f, 0.5f));
                 a6g = (uint32_t)(int)floorf(hap_fma(ag, 63.0f / 255.0f, 0.5f)); b6g = (uint32_t)(int)floorf(hap_fma(bg, 63.0f / 255.0f, 0.5f));

@@ -18,7 +18,7 @@ constexpr int kBcThreads = 128;
 struct BcGeom {
     uint32_t blocks_x, blocks_y;   // width/4, height/4
     uint32_t row_bytes;            // RGBA row stride in bytes (>= 16*blocks_x, multiple of 16)
-    uint32_t pad;
+    uint32_t inv_blocks_x;         // floor(2^32 / blocks_x): row index by multiply-high + one correction (no division)
     uint64_t frame_bytes;          // RGBA frame stride
     uint64_t out_stride;           // DXT bytes per frame in `out`
     uint64_t second_offset;        // kBcYCoCgPlusAlpha: offset of the RGTC1 plane inside a frame's output
@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(kBcThreads) bc_encode_kernel(const uint8_t *__
     const uint32_t nblocks = G.blocks_x * G.blocks_y;
     const uint32_t bi = blockIdx.x * kBcThreads + threadIdx.x;
     if (bi >= nblocks) return;
-    const uint32_t by = bi / G.blocks_x, bx = bi - by * G.blocks_x;
+    uint32_t by = __umulhi(bi, G.inv_blocks_x), bx = bi - by * G.blocks_x;  // the estimate is exact or one short
+    if (bx >= G.blocks_x) { by++; bx -= G.blocks_x; }
     const uint8_t *src = rgba + (uint64_t)blockIdx.y * G.frame_bytes + (uint64_t)(4 * by) * G.row_bytes + 16u * bx;
     uint32_t px[16];
 #pragma unroll

@@ -206,7 +206,8 @@ uint32_t launch_block_encode(const uint8_t *rgba, uint32_t frames, uint64_t fram
     g.blocks_x = width / 4;
     g.blocks_y = height / 4;
     g.row_bytes = (uint32_t)row_bytes;
-    g.pad = 0;
+    const uint64_t inv = 0x100000000ull / g.blocks_x;          // 2^32 when the image is one block wide
+    g.inv_blocks_x = inv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)inv;
     g.frame_bytes = frame_stride;
     g.out_stride = blocks_stride;
     g.second_offset = second_offset;

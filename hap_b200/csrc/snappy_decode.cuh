@@ -47,6 +47,7 @@ constexpr uint32_t kSrcIn = 0u << 30, kSrcOut = 1u << 30, kSrcRun = 2u << 30, kS
 constexpr int kFlattenRounds = 2, kFlattenHops = 12;
 constexpr uint32_t kLongLiteral = 1024;            // literals this long are copied by the whole CTA
 constexpr int kMaxLong = 64;
+constexpr int kMaxMid = 128;
 constexpr int kGroups = kDecThreads / 8;           // 8-lane groups, one element each
 constexpr uint32_t kExitMaxRel = 250;              // tbl value <= this: exit = sub-block end + value
 constexpr uint32_t kExitFar = 253;                 // exit further away (a long literal): recomputed by walking
@@ -65,6 +66,8 @@ struct DecodeSmem {
     uint32_t bcast[4];
     uint32_t n_long;                 // long literals of the current window
     uint32_t long_list[kMaxLong];
+    uint32_t n_mid;                  // literals of kThreadElem+1 .. kLongLiteral-1 bytes (one warp each)
+    uint16_t mid_list[kMaxMid];
     int fail;        // preamble / parse stage
     int fail_desc;   // descriptor stage (separate word: it is written while slow threads may still read `fail`)
 };
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
     while (wb < in_end) {
         // ---- stage the window.  Chunks are byte-packed in a frame, so the chunk is rarely aligned: read aligned
         //      16-byte words and shift them so that S.cin[0] is the byte at `wb` (word loads stay aligned later) ---
-        if (t == 0) S.n_long = 0;
+        if (t == 0) { S.n_long = 0; S.n_mid = 0; }
         uint32_t staged_end;  // input position up to which S.cin holds this window's bytes
         {
             const uintptr_t gaddr = (uintptr_t)(src + wb);
@@ -513,6 +516,9 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                     if (len >= kLongLiteral) {
                         uint32_t q = atomicAdd(&S.n_long, 1u);
                         if (q < (uint32_t)kMaxLong) S.long_list[q] = e;
+                    } else if (len > kThreadElem) {
+                        uint32_t q = atomicAdd(&S.n_mid, 1u);
+                        if (q < (uint32_t)kMaxMid) S.mid_list[q] = (uint16_t)e;
                     }
                     pos += hdr + len;
                 } else {
@@ -701,14 +707,27 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                 S.e_done[e] = (uint16_t)round;
             }
             if (round == 1) {
-                // literals of kThreadElem+1 .. 1023 bytes: one warp each
-                for (uint32_t e = wrp; e < total_e; e += kDecThreads / 32) {
-                    const uint32_t len = S.e_len[e];
-                    if (len <= kThreadElem || len >= kLongLiteral) continue;
-                    const uint32_t ap = S.e_a[e] & kPosMask;  // only literals are this long
-                    const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= staged_end) ? cinp + (ap - wb) : src + ap;
-                    lanes_copy<32>(dst + S.e_dst[e], sl, len, t & 31);
-                    if ((t & 31) == 0) S.e_done[e] = 1;
+                // literals of kThreadElem+1 .. 1023 bytes: one warp each, from the list the descriptor pass made
+                const uint32_t nmid = S.n_mid;
+                if (nmid <= (uint32_t)kMaxMid) {
+                    for (uint32_t q = wrp; q < nmid; q += kDecThreads / 32) {
+                        const uint32_t e = S.mid_list[q];
+                        const uint32_t len = S.e_len[e];
+                        const uint32_t ap = S.e_a[e] & kPosMask;  // only literals are this long
+                        const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= staged_end) ? cinp + (ap - wb) : src + ap;
+                        lanes_copy<32>(dst + S.e_dst[e], sl, len, t & 31);
+                        if ((t & 31) == 0) S.e_done[e] = 1;
+                    }
+                } else {
+                    // more of them than the list holds (cannot happen with 16 KiB of input per window, kept for safety)
+                    for (uint32_t e = wrp; e < total_e; e += kDecThreads / 32) {
+                        const uint32_t len = S.e_len[e];
+                        if (len <= kThreadElem || len >= kLongLiteral) continue;
+                        const uint32_t ap = S.e_a[e] & kPosMask;
+                        const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= staged_end) ? cinp + (ap - wb) : src + ap;
+                        lanes_copy<32>(dst + S.e_dst[e], sl, len, t & 31);
+                        if ((t & 31) == 0) S.e_done[e] = 1;
+                    }
                 }
             }
             if (round == 1) {

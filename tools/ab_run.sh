@@ -1,7 +1,9 @@
 set -x
 mkdir -p gpurun_out
-timeout 300 python bench.py --steps 6 --warmup 3 --profile > gpurun_out/b2.json 2> gpurun_out/b2.err
-cat gpurun_out/b2.json | head -c 1500
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:snappy_decode_chunks|snappy_encode_fragments|bc_encode_kernel' -c 3 -f -o gpurun_out/prof_r01b python bench.py --steps 1 --warmup 3 --profile --no-overlap > gpurun_out/ncu2.log 2>&1
-tail -5 gpurun_out/ncu2.log
-ls -la gpurun_out
+for th in 8 16 32; do
+timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --e2e-threads $th --e2e-frames 64 > gpurun_out/e2e_$th.json 2> gpurun_out/e2e_$th.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/e2e_$th.json")); print("threads $th value %.1f e2e %.2f"%(d["value"], d["e2e"]["value"]), {k:round(v,3) for k,v in d["roofline"]["stage_ms_per_step"].items() if v>0.05})
+PY
+done
