@@ -67,7 +67,15 @@ struct Fiber {
     unsigned or_phase = 0;
 };
 
+struct NamedBar {
+    int arrived = 0;
+    unsigned gen = 0;
+    int acc = 0;
+    int res[2] = {0, 0};
+};
+
 struct Block {
+    NamedBar named[16];
     std::vector<Fiber> fibers;
     std::vector<Warp> warps;
     int arrived = 0;
@@ -108,6 +116,29 @@ inline void syncthreads() {
     } else {
         while (B.gen == g) yield();
     }
+}
+
+// bar.sync / bar.arrive / bar.red.or with a barrier number and a participant count
+inline void bar_sync(int id, int n) {
+    NamedBar &N = g_block()->named[id];
+    g_barriers()++;
+    unsigned g = N.gen;
+    if (++N.arrived >= n) { N.res[g & 1] = N.acc; N.acc = 0; N.arrived = 0; N.gen++; }
+    else while (N.gen == g) yield();
+}
+inline void bar_arrive(int id, int n) {
+    NamedBar &N = g_block()->named[id];
+    unsigned g = N.gen;
+    if (++N.arrived >= n) { N.res[g & 1] = N.acc; N.acc = 0; N.arrived = 0; N.gen++; }
+}
+inline int bar_or(int id, int n, int pred) {
+    NamedBar &N = g_block()->named[id];
+    g_barriers()++;
+    unsigned g = N.gen;
+    if (pred) N.acc = 1;
+    if (++N.arrived >= n) { N.res[g & 1] = N.acc; N.acc = 0; N.arrived = 0; N.gen++; }
+    else while (N.gen == g) yield();
+    return N.res[g & 1];
 }
 
 inline void warp_barrier(unsigned mask) {
@@ -229,6 +260,9 @@ static inline void __syncthreads() { emu::syncthreads(); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_barrier(mask); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
+static inline void hap_bar_sync(int id, int n) { emu::bar_sync(id, n); }
+static inline void hap_bar_arrive(int id, int n) { emu::bar_arrive(id, n); }
+static inline int hap_bar_or(int id, int n, int pred) { return emu::bar_or(id, n, pred); }
 
 static inline int __syncthreads_or(int pred) {
     emu::Block *B = emu::g_block();
