@@ -12,7 +12,6 @@
 #include "hap_host.h"
 #include "hap_parse.cuh"
 #include "snappy_decode.cuh"
-#include "snappy_decode_sparse.cuh"
 #include "snappy_encode.cuh"
 
 #include <atomic>
@@ -29,7 +28,7 @@ std::atomic<unsigned long long> g_launches{0};
 
 // Optional per-stage device timing (HapB200SetStageTiming): CUDA events around every kernel, on the
 // stream the kernel is launched on.  Off by default; bench.py turns it on for its roofline pass only.
-enum Stage { kStBcEncode = 0, kStSnappyEncode, kStPlan, kStPlace, kStParse, kStSnappyDecode, kStCollect, kStBcDecode, kStSnappyDecodeTables, kStCount };
+enum Stage { kStBcEncode = 0, kStSnappyEncode, kStPlan, kStPlace, kStParse, kStSnappyDecode, kStCollect, kStBcDecode, kStCount };
 struct StageTimer {
     std::mutex mu;
     bool on = false;
@@ -85,8 +84,6 @@ void runtime_init()
     }
     bool ok = cudaFuncSetAttribute(snappy_decode_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(DecodeSmem)) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(snappy_decode_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sizeof(WalkSmem)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(snappy_encode_fragments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(EncodeSmem)) == cudaSuccess;
     // NULL-stream calls and the host-pointer entry points run on the LEGACY default stream: it orders itself
@@ -248,16 +245,6 @@ uint32_t launch_block_decode(const uint8_t *blocks, const uint8_t *alpha, uint32
 }
 
 // device frames -> texture `index` of each; jobs scratch is allocated here
-// K7s then K7: every chunk goes to the sparse-stream kernel first; the table kernel takes over the chunks that one
-// marked kChunkNeedsTables (dense element streams, e.g. Google Snappy's on DXT5) from where it stopped, and returns
-// at once for all the others.
-void launch_chunk_decode(ChunkJob *jobs, int njobs, cudaStream_t st)
-{
-    HAP_KLAUNCH(kStSnappyDecode, snappy_decode_sparse_kernel, dim3((unsigned)njobs), dim3(kDecThreads), sizeof(WalkSmem), st, jobs, njobs);
-    HAP_KLAUNCH(kStSnappyDecodeTables, snappy_decode_chunks_kernel, dim3((unsigned)njobs), dim3(kDecThreads), sizeof(DecodeSmem), st, jobs,
-                njobs, 1);
-}
-
 uint32_t launch_decode_batch(const uint8_t *in, uint32_t frames, uint64_t in_stride, const unsigned long long *in_bytes,
                              uint32_t index, uint32_t max_chunks, uint8_t *out, uint64_t out_stride,
                              unsigned long long *used, uint32_t *formats, uint32_t *results, cudaStream_t st)
@@ -268,7 +255,8 @@ uint32_t launch_decode_batch(const uint8_t *in, uint32_t frames, uint64_t in_str
     if (!jobs.alloc(njobs * sizeof(ChunkJob)) || !whole.alloc((size_t)frames * 4)) { cudaGetLastError(); return HapResult_Internal_Error; }
     HAP_KLAUNCH(kStParse, hap_parse_frames_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, in, in_stride, in_bytes, frames, index,
                 max_chunks, out, out_stride, jobs.as<ChunkJob>(), used, formats, results, whole.as<uint32_t>());
-    launch_chunk_decode(jobs.as<ChunkJob>(), (int)njobs, st);
+    HAP_KLAUNCH(kStSnappyDecode, snappy_decode_chunks_kernel, dim3((unsigned)njobs), dim3(kDecThreads), sizeof(DecodeSmem), st,
+                jobs.as<ChunkJob>(), (int)njobs);
     HAP_KLAUNCH(kStCollect, hap_collect_status_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, jobs.as<ChunkJob>(), frames,
                 max_chunks, whole.as<uint32_t>(), results, used);
     return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
@@ -645,7 +633,8 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
         }
         if (!djobs.alloc(jobs.size() * sizeof(ChunkJob)) ||
             cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(ChunkJob), cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
-        launch_chunk_decode(djobs.as<ChunkJob>(), (int)jobs.size(), st);
+        HAP_KLAUNCH(kStSnappyDecode, snappy_decode_chunks_kernel, dim3((unsigned)jobs.size()), dim3(kDecThreads), sizeof(DecodeSmem), st,
+                    djobs.as<ChunkJob>(), (int)jobs.size());
         if (compressor == kHapComplex && jobs.size() > 1) {
             WorkState ws;
             callback(work_function, &ws, (unsigned)jobs.size(), info);  // hap.c:861

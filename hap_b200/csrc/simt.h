@@ -14,19 +14,6 @@
 
 #define HAP_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define HAP_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
-
-// Named barriers (PTX bar.sync / bar.arrive / bar.red with a barrier number and a thread count): a subset of the
-// CTA's warps synchronises without stopping the others, and one group can signal another (arrive) without waiting.
-// `n` counts every thread that takes part, syncing or arriving, and is a multiple of 32.
-__device__ __forceinline__ void hap_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void hap_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ int hap_bar_or(int id, int n, int pred)
-{
-    int r;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
-                 : "=r"(r) : "r"(pred), "r"(id), "r"(n) : "memory");
-    return r;
-}
 #endif
 
 #define HAP_FULL_MASK 0xffffffffu

@@ -36,11 +36,8 @@ struct ChunkJob {
     uint32_t src_bytes;
     uint32_t dst_bytes;   // decoded size the container arithmetic expects (hap.c:813, :833)
     uint32_t compressor;  // kHapCompressorNone 0x0A | kHapCompressorSnappy 0x0B (hap.c:41-42)
-    uint32_t status;      // out: HapResult of this chunk (hap.c:617-640); kChunkNeedsTables between K7s and K7
-    uint32_t resume_wb;   // K7s -> K7: input position of the first element that is still to be decoded ...
-    uint32_t resume_d0;   // ... and the output bytes produced before it
+    uint32_t status;      // out: HapResult of this chunk (hap.c:617-640)
 };
-constexpr uint32_t kChunkNeedsTables = 0xFFFF0001u;   // K7s met a dense stream and handed the chunk to K7
 
 constexpr int kDecThreads = 256;
 constexpr int kDecSub = 64;                        // compressed bytes owned by one thread per window
@@ -288,7 +285,7 @@ __device__ unsigned long long g_decode_counts[8];  // windows, elements, execute
 #define COUNT_ADD(i, v) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(ChunkJob *jobs, int njobs, int only_flagged)
+__global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(ChunkJob *jobs, int njobs)
 {
     HAP_DYN_SMEM(smem_raw);
     DecodeSmem &S = *reinterpret_cast<DecodeSmem *>(smem_raw);
@@ -302,9 +299,6 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
     const uint32_t in_end = job.src_bytes;
     const uint32_t expected = job.dst_bytes;
 
-    // second pass after K7s: only the chunks it handed over, each from the point it reached
-    const bool resume = only_flagged != 0;
-    if (resume && job.status != kChunkNeedsTables) return;
     if (job.compressor == 0) return;  // unused slot of a batched frame (hap_parse.cuh)
     if (job.compressor == kHapChunkRaw) {
         // hap.c:630-636: verbatim chunk
@@ -331,13 +325,8 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
         return;
     }
 
-    // ---- preamble: varint32 uncompressed length (a resumed chunk is past it) ---------------------------
-    if (t == 0 && resume) {
-        S.fail = 0;
-        S.fail_desc = 0;
-        S.bcast[0] = job.resume_wb;
-    }
-    if (t == 0 && !resume) {
+    // ---- preamble: varint32 uncompressed length -----------------------------------------------
+    if (t == 0) {
         uint64_t v = 0;
         uint32_t i = 0;
         bool ok = false;
@@ -356,7 +345,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
         return;
     }
     uint32_t wb = S.bcast[0];  // window base: a true element start
-    uint32_t d0 = resume ? job.resume_d0 : 0;  // output bytes produced by earlier windows
+    uint32_t d0 = 0;           // output bytes produced by earlier windows
     __syncthreads();
 
     // Sub-blocks covered per window.  Dense streams (a few bytes per element, e.g. Google Snappy on DXT5) fill the

@@ -58,26 +58,23 @@ class HapB200(HapABI):
     def launches(self) -> int:
         return int(self.lib.HapB200KernelLaunchCount())
 
-    STAGES = ("bc_encode", "snappy_encode", "plan", "place", "parse", "snappy_decode", "collect", "bc_decode", "snappy_decode_tables")
+    STAGES = ("bc_encode", "snappy_encode", "plan", "place", "parse", "snappy_decode", "collect", "bc_decode")
 
     def set_stage_timing(self, on: bool):
         self.lib.HapB200SetStageTiming(1 if on else 0)
 
     def stage_times(self):
         """{stage: (total ms, launches)} since the last call; synchronises the device."""
-        ms = (C.c_double * len(self.STAGES))()
-        n = (C.c_ulonglong * len(self.STAGES))()
-        self.lib.HapB200StageTimes(ms, n, len(self.STAGES))
+        ms = (C.c_double * 8)()
+        n = (C.c_ulonglong * 8)()
+        self.lib.HapB200StageTimes(ms, n, 8)
         return {s: (float(ms[i]), int(n[i])) for i, s in enumerate(self.STAGES)}
 
     def decode_phase_cycles(self, reset=True):
         out = (C.c_ulonglong * 16)()
         self.lib.HapB200DebugDecodePhaseCycles(out, 16, 1 if reset else 0)
-        self.last_decode_counts = {"windows": int(out[8]), "elements": int(out[9]), "execute_rounds": int(out[10]),
-                                   "walker_wait_cycles": int(out[13]), "mover_wait_cycles": int(out[14])}
-        # K7 (table kernel) marks: 0 stage, 5 exit tables, 6 chain hop, 1 walk, 2 scans, 3 descriptors+runs, 7 flatten,
-        # 4 execute.  K7s (sparse kernel): 0 stage and 1 walk+describe by the walker warp, 7 and 4 by the movers (the two
-        # groups run concurrently, so the shares describe each group's own time)
+        self.last_decode_counts = {"windows": int(out[8]), "elements": int(out[9]), "execute_rounds": int(out[10])}
+        # kernel marks: 0 stage, 5 exit tables, 6 chain hop, 1 walk, 2 scans, 3 descriptors+runs, 7 flatten, 4 execute
         names = {0: "stage", 5: "exit_tables", 6: "chain_hop", 1: "walk", 2: "scan", 3: "describe", 7: "flatten", 4: "execute"}
         return {names[i]: int(out[i]) for i in (0, 5, 6, 1, 2, 3, 7, 4)}
 

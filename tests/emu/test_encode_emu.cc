@@ -5,7 +5,7 @@
 #define HAPB200_EMU
 #include "hap_assemble.cuh"
 #include "hap_host.h"
-#include "snappy_decode_sparse.cuh"
+#include "snappy_decode.cuh"
 
 extern "C" {
 #include "bc_oracle.h"
@@ -121,10 +121,8 @@ static void check(const std::string &name, const std::vector<Tex> &tex, int mode
             jobs.push_back(ChunkJob{sec, back.data() + 32, loc.len, loc.len, kHapChunkRaw, 99});
         }
         if (!ok) break;
-        HAP_LAUNCH(snappy_decode_sparse_kernel, dim3((unsigned)jobs.size()), dim3(kDecThreads), sizeof(WalkSmem), nullptr,
-                   jobs.data(), (int)jobs.size());
         HAP_LAUNCH(snappy_decode_chunks_kernel, dim3((unsigned)jobs.size()), dim3(kDecThreads), sizeof(DecodeSmem), nullptr,
-                   jobs.data(), (int)jobs.size(), 1);
+                   jobs.data(), (int)jobs.size());
         size_t total = 0;
         for (auto &j : jobs) { if (j.status != 0) { ok = false; why = "K7 status " + std::to_string(j.status); } total += j.dst_bytes; }
         if (ok && memcmp(back.data() + 32, tex[i].data.data(), total) != 0) { ok = false; why = "K7 payload mismatch"; }

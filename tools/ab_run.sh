@@ -1,14 +1,9 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-for fr in 55 222; do
-  timeout 300 python bench.py --steps 6 --warmup 3 --frames $fr --profile > gpurun_out/ab_walk_$fr.json 2> gpurun_out/ab_walk_$fr.err
-  python - <<PY
+for th in 8 16 32; do
+timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --e2e-threads $th --e2e-frames 64 > gpurun_out/e2e_$th.json 2> gpurun_out/e2e_$th.err
+python - <<PY
 import json
-try:
-    d=json.load(open("gpurun_out/ab_walk_$fr.json")); r=d["roofline"]
-    print("RESULT walk $fr", "value %.1f ms/step %.3f"%(d["value"], d["ms_per_step"]), {k:round(v*55/$fr,3) for k,v in r["stage_ms_per_step"].items() if v>0.02}, r["decode_phase_share"], r["decode_counts"])
-except Exception as e: print("RESULT FAILED", e)
+d=json.load(open("gpurun_out/e2e_$th.json")); print("threads $th value %.1f e2e %.2f"%(d["value"], d["e2e"]["value"]), {k:round(v,3) for k,v in d["roofline"]["stage_ms_per_step"].items() if v>0.05})
 PY
 done
-timeout 200 python tools/measure_ref_decode.py > gpurun_out/ref_stream_decode.json 2> gpurun_out/ref_stream_decode.err; cat gpurun_out/ref_stream_decode.json
