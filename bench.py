@@ -6,9 +6,11 @@
 Workload (BASELINE.json `metric` "4K Hap-Q encode/decode GB/s per GPU", configs[2]): 3840x2160 RGBA8
 synthetic video frames -> Hap Q (scaled-YCoCg-DXT5, Snappy, 8 chunks) -> decoded back to the DXT
 texture bytes (what HapDecode returns).  One STEP = one pass of that round trip over a batch of
-`--frames` device-resident frames per GPU (default 55 = 1.8 GB of RGBA, far larger than the 126 MB
-L2, so nothing is served from cache between steps; 55 frames x 8 chunks = 440 decode CTAs = one full
-wave of 148 SMs x 3 resident CTAs).  `value` = RGBA bytes pushed through the round
+`--frames` device-resident frames per GPU (default 222 = 7.4 GB of RGBA, far larger than the 126 MB
+L2, so nothing is served from cache between steps; 222 frames x 8 chunks = 1776 decode CTAs = four full
+waves of 148 SMs x 3 resident CTAs -- chunks differ in length (letterbox rows compress to almost nothing),
+and with several waves the SMs that finish early pick up the next chunk instead of idling: measured
++5 % over a single wave).  `value` = RGBA bytes pushed through the round
 trip per second, all GPUs together (frames are independent: ranks take disjoint frames, no collective
 on the data path, weak scaling).
 Extra legs, outside the timed region: per-stage CUDA-event timing for the roofline object, the
@@ -318,7 +320,8 @@ def run_gpu_arm(args, rank, local_rank, world):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dominant)
+            per_frame = json.load(open(tpath)).get("per_frame_bytes", {}).get(dominant)
+            traffic = per_frame * F if per_frame is not None else None   # measured per frame (ncu), scaled to this launch
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -432,7 +435,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=55, help="device-resident frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=222, help="device-resident frames per GPU per step")
     ap.add_argument("--e2e-frames", type=int, default=32)
     ap.add_argument("--e2e-threads", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
