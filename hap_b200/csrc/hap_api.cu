@@ -10,6 +10,7 @@
 #include "bc_encode.cuh"
 #include "hap_assemble.cuh"
 #include "hap_host.h"
+#include "hap_mov.h"
 #include "hap_parse.cuh"
 #include "snappy_decode.cuh"
 #include "snappy_encode.cuh"
@@ -900,6 +901,89 @@ unsigned int HapB200DecodeRGBA(const void *inputBuffer, unsigned long inputBuffe
     }
     cudaFree(dxt);
     cudaFree(img);
+    return r;
+}
+
+// ---- include/hap_mov.h: QuickTime sample tables around Hap frames (host code only) -------------------------
+
+unsigned int HapB200MovFourCCForFrame(const void *frame, unsigned long frameBytes, unsigned int *fourcc)
+{
+    if (!frame || !fourcc) return HapResult_Bad_Arguments;
+    unsigned int count = 0, f0 = 0, f1 = 0;
+    if (HapGetFrameTextureCount(frame, frameBytes, &count) != HapResult_No_Error || count < 1 || count > 2) return HapResult_Bad_Frame;
+    if (HapGetFrameTextureFormat(frame, frameBytes, 0, &f0) != HapResult_No_Error) return HapResult_Bad_Frame;
+    if (count == 2 && HapGetFrameTextureFormat(frame, frameBytes, 1, &f1) != HapResult_No_Error) return HapResult_Bad_Frame;
+    // HapVideoDRAFT.md:132-142
+    char c = 0;
+    if (count == 1) {
+        switch (f0) {
+        case HapTextureFormat_RGB_DXT1: c = '1'; break;
+        case HapTextureFormat_RGBA_DXT5: c = '5'; break;
+        case HapTextureFormat_YCoCg_DXT5: c = 'Y'; break;
+        case HapTextureFormat_A_RGTC1: c = 'A'; break;
+        case HapTextureFormat_RGBA_BPTC_UNORM: c = '7'; break;
+        case HapTextureFormat_RGB_BPTC_UNSIGNED_FLOAT:
+        case HapTextureFormat_RGB_BPTC_SIGNED_FLOAT: c = 'H'; break;
+        default: break;
+        }
+    } else if ((f0 == HapTextureFormat_YCoCg_DXT5 && f1 == HapTextureFormat_A_RGTC1) ||
+               (f1 == HapTextureFormat_YCoCg_DXT5 && f0 == HapTextureFormat_A_RGTC1)) {
+        c = 'M';
+    }
+    if (!c) return HapResult_Bad_Frame;
+    *fourcc = HAPB200_FOURCC('H', 'a', 'p', c);
+    return HapResult_No_Error;
+}
+
+HapB200Mov *HapB200MovOpen(const char *path) { return hapmov::open_read(path); }
+
+unsigned int HapB200MovInfo(const HapB200Mov *mov, unsigned int *fourcc, unsigned int *width, unsigned int *height,
+                            unsigned long *frameCount, unsigned int *timescale, unsigned long *duration)
+{
+    if (!mov) return HapResult_Bad_Arguments;
+    if (fourcc) *fourcc = mov->fourcc;
+    if (width) *width = mov->width;
+    if (height) *height = mov->height;
+    if (frameCount) *frameCount = (unsigned long)mov->size.size();
+    if (timescale) *timescale = mov->timescale;
+    if (duration) *duration = (unsigned long)mov->duration;
+    return HapResult_No_Error;
+}
+
+unsigned long HapB200MovFrameBytes(const HapB200Mov *mov, unsigned long index)
+{
+    return (mov && index < mov->size.size()) ? mov->size[index] : 0;
+}
+
+unsigned int HapB200MovReadFrame(HapB200Mov *mov, unsigned long index, void *buffer, unsigned long bufferBytes,
+                                 unsigned long *bytesUsed, unsigned int *durationTicks)
+{
+    if (!mov || mov->writing || !buffer || index >= mov->size.size()) return HapResult_Bad_Arguments;
+    const unsigned long n = mov->size[index];
+    if (n > bufferBytes) return HapResult_Buffer_Too_Small;
+    if (fseeko(mov->f, (off_t)mov->offset[index], SEEK_SET) != 0 || fread(buffer, 1, n, mov->f) != n) return HapResult_Internal_Error;
+    if (bytesUsed) *bytesUsed = n;
+    if (durationTicks) *durationTicks = mov->ticks[index];
+    return HapResult_No_Error;
+}
+
+HapB200Mov *HapB200MovCreate(const char *path, unsigned int fourcc, unsigned int width, unsigned int height, unsigned int timescale)
+{
+    return hapmov::create(path, fourcc, width, height, timescale);
+}
+
+unsigned int HapB200MovWriteFrame(HapB200Mov *mov, const void *frame, unsigned long frameBytes, unsigned int durationTicks)
+{
+    return hapmov::write_frame(mov, frame, frameBytes, durationTicks);
+}
+
+unsigned int HapB200MovClose(HapB200Mov *mov)
+{
+    if (!mov) return HapResult_No_Error;
+    unsigned int r = HapResult_No_Error;
+    if (mov->writing) r = hapmov::finish(mov);
+    if (mov->f && fclose(mov->f) != 0 && r == HapResult_No_Error) r = HapResult_Internal_Error;
+    delete mov;
     return r;
 }
 

@@ -29,12 +29,13 @@ def have_gpu():
 
 def test_exports_every_declared_symbol(lib):
     names = set()
-    for hdr in ("hap.h", "hap_b200.h"):
+    for hdr in ("hap.h", "hap_b200.h", "hap_mov.h"):
         text = open(os.path.join(ROOT, "include", hdr)).read()
         names |= set(re.findall(r"\b(Hap(?:B200)?[A-Z][A-Za-z0-9]*)\s*\(", text))
     names -= {"HapDecodeWorkFunction", "HapDecodeCallback", "HapMaxEncodedLength()"}
     assert {"HapEncode", "HapDecode", "HapMaxEncodedLength", "HapGetFrameTextureCount", "HapGetFrameTextureFormat",
-            "HapGetFrameTextureChunkCount", "HapB200EncodeRGBABatch", "HapB200DecodeBatch"} <= names
+            "HapGetFrameTextureChunkCount", "HapB200EncodeRGBABatch", "HapB200DecodeBatch", "HapB200MovOpen",
+            "HapB200MovWriteFrame"} <= names
     for n in sorted(names):
         assert hasattr(lib.lib, n), n
 
