@@ -12,83 +12,146 @@
 
 namespace hapb200 {
 
-HAP_HD void bc1_palette(uint32_t c0, uint32_t c1, bool force4, uint32_t pal[4])
+// ---- palette look-ups by byte permute --------------------------------------------------------------------------
+// A block's palette has 4 (colour) or 8 (BC4) byte-sized entries per channel: they fit one or two registers, and
+// PRMT picks four of them at once when its selector holds the four texel indices of a block row, one per nibble.
+// The indices arrive 2 or 3 bits apart; two mask-shift-or steps spread them to nibbles.
+#if defined(HAPB200_EMU) || !defined(__CUDA_ARCH__)
+HAP_HD uint32_t hap_prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
-    // pal entries packed r | g<<8 | b<<16 | a<<24
-    uint32_t r0 = expand5(c0 >> 11), g0 = expand6((c0 >> 5) & 63), b0 = expand5(c0 & 31);
-    uint32_t r1 = expand5(c1 >> 11), g1 = expand6((c1 >> 5) & 63), b1 = expand5(c1 & 31);
-    pal[0] = r0 | (g0 << 8) | (b0 << 16) | 0xFF000000u;
-    pal[1] = r1 | (g1 << 8) | (b1 << 16) | 0xFF000000u;
-    if (force4 || c0 > c1) {
-        pal[2] = ((2 * r0 + r1) / 3) | (((2 * g0 + g1) / 3) << 8) | (((2 * b0 + b1) / 3) << 16) | 0xFF000000u;
-        pal[3] = ((r0 + 2 * r1) / 3) | (((g0 + 2 * g1) / 3) << 8) | (((b0 + 2 * b1) / 3) << 16) | 0xFF000000u;
-    } else {
-        pal[2] = ((r0 + r1) / 2) | (((g0 + g1) / 2) << 8) | (((b0 + b1) / 2) << 16) | 0xFF000000u;
-        pal[3] = 0;  // transparent black
-    }
+    const uint64_t src = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) r |= (uint32_t)((src >> (8 * ((sel >> (4 * k)) & 7))) & 0xFF) << (8 * k);
+    return r;
 }
-
-HAP_HD void bc4_palette(uint32_t a0, uint32_t a1, uint32_t pal[8])
+HAP_HD int hap_min_relu(int a, int b) { int m = a < b ? a : b; return m < 0 ? 0 : m; }
+#else
+__device__ __forceinline__ uint32_t hap_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+__device__ __forceinline__ int hap_min_relu(int a, int b) { return __vimin_s32_relu(a, b); }   // clamp(a, 0, b) for b >= 0
+#endif
+HAP_HD uint32_t spread3_to_nibbles(uint32_t x)   // i0 | i1<<3 | i2<<6 | i3<<9  ->  i0 | i1<<4 | i2<<8 | i3<<12
 {
-    pal[0] = a0;
-    pal[1] = a1;
+    x = (x & 0x3Fu) | ((x & 0xFC0u) << 2);
+    return (x & 0x0707u) | ((x & 0x3838u) << 1);
+}
+HAP_HD uint32_t spread2_to_nibbles(uint32_t x)   // i0 | i1<<2 | i2<<4 | i3<<6  ->  i0 | i1<<4 | i2<<8 | i3<<12
+{
+    x = (x & 0x0Fu) | ((x & 0xF0u) << 4);
+    return (x & 0x0303u) | ((x & 0x0C0Cu) << 2);
+}
+HAP_HD uint32_t byte_of(uint32_t x, int k) { return hap_prmt(x, 0, 0x4440u + (uint32_t)k); }   // zero-extended byte k
+
+// BC4 block (w0, w1) -> its 16 values, four per register (row r = texels 4r .. 4r+3)
+HAP_HD void bc4_rows(uint32_t w0, uint32_t w1, uint32_t rows[4])
+{
+    const uint32_t a0 = w0 & 0xFF, a1 = (w0 >> 8) & 0xFF;
+    uint32_t p[8];
+    p[0] = a0;
+    p[1] = a1;
     if (a0 > a1) {
+        // ((8-i) a0 + (i-1) a1) / 7, truncating; the numerators stay below 1786, where q/7 == (q * 9363) >> 16
 #pragma unroll
-        for (uint32_t i = 2; i < 8; i++) pal[i] = ((8 - i) * a0 + (i - 1) * a1) / 7;
+        for (uint32_t i = 2; i < 8; i++) p[i] = (((8 - i) * a0 + (i - 1) * a1) * 9363u) >> 16;
     } else {
+        // ((6-i) a0 + (i-1) a1) / 5: numerators below 1276, where q/5 == (q * 13108) >> 16
 #pragma unroll
-        for (uint32_t i = 2; i < 6; i++) pal[i] = ((6 - i) * a0 + (i - 1) * a1) / 5;
-        pal[6] = 0;
-        pal[7] = 255;
+        for (uint32_t i = 2; i < 6; i++) p[i] = (((6 - i) * a0 + (i - 1) * a1) * 13108u) >> 16;
+        p[6] = 0;
+        p[7] = 255;
+    }
+    const uint32_t plo = p[0] | (p[1] << 8) | (p[2] << 16) | (p[3] << 24), phi = p[4] | (p[5] << 8) | (p[6] << 16) | (p[7] << 24);
+    const uint32_t lo = (w0 >> 16) | (w1 << 16), hi = w1 >> 16;   // the 48 index bits
+    rows[0] = hap_prmt(plo, phi, spread3_to_nibbles(lo & 0xFFFu));
+    rows[1] = hap_prmt(plo, phi, spread3_to_nibbles((lo >> 12) & 0xFFFu));
+    rows[2] = hap_prmt(plo, phi, spread3_to_nibbles(((lo >> 24) | (hi << 8)) & 0xFFFu));
+    rows[3] = hap_prmt(plo, phi, spread3_to_nibbles((hi >> 4) & 0xFFFu));
+}
+
+// BC1 colour block (w0 = endpoints, w1 = indices) -> per channel its 16 values, four per register.
+// force4: DXT5-style blocks are always in 4-colour mode.  ch[0..3] = R, G, B, A planes, [r] = row.
+HAP_HD void bc1_rows(uint32_t w0, uint32_t w1, bool force4, uint32_t ch[4][4])
+{
+    const uint32_t c0 = w0 & 0xFFFF, c1 = w0 >> 16;
+    const uint32_t e0[3] = {expand5(c0 >> 11), expand6((c0 >> 5) & 63), expand5(c0 & 31)};
+    const uint32_t e1[3] = {expand5(c1 >> 11), expand6((c1 >> 5) & 63), expand5(c1 & 31)};
+    const bool four = force4 || c0 > c1;
+    uint32_t pal[4];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        // thirds, truncating: numerators below 766, where q/3 == (q * 21846) >> 16; or the average and 0
+        const uint32_t p2 = four ? ((2 * e0[c] + e1[c]) * 21846u) >> 16 : (e0[c] + e1[c]) >> 1;
+        const uint32_t p3 = four ? ((e0[c] + 2 * e1[c]) * 21846u) >> 16 : 0u;
+        pal[c] = e0[c] | (e1[c] << 8) | (p2 << 16) | (p3 << 24);
+    }
+    pal[3] = four ? 0xFFFFFFFFu : 0x00FFFFFFu;   // 3-colour mode: index 3 is transparent black
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const uint32_t sel = spread2_to_nibbles((w1 >> (8 * r)) & 0xFFu);
+#pragma unroll
+        for (int c = 0; c < 4; c++) ch[c][r] = hap_prmt(pal[c], 0, sel);
     }
 }
 
-// texel t of a decoded block; out[16] packed RGBA
+// four planar rows -> the 16 packed RGBA texels
+HAP_HD void interleave_rows(const uint32_t R[4], const uint32_t G[4], const uint32_t B[4], const uint32_t A[4], uint32_t out[16])
+{
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const uint32_t rg_lo = hap_prmt(R[r], G[r], 0x5140u), rg_hi = hap_prmt(R[r], G[r], 0x7362u);   // R0 G0 R1 G1 | R2 G2 R3 G3
+        const uint32_t ba_lo = hap_prmt(B[r], A[r], 0x5140u), ba_hi = hap_prmt(B[r], A[r], 0x7362u);
+        out[4 * r + 0] = hap_prmt(rg_lo, ba_lo, 0x5410u);
+        out[4 * r + 1] = hap_prmt(rg_lo, ba_lo, 0x7632u);
+        out[4 * r + 2] = hap_prmt(rg_hi, ba_hi, 0x5410u);
+        out[4 * r + 3] = hap_prmt(rg_hi, ba_hi, 0x7632u);
+    }
+}
+
+// texel t of a decoded block; out[16] packed RGBA (kBcRgtc1: the value in every colour channel, A = 255)
 HAP_HD void decode_block(int kind, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t out[16])
 {
+    const uint32_t ones[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
     if (kind == kBcDxt1) {
-        uint32_t pal[4];
-        bc1_palette(w0 & 0xFFFF, w0 >> 16, false, pal);
-#pragma unroll
-        for (int t = 0; t < 16; t++) {
-            uint32_t i = (w1 >> (2 * t)) & 3;
-            out[t] = i == 0 ? pal[0] : i == 1 ? pal[1] : i == 2 ? pal[2] : pal[3];
-        }
+        uint32_t ch[4][4];
+        bc1_rows(w0, w1, false, ch);
+        interleave_rows(ch[0], ch[1], ch[2], ch[3], out);
         return;
     }
-    uint32_t ap[8];
-    bc4_palette(w0 & 0xFF, (w0 >> 8) & 0xFF, ap);
-    const uint64_t abits = ((uint64_t)w1 << 16) | (w0 >> 16);
+    uint32_t a[4];
+    bc4_rows(w0, w1, a);
     if (kind == kBcRgtc1) {
-#pragma unroll
-        for (int t = 0; t < 16; t++) {
-            uint32_t i = (uint32_t)(abits >> (3 * t)) & 7, a = ap[0];
-#pragma unroll
-            for (uint32_t k = 1; k < 8; k++) a = i == k ? ap[k] : a;
-            out[t] = a;  // one byte per texel, caller packs
-        }
+        interleave_rows(a, a, a, ones, out);
         return;
     }
-    uint32_t pal[4];
-    bc1_palette(w2 & 0xFFFF, w2 >> 16, true, pal);
+    uint32_t ch[4][4];
+    bc1_rows(w2, w3, true, ch);
+    if (kind == kBcDxt5) {
+        interleave_rows(ch[0], ch[1], ch[2], a, out);
+        return;
+    }
+    // scaled YCoCg: (R',G',B',A) = (Co', Cg', scale bits, Y); exact quarter units, round half up.
+    // quarter units per stored chroma step from the texel's B': B' >> 3 = 0 -> 4, 1 -> 2, else 1.
+    // Only the palette's four B' values occur, so the step is looked up per palette entry, then per texel by PRMT.
+    const uint32_t c0 = w2 & 0xFFFF, c1 = w2 >> 16;
+    const uint32_t b0 = expand5(c0 & 31), b1 = expand5(c1 & 31);
+    const uint32_t bp[4] = {b0, b1, ((2 * b0 + b1) * 21846u) >> 16, ((b0 + 2 * b1) * 21846u) >> 16};
+    uint32_t qpal = 0;
 #pragma unroll
-    for (int t = 0; t < 16; t++) {
-        uint32_t i = (uint32_t)(abits >> (3 * t)) & 7, a = ap[0];
+    for (int i = 0; i < 4; i++) {
+        const uint32_t sc = bp[i] >> 3;
+        qpal |= (sc == 0 ? 4u : sc == 1 ? 2u : 1u) << (8 * i);
+    }
 #pragma unroll
-        for (uint32_t k = 1; k < 8; k++) a = i == k ? ap[k] : a;
-        uint32_t ci = (w3 >> (2 * t)) & 3;
-        uint32_t c = ci == 0 ? pal[0] : ci == 1 ? pal[1] : ci == 2 ? pal[2] : pal[3];
-        if (kind == kBcDxt5) {
-            out[t] = (c & 0x00FFFFFFu) | (a << 24);
-        } else {
-            // scaled YCoCg: (R',G',B',A) = (Co', Cg', scale bits, Y); exact quarter units, round half up
-            int sc = (int)((c >> 16) & 0xFF) >> 3;         // 0,1,3 -> scale 1,2,4
-            int q = sc >= 3 ? 1 : sc >= 1 ? (sc == 2 ? 1 : 2) : 4;
-            int co4 = ((int)(c & 0xFF) - 128) * q, cg4 = ((int)((c >> 8) & 0xFF) - 128) * q, y4 = 4 * (int)a;
-            uint32_t R = (uint32_t)hap_clampi((y4 + co4 - cg4 + 2) >> 2, 0, 255);
-            uint32_t G = (uint32_t)hap_clampi((y4 + cg4 + 2) >> 2, 0, 255);
-            uint32_t B = (uint32_t)hap_clampi((y4 - co4 - cg4 + 2) >> 2, 0, 255);
-            out[t] = R | (G << 8) | (B << 16) | 0xFF000000u;
+    for (int r = 0; r < 4; r++) {
+        const uint32_t q4 = hap_prmt(qpal, 0, spread2_to_nibbles((w3 >> (8 * r)) & 0xFFu));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int q = (int)byte_of(q4, k);
+            const int co4 = ((int)byte_of(ch[0][r], k) - 128) * q, cg4 = ((int)byte_of(ch[1][r], k) - 128) * q;
+            const int y4 = 4 * (int)byte_of(a[r], k) + 2;
+            const uint32_t R = (uint32_t)hap_min_relu((y4 + co4 - cg4) >> 2, 255);
+            const uint32_t G = (uint32_t)hap_min_relu((y4 + cg4) >> 2, 255);
+            const uint32_t B = (uint32_t)hap_min_relu((y4 - co4 - cg4) >> 2, 255);
+            out[4 * r + k] = R | (G << 8) | (B << 16) | 0xFF000000u;
         }
     }
 }
@@ -117,19 +180,15 @@ __global__ void __launch_bounds__(kBcThreads) bc_decode_kernel(const uint8_t *__
     if (KIND == kBcDxt1 || KIND == kBcRgtc1) {
         uint2 v = reinterpret_cast<const uint2 *>(in)[bi];
         decode_block(KIND, v.x, v.y, 0, 0, px);
-        if (KIND == kBcRgtc1) {
-#pragma unroll
-            for (int t = 0; t < 16; t++) px[t] = px[t] * 0x010101u | 0xFF000000u;
-        }
     } else {
         uint4 v = reinterpret_cast<const uint4 *>(in)[bi];
         decode_block(KIND, v.x, v.y, v.z, v.w, px);
         if (G.merge_alpha) {
             uint2 a = reinterpret_cast<const uint2 *>(alpha_blocks + (uint64_t)blockIdx.y * G.alpha_stride)[bi];
-            uint32_t al[16];
-            decode_block(kBcRgtc1, a.x, a.y, 0, 0, al);
+            uint32_t al[4];
+            bc4_rows(a.x, a.y, al);
 #pragma unroll
-            for (int t = 0; t < 16; t++) px[t] = (px[t] & 0x00FFFFFFu) | (al[t] << 24);
+            for (int t = 0; t < 16; t++) px[t] = hap_prmt(px[t], al[t >> 2], 0x4210u + ((uint32_t)(t & 3) << 12));   // alpha byte t%4 of its row
         }
     }
     uint8_t *dst = rgba + (uint64_t)blockIdx.y * G.frame_bytes + (uint64_t)(4 * by) * G.row_bytes + 16u * bx;

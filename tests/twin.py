@@ -28,3 +28,11 @@ def encode(kind: str, rgba: np.ndarray) -> bytes:
     out = np.empty(n, np.uint8)
     _lib().twin_encode(C.c_void_p(rgba.ctypes.data), w, h, KIND[kind], C.c_void_p(out.ctypes.data))
     return out.tobytes()
+
+
+def decode(kind: str, blocks: bytes, w: int, h: int) -> np.ndarray:
+    """Host build of the block decoder the kernels compile (bc_decode.cuh) -> (h, w, 4) uint8."""
+    b = np.frombuffer(blocks, dtype=np.uint8)
+    out = np.empty((h, w, 4), np.uint8)
+    _lib().twin_decode(C.c_void_p(b.ctypes.data), w, h, KIND[kind], C.c_void_p(out.ctypes.data))
+    return out
