@@ -449,8 +449,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=222, help="device-resident frames per GPU per step")
-    ap.add_argument("--e2e-frames", type=int, default=32)
-    ap.add_argument("--e2e-threads", type=int, default=8)
+    ap.add_argument("--e2e-frames", type=int, default=64)
+    ap.add_argument("--e2e-threads", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: skip the e2e and CPU legs")
     ap.add_argument("--no-overlap", action="store_true", help="encode and decode of a batch back to back on one stream")

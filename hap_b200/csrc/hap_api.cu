@@ -106,21 +106,51 @@ bool runtime_ok()
 // different host threads overlap their copies and kernels (the reference is re-entrant, hap.c has no globals).
 // With any device pointer among the arguments the call uses the legacy default stream under a mutex, which
 // orders it after whatever produced those buffers on the caller's (blocking) streams.
+// A pooled stream brings its own memory pool: scratch freed by one host-pointer call is handed to the next call
+// on the SAME stream.  With the device's default pool, memory freed on one stream and re-used on another makes the
+// second stream wait for the first, which chained concurrent calls from different host threads one behind the other.
+struct PooledStream {
+    cudaStream_t st = nullptr;
+    cudaMemPool_t mem = nullptr;
+};
+thread_local cudaMemPool_t g_call_mem = nullptr;   // pool of the host-pointer call running on this thread, if any
+
 struct CallStream {
     cudaStream_t st = nullptr;
     bool pooled = false;
+    PooledStream ps;
     std::unique_lock<std::mutex> serial;
     static std::mutex &pool_mu() { static std::mutex m; return m; }
-    static std::vector<cudaStream_t> &pool() { static std::vector<cudaStream_t> v; return v; }
+    static std::vector<PooledStream> &pool() { static std::vector<PooledStream> v; return v; }
     explicit CallStream(bool all_host)
     {
         if (all_host) {
             {
                 std::lock_guard<std::mutex> l(pool_mu());
-                if (!pool().empty()) { st = pool().back(); pool().pop_back(); }
+                if (!pool().empty()) { ps = pool().back(); pool().pop_back(); }
             }
-            if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); st = nullptr; }
+            if (!ps.st) {
+                if (cudaStreamCreateWithFlags(&ps.st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ps.st = nullptr; }
+                int dev = 0;
+                cudaMemPoolProps props;
+                memset(&props, 0, sizeof props);
+                props.allocType = cudaMemAllocationTypePinned;
+                props.handleTypes = cudaMemHandleTypeNone;
+                props.location.type = cudaMemLocationTypeDevice;
+                if (ps.st && cudaGetDevice(&dev) == cudaSuccess) {
+                    props.location.id = dev;
+                    if (cudaMemPoolCreate(&ps.mem, &props) == cudaSuccess) {
+                        unsigned long long keep = ~0ull;
+                        cudaMemPoolSetAttribute(ps.mem, cudaMemPoolAttrReleaseThreshold, &keep);
+                    } else {
+                        cudaGetLastError();
+                        ps.mem = nullptr;   // fall back to the default pool
+                    }
+                }
+            }
+            st = ps.st;
             pooled = st != nullptr;
+            if (pooled) g_call_mem = ps.mem;
         }
         if (!pooled) {
             serial = std::unique_lock<std::mutex>(g_rt.mu);
@@ -130,8 +160,9 @@ struct CallStream {
     ~CallStream()
     {
         if (pooled) {
+            g_call_mem = nullptr;
             std::lock_guard<std::mutex> l(pool_mu());
-            pool().push_back(st);
+            pool().push_back(ps);
         }
     }
 };
@@ -148,7 +179,11 @@ struct DevBuf {
     void *p = nullptr;
     cudaStream_t s;
     explicit DevBuf(cudaStream_t st) : s(st) {}
-    bool alloc(size_t n) { return cudaMallocAsync(&p, n ? n : 16, s) == cudaSuccess; }
+    bool alloc(size_t n)
+    {
+        if (g_call_mem) return cudaMallocFromPoolAsync(&p, n ? n : 16, g_call_mem, s) == cudaSuccess;
+        return cudaMallocAsync(&p, n ? n : 16, s) == cudaSuccess;
+    }
     ~DevBuf() { if (p) cudaFreeAsync(p, s); }
     template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
