@@ -32,7 +32,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, CHUNKS = 3840, 2160, 8
+W, H, CHUNKS = 3840, 2160, int(os.environ.get("HAPB200_BENCH_CHUNKS", "8"))  # 8 = the metric's configuration (the override is for experiments)
 RGBA_BYTES = 4 * W * H            # 33 177 600
 DXT_BYTES = W * H                 # 8 294 400 (16 B per 4x4 block)
 WORKLOAD = "hap_q_4k_rgba_encode_decode(3840x2160,YCoCg-DXT5,snappy,8chunks)"
@@ -49,8 +49,11 @@ def measured_peak_hbm():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler process is started ahead
+    of the warm-up steps (nvidia-smi can take a few hundred milliseconds to print its first line, longer than a
+    short timed region); every line carries nvidia-smi's own timestamp and only the lines stamped inside
+    [t0, t1] -- the wall-clock interval of the timed region -- are kept."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
@@ -63,38 +66,44 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0: float = None, t1: float = None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.proc:
             return out
+        time.sleep(0.05)   # let the line of the last interval arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        inside, everything = [], []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 7:
+                if len(f) < 8:
                     continue
                 try:
-                    sm.append(float(f[0])); mx.append(float(f[1]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rec = (float(f[1]), float(f[2]), [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                                         "sw_power_cap"), f[4:8]) if v.lower().startswith("active")])
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                everything.append(rec)
+                if t0 is None or (t0 - 0.005 <= ts <= t1 + 0.02):
+                    inside.append(rec)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        use, where = (inside, "timed region") if inside else (everything[-5:], "around the timed region (none stamped inside it)")
+        if use:
+            out = {"sm_mhz": statistics.median(r[0] for r in use), "sm_max_mhz": max(r[1] for r in use),
+                   "reasons": sorted({n for r in use for n in r[2]}), "samples": len(use), "sampled": where}
         return out
 
 
@@ -248,6 +257,9 @@ def run_gpu_arm(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             step()
@@ -255,12 +267,10 @@ def run_gpu_arm(args, rank, local_rank, world):
         barrier()
         assert res.tolist() == [0] * F and tex_used.tolist() == [DXT_BYTES] * F, "decode failed in warm-up"
         state["n"] = 0
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         launches0 = lib.launches()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wall0 = time.time()
         e0.record(stream)
         # K steps = K batches encoded AND K batches decoded: in overlap mode the first timed step has nothing of
         # its own to decode yet, so the batch of the last step is decoded inside the timed region by drain()
@@ -269,8 +279,9 @@ def run_gpu_arm(args, rank, local_rank, world):
         drain()
         e1.record(stream)
         barrier()
+        wall1 = time.time()
         launches = lib.launches() - launches0
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop(wall0, wall1) if rank == 0 else None
         assert res.tolist() == [0] * F and tex_used.tolist() == [DXT_BYTES] * F, "decode failed in the timed region"
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
