@@ -6,11 +6,11 @@
 Workload (BASELINE.json `metric` "4K Hap-Q encode/decode GB/s per GPU", configs[2]): 3840x2160 RGBA8
 synthetic video frames -> Hap Q (scaled-YCoCg-DXT5, Snappy, 8 chunks) -> decoded back to the DXT
 texture bytes (what HapDecode returns).  One STEP = one pass of that round trip over a batch of
-`--frames` device-resident frames per GPU (default 222 = 7.4 GB of RGBA, far larger than the 126 MB
-L2, so nothing is served from cache between steps; 222 frames x 8 chunks = 1776 decode CTAs = four full
+`--frames` device-resident frames per GPU (default 444 = 14.7 GB of RGBA, far larger than the 126 MB
+L2, so nothing is served from cache between steps; 444 frames x 8 chunks = 3552 decode CTAs = eight full
 waves of 148 SMs x 3 resident CTAs -- chunks differ in length (letterbox rows compress to almost nothing),
 and with several waves the SMs that finish early pick up the next chunk instead of idling: measured
-+5 % over a single wave).  `value` = RGBA bytes pushed through the round
++5 % at four waves and +8 % at eight over a single wave).  `value` = RGBA bytes pushed through the round
 trip per second, all GPUs together (frames are independent: ranks take disjoint frames, no collective
 on the data path, weak scaling).
 Extra legs, outside the timed region: per-stage CUDA-event timing for the roofline object, the
@@ -459,7 +459,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=222, help="device-resident frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=444, help="device-resident frames per GPU per step")
     ap.add_argument("--e2e-frames", type=int, default=64)
     ap.add_argument("--e2e-threads", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
