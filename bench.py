@@ -291,6 +291,68 @@ def run_gpu_arm(args, rank, local_rank, world):
     value = world * F * RGBA_BYTES / (ms_per_step * 1e-3) / 1e9
     mean_frame = float(used[0].double().mean().item())
 
+    # ---- end-to-end leg (every rank at once: the whole-job number at N GPUs): the host-pointer C-ABI (one frame per
+    #      call, pinned host buffers), PCIe copies inside the timed region.  The calls are re-entrant like the
+    #      reference's; `--e2e-threads` host threads per GPU keep that many frames in flight, the way a player or
+    #      transcoder with a worker pool drives the codec. ------------------------------------------------------
+    e2e = None
+    if not args.profile:
+        import ctypes as C
+        from concurrent.futures import ThreadPoolExecutor
+        from hap_b200.abi import DECODE_CB
+
+        FE, T = args.e2e_frames, max(1, args.e2e_threads)
+        n_host = min(FE, F, 16)                      # distinct source frames in pinned host memory, cycled
+        host_rgba = torch.empty((n_host, H, W, 4), dtype=torch.uint8).pin_memory()
+        host_rgba.copy_(rgba[:n_host])
+        host_frame = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(T)]
+        host_tex = [torch.empty(DXT_BYTES, dtype=torch.uint8).pin_memory() for _ in range(T)]
+
+        def _cb(function, p, count, info):
+            for i in range(count):
+                function(p, i)
+        cb = DECODE_CB(_cb)
+
+        def worker(w):
+            usedc, fmtc = C.c_ulong(0), C.c_uint(0)
+            h2d = d2h = 0
+            for i in range(w, FE, T):
+                src_frame = host_rgba[i % n_host]
+                r = lib.lib.HapB200EncodeRGBA(src_frame.data_ptr(), W, H, 4 * W, codec, 1, CHUNKS, host_frame[w].data_ptr(), cap,
+                                              C.byref(usedc))
+                assert r == 0, r
+                n = usedc.value
+                r = lib._dec(host_frame[w].data_ptr(), n, 0, cb, None, host_tex[w].data_ptr(), DXT_BYTES, C.byref(usedc), C.byref(fmtc))
+                assert r == 0 and usedc.value == DXT_BYTES, (r, usedc.value)
+                h2d += RGBA_BYTES + n
+                d2h += n + DXT_BYTES
+            return h2d, d2h
+
+        pool = ThreadPoolExecutor(T)
+
+        def e2e_step():
+            parts = list(pool.map(worker, range(T)))
+            return sum(p[0] for p in parts), sum(p[1] for p in parts)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_iters = 3
+        for _ in range(e2e_iters):
+            h2d, d2h = e2e_step()
+        torch.cuda.synchronize(dev)
+        e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_iters], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)     # the slowest rank closes the step
+        e2e_t = float(e2e_t.item())
+        e2e = {"value": world * FE * RGBA_BYTES / e2e_t / 1e9, "unit": "GB/s", "h2d_bytes_per_step": world * h2d,
+               "d2h_bytes_per_step": world * d2h, "frames_per_step": world * FE, "host_threads": T * world,
+               "api": "HapB200EncodeRGBA + HapDecode, pinned host buffers, one frame per call, calls from a pool of "
+                      f"{T} host threads per GPU, all {world} GPU(s) at once"}
+        del host_rgba, host_frame, host_tex
+        pool.shutdown()
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -355,58 +417,6 @@ def run_gpu_arm(args, rank, local_rank, world):
     if args.profile:
         emit({"profile_only": True, "ms_per_step": ms_per_step, "value": value, "roofline": roofline})
         return
-
-    # ---- end-to-end leg: the host-pointer C-ABI (one frame per call, pinned host buffers), PCIe copies inside
-    #      the timed region.  The calls are re-entrant like the reference's; `--e2e-threads` host threads keep that
-    #      many frames in flight, the way a player or transcoder with a worker pool drives the codec. -----------
-    import ctypes as C
-    from concurrent.futures import ThreadPoolExecutor
-    from hap_b200.abi import DECODE_CB
-
-    FE, T = args.e2e_frames, max(1, args.e2e_threads)
-    host_rgba = torch.empty((min(FE, F), H, W, 4), dtype=torch.uint8).pin_memory()
-    host_rgba.copy_(rgba[: min(FE, F)])
-    host_frame = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(T)]
-    host_tex = [torch.empty(DXT_BYTES, dtype=torch.uint8).pin_memory() for _ in range(T)]
-
-    def _cb(function, p, count, info):
-        for i in range(count):
-            function(p, i)
-    cb = DECODE_CB(_cb)
-
-    def worker(w):
-        usedc, fmtc = C.c_ulong(0), C.c_uint(0)
-        h2d = d2h = 0
-        for i in range(w, FE, T):
-            src_frame = host_rgba[i % host_rgba.shape[0]]
-            r = lib.lib.HapB200EncodeRGBA(src_frame.data_ptr(), W, H, 4 * W, codec, 1, CHUNKS, host_frame[w].data_ptr(), cap,
-                                          C.byref(usedc))
-            assert r == 0, r
-            n = usedc.value
-            r = lib._dec(host_frame[w].data_ptr(), n, 0, cb, None, host_tex[w].data_ptr(), DXT_BYTES, C.byref(usedc), C.byref(fmtc))
-            assert r == 0 and usedc.value == DXT_BYTES, (r, usedc.value)
-            h2d += RGBA_BYTES + n
-            d2h += n + DXT_BYTES
-        return h2d, d2h
-
-    pool = ThreadPoolExecutor(T)
-
-    def e2e_step():
-        parts = list(pool.map(worker, range(T)))
-        return sum(p[0] for p in parts), sum(p[1] for p in parts)
-
-    for _ in range(2):
-        e2e_step()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    e2e_iters = 3
-    for _ in range(e2e_iters):
-        h2d, d2h = e2e_step()
-    torch.cuda.synchronize(dev)
-    e2e_t = (time.perf_counter() - t0) / e2e_iters
-    e2e = {"value": FE * RGBA_BYTES / e2e_t / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "frames_per_step": FE, "host_threads": T,
-           "api": "HapB200EncodeRGBA + HapDecode, pinned host buffers, one frame per call, calls from a host thread pool"}
 
     # ---- CPU baseline leg (bounded) ------------------------------------------------------------------
     cpu = None

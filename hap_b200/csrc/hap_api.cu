@@ -70,6 +70,7 @@ struct Runtime {
     bool ready = false;
     bool failed = false;
     cudaStream_t stream = nullptr;
+    int device = 0;   // the device of the thread that made the first call: every later call runs there
 };
 Runtime g_rt;
 std::once_flag g_once;
@@ -78,6 +79,7 @@ void runtime_init()
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { g_rt.failed = true; cudaGetLastError(); return; }
+    g_rt.device = dev;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long keep = ~0ull;  // keep freed scratch in the pool: steady-state calls never hit the OS
@@ -98,7 +100,15 @@ void runtime_init()
 bool runtime_ok()
 {
     std::call_once(g_once, runtime_init);
-    return g_rt.ready;
+    if (!g_rt.ready) return false;
+    // The current device is per host thread and a new thread starts on device 0: a worker thread of a process that
+    // drives GPU 3 would otherwise allocate and launch on GPU 0 (found with the bench's host thread pool on rank 1).
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != g_rt.device) {
+        cudaGetLastError();
+        if (cudaSetDevice(g_rt.device) != cudaSuccess) { cudaGetLastError(); return false; }
+    }
+    return true;
 }
 
 // Stream of one host-pointer call.  When every buffer of the call is host memory nothing outside the call can
