@@ -71,6 +71,7 @@ struct Runtime {
     bool failed = false;
     cudaStream_t stream = nullptr;
     int device = 0;   // the device of the thread that made the first call: every later call runs there
+    int sm_count = 148;
 };
 Runtime g_rt;
 std::once_flag g_once;
@@ -80,6 +81,7 @@ void runtime_init()
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { g_rt.failed = true; cudaGetLastError(); return; }
     g_rt.device = dev;
+    if (cudaDeviceGetAttribute(&g_rt.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_rt.sm_count <= 0) { cudaGetLastError(); g_rt.sm_count = 148; }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long keep = ~0ull;  // keep freed scratch in the pool: steady-state calls never hit the OS
@@ -235,8 +237,13 @@ uint32_t launch_encode(const uint8_t *base, const FrameGeom &G, uint32_t frames,
         cudaGetLastError();
         return HapResult_Internal_Error;
     }
-    HAP_KLAUNCH(kStSnappyEncode, snappy_encode_fragments_kernel, dim3((unsigned)nfrag), dim3(kEncThreads), sizeof(EncodeSmem), st, base, G,
-                scratch.as<uint8_t>(), fsize.as<uint32_t>());
+#ifndef HAPB200_ENC_PERSISTENT
+#define HAPB200_ENC_PERSISTENT 1
+#endif
+    // one resident CTA per SM strides over the fragments (the kernel's 131 KB of shared memory allow no second one)
+    const unsigned k5_grid = HAPB200_ENC_PERSISTENT ? (unsigned)(nfrag < (uint64_t)g_rt.sm_count ? nfrag : (uint64_t)g_rt.sm_count) : (unsigned)nfrag;
+    HAP_KLAUNCH(kStSnappyEncode, snappy_encode_fragments_kernel, dim3(k5_grid), dim3(kEncThreads), sizeof(EncodeSmem), st, base, G,
+                (uint32_t)nfrag, scratch.as<uint8_t>(), fsize.as<uint32_t>());
     HAP_KLAUNCH(kStPlan, hap_plan_frames_kernel, dim3(frames), dim3(kPlanThreads), 0, st, G, base, fsize.as<uint32_t>(),
                 fdst.as<uint32_t>(), out, out_stride, used);
     HAP_KLAUNCH(kStPlace, hap_place_fragments_kernel, dim3((unsigned)nfrag), dim3(kPlaceThreads), 0, st, G, base,

@@ -331,34 +331,33 @@ struct FrameGeom {
     SectionGeom s[2];
 };
 
-// grid.x = frames * frags_per_frame.  dxt: base pointer of the texture bytes; scratch: [grid.x][kFragCap];
-// frag_size: [grid.x] (kFragStoredRaw when the fragment was not compressed).
-__global__ void __launch_bounds__(kEncThreads) snappy_encode_fragments_kernel(
-    const uint8_t *__restrict__ dxt, FrameGeom G, uint8_t *__restrict__ scratch, uint32_t *__restrict__ frag_size)
+// Where fragment `gfrag` of the batch lives and how long it is.
+struct FragRef {
+    const uint8_t *in;
+    uint32_t words;      // 0: the section is not compressed (fragment stored raw)
+};
+__device__ __forceinline__ FragRef locate_fragment(const uint8_t *dxt, const FrameGeom &G, uint32_t gfrag)
 {
-    HAP_DYN_SMEM(smem_raw);
-    EncodeSmem &S = *reinterpret_cast<EncodeSmem *>(smem_raw);
-    const int t = threadIdx.x;
-    const uint32_t gfrag = blockIdx.x;
     const uint32_t frame = gfrag / G.frags_per_frame;
     const uint32_t f = gfrag % G.frags_per_frame;
-    const SectionGeom &sec = (G.sections == 2 && f >= G.s[1].frag_base) ? G.s[1] : G.s[0];
-    const uint32_t fl = f - sec.frag_base;
-    const uint32_t chunk = fl / sec.frags_per_chunk, j = fl % sec.frags_per_chunk;
-    if (!sec.compress) {
-        if (t == 0) frag_size[gfrag] = kFragStoredRaw;
-        return;
-    }
-    const uint64_t in_off = (uint64_t)frame * sec.in_stride + sec.in_offset + (uint64_t)chunk * sec.chunk_bytes +
-                            (uint64_t)j * kFragBytes;
-    const uint32_t left = sec.chunk_bytes - j * kFragBytes;
-    const uint32_t n = left < (uint32_t)kFragBytes ? left : (uint32_t)kFragBytes;
-    const uint32_t W = n >> 2;
-    const uint8_t *in = dxt + in_off;
-    uint32_t d[8];
-    const uint32_t i0 = (uint32_t)t * kStrip;
-    if ((((uintptr_t)in) & 15) == 0 && i0 + kStrip <= W) {
-        const uint4 *in4 = reinterpret_cast<const uint4 *>(in) + 2 * t;
+    const bool second = G.sections == 2 && f >= G.s[1].frag_base;
+    const uint32_t frag_base = second ? G.s[1].frag_base : G.s[0].frag_base, fpc = second ? G.s[1].frags_per_chunk : G.s[0].frags_per_chunk;
+    const uint32_t chunk_bytes = second ? G.s[1].chunk_bytes : G.s[0].chunk_bytes, compress = second ? G.s[1].compress : G.s[0].compress;
+    const uint64_t in_stride = second ? G.s[1].in_stride : G.s[0].in_stride, in_offset = second ? G.s[1].in_offset : G.s[0].in_offset;
+    const uint32_t fl = f - frag_base;
+    const uint32_t chunk = fl / fpc, j = fl % fpc;
+    FragRef r;
+    r.in = dxt + (uint64_t)frame * in_stride + in_offset + (uint64_t)chunk * chunk_bytes + (uint64_t)j * kFragBytes;
+    const uint32_t left = chunk_bytes - j * kFragBytes;
+    r.words = compress ? (left < (uint32_t)kFragBytes ? left : (uint32_t)kFragBytes) >> 2 : 0u;
+    return r;
+}
+
+// A thread's 8 words of a fragment, from global memory: two 16-byte loads when possible
+__device__ __forceinline__ void load_strip(const FragRef &fr, uint32_t i0, uint32_t d[8])
+{
+    if ((((uintptr_t)fr.in) & 15) == 0 && i0 + kStrip <= fr.words) {
+        const uint4 *in4 = reinterpret_cast<const uint4 *>(fr.in) + (i0 >> 2);
         const uint4 a = in4[0], b = in4[1];
         d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
     } else {
@@ -366,24 +365,66 @@ __global__ void __launch_bounds__(kEncThreads) snappy_encode_fragments_kernel(
         for (int k = 0; k < kStrip; k++) {
             const uint32_t i = i0 + k;
             d[k] = 0;
-            if (i < W) d[k] = in[4 * i] | (in[4 * i + 1] << 8) | (in[4 * i + 2] << 16) | ((uint32_t)in[4 * i + 3] << 24);
+            if (i < fr.words) d[k] = fr.in[4 * i] | (fr.in[4 * i + 1] << 8) | (fr.in[4 * i + 2] << 16) | ((uint32_t)fr.in[4 * i + 3] << 24);
         }
     }
-    *reinterpret_cast<uint4 *>(&S.data[i0]) = make_uint4(d[0], d[1], d[2], d[3]);
-    *reinterpret_cast<uint4 *>(&S.data[i0 + 4]) = make_uint4(d[4], d[5], d[6], d[7]);
-    {
-        uint4 *tb = reinterpret_cast<uint4 *>(S.u.table);
-        const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-        for (int q = t; q < (1 << kEncHashBits) / 4; q += kEncThreads) tb[q] = ones;
+}
+
+// A fixed grid (one CTA per SM: the kernel needs 131 KB of shared memory) strides over the nfrag = frames *
+// frags_per_frame fragments of the batch.  A thread's words of the NEXT fragment are loaded before the current one is
+// compressed, so the HBM latency of the input and the turn-over between CTAs -- both fully exposed with a single CTA
+// per SM -- are covered by a fragment's worth of work.
+// dxt: base pointer of the texture bytes; scratch: [nfrag][kFragCap]; frag_size: [nfrag] (kFragStoredRaw when the
+// fragment was not compressed).
+__global__ void __launch_bounds__(kEncThreads) snappy_encode_fragments_kernel(
+    const uint8_t *__restrict__ dxt, FrameGeom G, uint32_t nfrag, uint8_t *__restrict__ scratch, uint32_t *__restrict__ frag_size)
+{
+    HAP_DYN_SMEM(smem_raw);
+    EncodeSmem &S = *reinterpret_cast<EncodeSmem *>(smem_raw);
+    const int t = threadIdx.x;
+    const uint32_t i0 = (uint32_t)t * kStrip;
+    uint32_t gfrag = blockIdx.x;
+    if (gfrag >= nfrag) return;
+    FragRef cur = locate_fragment(dxt, G, gfrag);
+    uint32_t d[8];
+    load_strip(cur, i0, d);
+    for (;;) {
+        const uint32_t next = gfrag + gridDim.x;
+        FragRef nxt;
+        uint32_t nd[8];
+        const bool more = next < nfrag;
+        if (more) {
+            nxt = locate_fragment(dxt, G, next);
+            load_strip(nxt, i0, nd);     // in flight while this fragment is compressed
+        }
+        if (cur.words == 0) {
+            if (t == 0) frag_size[gfrag] = kFragStoredRaw;
+        } else {
+            const uint32_t W = cur.words;
+            *reinterpret_cast<uint4 *>(&S.data[i0]) = make_uint4(d[0], d[1], d[2], d[3]);
+            *reinterpret_cast<uint4 *>(&S.data[i0 + 4]) = make_uint4(d[4], d[5], d[6], d[7]);
+            {
+                uint4 *tb = reinterpret_cast<uint4 *>(S.u.table);
+                const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                for (int q = t; q < (1 << kEncHashBits) / 4; q += kEncThreads) tb[q] = ones;
+            }
+            __syncthreads();
+            const uint32_t period_words = (G.sections == 2 && (gfrag % G.frags_per_frame) >= G.s[1].frag_base) ? G.s[1].period_words : G.s[0].period_words;
+            const uint32_t total = W == (uint32_t)kFragWords ? compress_fragment<true>(S, d, W, period_words)
+                                                             : compress_fragment<false>(S, d, W, period_words);
+            uint8_t *o = scratch + (uint64_t)gfrag * kFragCap;
+            const uint32_t *o32s = S.out;
+            uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
+            for (uint32_t i = t; i < (total + 3) / 4; i += kEncThreads) o32[i] = o32s[i];
+            if (t == 0) frag_size[gfrag] = total;
+            __syncthreads();   // S.out, S.data and the tables are rewritten by the next fragment
+        }
+        if (!more) break;
+        gfrag = next;
+        cur = nxt;
+#pragma unroll
+        for (int k = 0; k < kStrip; k++) d[k] = nd[k];
     }
-    __syncthreads();
-    const uint32_t total = W == (uint32_t)kFragWords ? compress_fragment<true>(S, d, W, sec.period_words)
-                                                     : compress_fragment<false>(S, d, W, sec.period_words);
-    uint8_t *o = scratch + (uint64_t)gfrag * kFragCap;
-    const uint32_t *o32s = S.out;
-    uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
-    for (uint32_t i = t; i < (total + 3) / 4; i += kEncThreads) o32[i] = o32s[i];
-    if (t == 0) frag_size[gfrag] = total;
 }
 
 }  // namespace hapb200

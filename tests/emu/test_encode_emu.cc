@@ -45,8 +45,10 @@ static std::vector<uint8_t> gpu_encode(const std::vector<Tex> &tex, int mode)
     std::vector<uint32_t> fsize(G.frags_per_frame), fdst(G.frags_per_frame);
     unsigned long long used = 0;
     emu::g_order_mode() = mode;
-    HAP_LAUNCH(snappy_encode_fragments_kernel, dim3(G.frags_per_frame), dim3(kEncThreads), sizeof(EncodeSmem), nullptr,
-               in.data(), G, scratch.data(), fsize.data());
+    // a grid smaller than the fragment count, as on the device: CTAs stride over the fragments (modes alternate 1, 2, 3 CTAs)
+    const unsigned k5_grid = G.frags_per_frame < (unsigned)(1 + mode % 3) ? G.frags_per_frame : (unsigned)(1 + mode % 3);
+    HAP_LAUNCH(snappy_encode_fragments_kernel, dim3(k5_grid), dim3(kEncThreads), sizeof(EncodeSmem), nullptr,
+               in.data(), G, (uint32_t)G.frags_per_frame, scratch.data(), fsize.data());
     HAP_LAUNCH(hap_plan_frames_kernel, dim3(1), dim3(kPlanThreads), 0, nullptr, G, in.data(), fsize.data(), fdst.data(),
                out.data(), (uint64_t)cap, &used);
     HAP_LAUNCH(hap_place_fragments_kernel, dim3(G.frags_per_frame), dim3(kPlaceThreads), 0, nullptr, G, in.data(),
