@@ -140,10 +140,19 @@ __device__ __forceinline__ WalkResult walk_subblock(const uint8_t *cin, uint32_t
     return r;
 }
 
+// Next chain position after a literal whose length sits in 1..4 bytes behind the tag (m = 60..63); `v` = those bytes.
+// Rare, and not inlined into the 16 unrolled steps of the exit-table sweep.
+__device__ __noinline__ uint64_t long_literal_next(uint32_t o, uint32_t m, uint32_t v)
+{
+    const uint32_t extra = m - 59;
+    const uint32_t mm = extra == 4 ? v : (v & ((1u << (8 * extra)) - 1u));
+    return mm == 0xFFFFFFFFu ? ~0ull : (uint64_t)o + 1 + extra + (uint64_t)mm + 1;
+}
+
 // dst/src any alignment.  `lane` of `n_lanes` cooperating threads; 4 bytes per thread per step once the
 // destination is word-aligned, the source word assembled from two aligned words when it is not.
 template <int N_LANES>
-__device__ __forceinline__ void lanes_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t lane)
+__device__ __noinline__ void lanes_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t lane)
 {
     uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
     if (head > len) head = len;
@@ -165,12 +174,15 @@ __device__ __forceinline__ void lanes_copy(uint8_t *dst, const uint8_t *src, uin
     const uint32_t done = head + (nw << 2);
     for (uint32_t i = done + lane; i < len; i += N_LANES) dst[i] = src[i];
 }
+// (Not inlined, like lanes_copy: inlined at every call site the byte movers were a quarter of a 148 KB kernel whose
+// instruction-cache hit rate was 84 %.  Halving the code -- this and the re-rolled exit-table sweep -- turned out not to
+// change the kernel's speed, measured; it is kept for the smaller binary and because the kernel no longer spills.)
 // Up to kSmallElem (64) bytes by one thread.  Word path: every load is issued before the first store, so the
 // loads overlap instead of each waiting behind the store before it (the compiler must assume they alias).
 constexpr uint32_t kSmallElem = 64;
 constexpr uint32_t kThreadElem = 256;  // literals up to this long are also moved by one thread (their source is shared memory)
 constexpr uint32_t kStageWords = 8;  // words held in registers at a time (two passes cover 64 bytes)
-__device__ __forceinline__ void small_copy(uint8_t *d, const uint8_t *s, uint32_t len)
+__device__ __noinline__ void small_copy(uint8_t *d, const uint8_t *s, uint32_t len)
 {
     if ((((uintptr_t)d | (uintptr_t)s | len) & 3) == 0) {
         const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s);
@@ -403,35 +415,39 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
             // unrolled, so every tag byte is a compile-time extraction and only the table access touches memory
             const uint32_t blk_len = blk_end - blk_start;
             const uint32_t limit = in_end - blk_start;  // a chain position may not pass this
-            uint32_t w[18];
+            // The sweep runs over four groups of 16 offsets, highest first; a group's 16 bytes (+ 5 bytes of header
+            // look-ahead) are re-loaded from the staged window into registers, inside the group every tag byte is a
+            // compile-time extraction.  (Fully unrolled over all 64 offsets this was a third of the kernel's code.)
             const uint32_t *c32 = reinterpret_cast<const uint32_t *>(S.cin + (size_t)t * kDecSub);
+#pragma unroll 1
+            for (int g = kDecSub / 16 - 1; g >= 0; g--) {
+                uint32_t w[6];
 #pragma unroll
-            for (int k = 0; k < 18; k++) w[k] = c32[k];
+                for (int k = 0; k < 6; k++) w[k] = c32[4 * g + k];
 #pragma unroll
-            for (int o = kDecSub - 1; o >= 0; o--) {
-                const uint32_t tag = (w[o >> 2] >> (8 * (o & 3))) & 0xFFu;
-                const uint32_t kind = tag & 3u;
-                uint64_t nxt;
-                if (kind != 0) {
-                    nxt = (uint32_t)o + ((0x5320u >> (4 * kind)) & 0xFu);  // copy headers: 2, 3 or 5 bytes
-                } else {
-                    const uint32_t m = tag >> 2;
-                    if (m < 60) {
-                        nxt = (uint32_t)o + m + 2;                           // tag + (m+1) literal bytes
+                for (int oo = 15; oo >= 0; oo--) {
+                    const uint32_t o = (uint32_t)(16 * g + oo);
+                    const uint32_t tag = (w[oo >> 2] >> (8 * (oo & 3))) & 0xFFu;
+                    const uint32_t kind = tag & 3u;
+                    uint64_t nxt;
+                    if (kind != 0) {
+                        nxt = o + ((0x5320u >> (4 * kind)) & 0xFu);  // copy headers: 2, 3 or 5 bytes
                     } else {
-                        const uint32_t extra = m - 59;
-                        // the 4 bytes after the tag, assembled from registers
-                        const uint32_t lo_w = w[(o + 1) >> 2], hi_w = w[((o + 1) >> 2) + 1];
-                        const uint32_t v = __funnelshift_r(lo_w, hi_w, 8 * ((o + 1) & 3));
-                        const uint32_t mm = extra == 4 ? v : (v & ((1u << (8 * extra)) - 1u));
-                        nxt = mm == 0xFFFFFFFFu ? ~0ull : (uint64_t)o + 1 + extra + (uint64_t)mm + 1;
+                        const uint32_t m = tag >> 2;
+                        if (m < 60) {
+                            nxt = o + m + 2;                           // tag + (m+1) literal bytes
+                        } else {
+                            // the 4 bytes after the tag, assembled from registers
+                            const uint32_t lo_w = w[(oo + 1) >> 2], hi_w = w[((oo + 1) >> 2) + 1];
+                            nxt = long_literal_next(o, m, __funnelshift_r(lo_w, hi_w, 8 * ((oo + 1) & 3)));
+                        }
                     }
+                    uint32_t x;
+                    if (nxt > limit) x = kExitInvalid;               // header or payload runs past the input
+                    else if (nxt < blk_len) x = S.tbl[(uint32_t)nxt * kDecThreads + t];
+                    else x = nxt - blk_len <= kExitMaxRel ? (uint32_t)(nxt - blk_len) : kExitFar;
+                    S.tbl[o * kDecThreads + t] = (uint8_t)x;
                 }
-                uint32_t x;
-                if (nxt > limit) x = kExitInvalid;               // header or payload runs past the input
-                else if (nxt < blk_len) x = S.tbl[(uint32_t)nxt * kDecThreads + t];
-                else x = nxt - blk_len <= kExitMaxRel ? (uint32_t)(nxt - blk_len) : kExitFar;
-                S.tbl[(uint32_t)o * kDecThreads + t] = (uint8_t)x;
             }
         }
         __syncthreads();
