@@ -45,9 +45,10 @@ constexpr int kDecWin = kDecThreads * kDecSub;     // 16 KiB of compressed input
 constexpr int kDecMaxElems = 2048;                 // descriptors held in shared memory per window
 constexpr uint32_t kSrcIn = 0u << 30, kSrcOut = 1u << 30, kSrcRun = 2u << 30, kSrcMask = 3u << 30, kPosMask = (1u << 30) - 1;
 constexpr int kFlattenRounds = 2, kFlattenHops = 12;
-constexpr uint32_t kLongLiteral = 1024;            // literals this long are copied by the whole CTA
+constexpr uint32_t kLongLiteral = 16384;           // literals this long are copied by the whole CTA, one after the other; shorter ones by a
+                                                   // warp each (measured: 1024 here cost 7 % of the kernel -- the CTA-wide copies serialise)
 constexpr int kMaxLong = 64;
-constexpr int kMaxMid = 128;
+constexpr int kMaxMid = 256;
 constexpr int kGroups = kDecThreads / 8;           // 8-lane groups, one element each
 constexpr uint32_t kExitMaxRel = 250;              // tbl value <= this: exit = sub-block end + value
 constexpr uint32_t kExitFar = 253;                 // exit further away (a long literal): recomputed by walking
@@ -180,7 +181,7 @@ __device__ __noinline__ void lanes_copy(uint8_t *dst, const uint8_t *src, uint32
 // Up to kSmallElem (64) bytes by one thread.  Word path: every load is issued before the first store, so the
 // loads overlap instead of each waiting behind the store before it (the compiler must assume they alias).
 constexpr uint32_t kSmallElem = 64;
-constexpr uint32_t kThreadElem = 256;  // literals up to this long are also moved by one thread (their source is shared memory)
+constexpr uint32_t kThreadElem = 128;  // literals up to this long are also moved by one thread (their source is shared memory)
 constexpr uint32_t kStageWords = 8;  // words held in registers at a time (two passes cover 64 bytes)
 __device__ __noinline__ void small_copy(uint8_t *d, const uint8_t *s, uint32_t len)
 {
@@ -723,7 +724,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                 S.e_done[e] = (uint16_t)round;
             }
             if (round == 1) {
-                // literals of kThreadElem+1 .. 1023 bytes: one warp each, from the list the descriptor pass made
+                // literals of kThreadElem+1 .. kLongLiteral-1 bytes: one warp each, from the list the descriptor pass made
                 const uint32_t nmid = S.n_mid;
                 if (nmid <= (uint32_t)kMaxMid) {
                     for (uint32_t q = wrp; q < nmid; q += kDecThreads / 32) {
