@@ -49,6 +49,8 @@ constexpr uint32_t kLongLiteral = 16384;           // literals this long are cop
                                                    // warp each (measured: 1024 here cost 7 % of the kernel -- the CTA-wide copies serialise)
 constexpr int kMaxLong = 64;
 constexpr int kMaxMid = 256;
+constexpr uint32_t kMidPiece = 512;                // a warp moves a literal in pieces of this many bytes
+static_assert(kDecMaxElems <= 2048 && kLongLiteral / kMidPiece <= 32, "mid_list packs element (11 bits) and piece (5 bits)");
 constexpr int kGroups = kDecThreads / 8;           // 8-lane groups, one element each
 constexpr uint32_t kExitMaxRel = 250;              // tbl value <= this: exit = sub-block end + value
 constexpr uint32_t kExitFar = 253;                 // exit further away (a long literal): recomputed by walking
@@ -67,8 +69,9 @@ struct DecodeSmem {
     uint32_t bcast[4];
     uint32_t n_long;                 // long literals of the current window
     uint32_t long_list[kMaxLong];
-    uint32_t n_mid;                  // literals of kThreadElem+1 .. kLongLiteral-1 bytes (one warp each)
-    uint16_t mid_list[kMaxMid];
+    uint32_t n_mid;                  // pieces (<= kMidPiece bytes) of the literals of kThreadElem+1 .. kLongLiteral-1 bytes
+    uint32_t mid_next;               // next piece to hand out (warps take pieces as they become free)
+    uint16_t mid_list[kMaxMid];      // element | piece << 11
     int fail;        // preamble / parse stage
     int fail_desc;   // descriptor stage (separate word: it is written while slow threads may still read `fail`)
 };
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
     while (wb < in_end) {
         // ---- stage the window.  Chunks are byte-packed in a frame, so the chunk is rarely aligned: read aligned
         //      16-byte words and shift them so that S.cin[0] is the byte at `wb` (word loads stay aligned later) ---
-        if (t == 0) { S.n_long = 0; S.n_mid = 0; }
+        if (t == 0) { S.n_long = 0; S.n_mid = 0; S.mid_next = 0; }
         uint32_t staged_end;  // input position up to which S.cin holds this window's bytes
         {
             const uintptr_t gaddr = (uintptr_t)(src + wb);
@@ -534,8 +537,10 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                         uint32_t q = atomicAdd(&S.n_long, 1u);
                         if (q < (uint32_t)kMaxLong) S.long_list[q] = e;
                     } else if (len > kThreadElem) {
-                        uint32_t q = atomicAdd(&S.n_mid, 1u);
-                        if (q < (uint32_t)kMaxMid) S.mid_list[q] = (uint16_t)e;
+                        const uint32_t np = (len + kMidPiece - 1) / kMidPiece;
+                        const uint32_t q = atomicAdd(&S.n_mid, np);
+                        for (uint32_t pc = 0; pc < np; pc++)
+                            if (q + pc < (uint32_t)kMaxMid) S.mid_list[q + pc] = (uint16_t)(e | (pc << 11));
                     }
                     pos += hdr + len;
                 } else {
@@ -727,13 +732,20 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                 // literals of kThreadElem+1 .. kLongLiteral-1 bytes: one warp each, from the list the descriptor pass made
                 const uint32_t nmid = S.n_mid;
                 if (nmid <= (uint32_t)kMaxMid) {
-                    for (uint32_t q = wrp; q < nmid; q += kDecThreads / 32) {
-                        const uint32_t e = S.mid_list[q];
+                    // pieces are handed out one at a time, so a warp that drew short ones simply draws more
+                    for (;;) {
+                        uint32_t q = 0;
+                        if ((t & 31) == 0) q = atomicAdd(&S.mid_next, 1u);
+                        q = __shfl_sync(HAP_FULL_MASK, q, 0);
+                        if (q >= nmid) break;
+                        const uint32_t item = S.mid_list[q];
+                        const uint32_t e = item & 2047u, off = (item >> 11) * kMidPiece;
                         const uint32_t len = S.e_len[e];
+                        const uint32_t n = len - off < kMidPiece ? len - off : kMidPiece;
                         const uint32_t ap = S.e_a[e] & kPosMask;  // only literals are this long
                         const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= staged_end) ? cinp + (ap - wb) : src + ap;
-                        lanes_copy<32>(dst + S.e_dst[e], sl, len, t & 31);
-                        if ((t & 31) == 0) S.e_done[e] = 1;
+                        lanes_copy<32>(dst + S.e_dst[e] + off, sl + off, n, t & 31);
+                        if ((t & 31) == 0) S.e_done[e] = 1;   // honoured from round 2 on, when every piece is in place
                     }
                 } else {
                     // more of them than the list holds (cannot happen with 16 KiB of input per window, kept for safety)
