@@ -44,7 +44,7 @@ constexpr int kDecSub = 64;                        // compressed bytes owned by 
 constexpr int kDecWin = kDecThreads * kDecSub;     // 16 KiB of compressed input per window
 constexpr int kDecMaxElems = 2048;                 // descriptors held in shared memory per window
 constexpr uint32_t kSrcIn = 0u << 30, kSrcOut = 1u << 30, kSrcRun = 2u << 30, kSrcMask = 3u << 30, kPosMask = (1u << 30) - 1;
-constexpr int kFlattenRounds = 2, kFlattenHops = 12;
+constexpr int kFlattenRounds = 1, kFlattenHops = 12;  // (a second flatten round was measured: same execution rounds, 1.5-2 % slower; none: 3.8 -> 7.9 rounds on Google-Snappy streams)
 constexpr uint32_t kLongLiteral = 16384;           // literals this long are copied by the whole CTA, one after the other; shorter ones by a
                                                    // warp each (measured: 1024 here cost 7 % of the kernel -- the CTA-wide copies serialise)
 constexpr int kMaxLong = 64;
