@@ -14,6 +14,13 @@
 
 #define HAP_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define HAP_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+
+// Shared-memory accesses through a 32-bit shared-window address held in a register (for serial pointer-chasing
+// loops: with generic addressing ptxas re-derives the window base -- an S2R -- in every iteration).
+typedef uint32_t hap_saddr_t;
+__device__ __forceinline__ hap_saddr_t hap_smem_addr(const void *p) { return (hap_saddr_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t hap_lds_u8(hap_saddr_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void hap_sts_u16(hap_saddr_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v)); }
 #endif
 
 #define HAP_FULL_MASK 0xffffffffu

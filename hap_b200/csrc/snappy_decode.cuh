@@ -67,6 +67,7 @@ struct DecodeSmem {
     uint16_t entry[kDecThreads];     // true entry offset of each sub-block, 0xFFFF = jumped over
     uint32_t scratch[kDecThreads / 32];
     uint32_t bcast[4];
+    unsigned long long saddr_box;    // see the chain hop
     uint32_t n_long;                 // long literals of the current window
     uint32_t long_list[kMaxLong];
     uint32_t n_mid;                  // pieces (<= kMidPiece bytes) of the literals of kThreadElem+1 .. kLongLiteral-1 bytes
@@ -460,10 +461,15 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
             // window-relative positions: the dependent chain per hop is one table load plus a few ALU ops
             const uint32_t rel_end = in_end - wb;
             uint32_t rel = 0;
+            // The table's shared-window address, read back through a volatile word: ptxas otherwise re-derives it from
+            // the CTA-in-cluster id (an S2R, tens of cycles on this thread's critical path) in EVERY iteration of the hop.
+            volatile hap_saddr_t *base_box = reinterpret_cast<volatile hap_saddr_t *>(&S.saddr_box);
+            *base_box = hap_smem_addr(S.tbl);
+            const hap_saddr_t tbl_s = *base_box, entry_s = tbl_s + (hap_saddr_t)((const uint8_t *)S.entry - (const uint8_t *)S.tbl);
             while (rel < rel_end && rel < span * kDecSub) {
                 const uint32_t blk = rel >> 6, o = rel & 63;
-                const uint32_t x = S.tbl[o * kDecThreads + blk];
-                S.entry[blk] = (uint16_t)o;
+                const uint32_t x = hap_lds_u8(tbl_s + (o * kDecThreads + blk));
+                hap_sts_u16(entry_s + 2 * blk, o);
                 uint32_t bend = (blk + 1) << 6;
                 bend = bend < rel_end ? bend : rel_end;
                 if (x <= kExitMaxRel) {

@@ -260,6 +260,10 @@ static inline void __syncthreads() { emu::syncthreads(); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_barrier(mask); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
+typedef uintptr_t hap_saddr_t;
+static inline hap_saddr_t hap_smem_addr(const void *p) { return (hap_saddr_t)p; }
+static inline uint32_t hap_lds_u8(hap_saddr_t a) { return *(const uint8_t *)a; }
+static inline void hap_sts_u16(hap_saddr_t a, uint32_t v) { *(uint16_t *)a = (uint16_t)v; }
 static inline void hap_bar_sync(int id, int n) { emu::bar_sync(id, n); }
 static inline void hap_bar_arrive(int id, int n) { emu::bar_arrive(id, n); }
 static inline int hap_bar_or(int id, int n, int pred) { return emu::bar_or(id, n, pred); }
