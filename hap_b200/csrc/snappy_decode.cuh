@@ -52,8 +52,9 @@ constexpr int kMaxMid = 256;
 constexpr uint32_t kMidPiece = 512;                // a warp moves a literal in pieces of this many bytes
 static_assert(kDecMaxElems <= 2048 && kLongLiteral / kMidPiece <= 32, "mid_list packs element (11 bits) and piece (5 bits)");
 constexpr int kGroups = kDecThreads / 8;           // 8-lane groups, one element each
-constexpr uint32_t kExitMaxRel = 250;              // tbl value <= this: exit = sub-block end + value
-constexpr uint32_t kExitFar = 253;                 // exit further away (a long literal): recomputed by walking
+constexpr uint32_t kExitMaxRel = 186;              // tbl value <= this: exit = sub-block end + value
+constexpr uint32_t kExitFarBase = 187;             // kExitFarBase + o (o = 0..63): the chain leaves through a long literal whose
+                                                   // header sits at offset o of the sub-block; its end is read from that header
 constexpr uint32_t kExitInvalid = 254;             // the chain runs into an invalid element header
 
 struct DecodeSmem {
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                     uint32_t x;
                     if (nxt > limit) x = kExitInvalid;               // header or payload runs past the input
                     else if (nxt < blk_len) x = S.tbl[(uint32_t)nxt * kDecThreads + t];
-                    else x = nxt - blk_len <= kExitMaxRel ? (uint32_t)(nxt - blk_len) : kExitFar;
+                    else x = nxt - blk_len <= kExitMaxRel ? (uint32_t)(nxt - blk_len) : kExitFarBase + o;
                     S.tbl[o * kDecThreads + t] = (uint8_t)x;
                 }
             }
@@ -478,15 +479,11 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                     S.fail = 1;
                     break;
                 } else {
-                    // a long literal leaves this sub-block by more than a byte can hold: walk to it
-                    uint32_t p2 = wb + rel;
-                    for (;;) {
-                        uint32_t len, aux, hdr, kind;
-                        if (!read_element_header(cinp, wb, p2, in_end, len, aux, hdr, kind)) { S.fail = 1; p2 = in_end; break; }
-                        p2 += hdr + (kind == 0 ? len : 0);
-                        if (p2 - wb >= bend) break;
-                    }
-                    rel = p2 - wb;
+                    // a long literal leaves this sub-block by more than a byte can hold: the table names its header
+                    const uint32_t p2 = wb + (blk << 6) + (x - kExitFarBase);
+                    uint32_t len, aux, hdr, kind;
+                    if (!read_element_header(cinp, wb, p2, in_end, len, aux, hdr, kind) || kind != 0) { S.fail = 1; break; }
+                    rel = p2 + hdr + len - wb;
                 }
             }
         }
