@@ -49,7 +49,7 @@ constexpr uint32_t kLongLiteral = 16384;           // literals this long are cop
                                                    // warp each (measured: 1024 here cost 7 % of the kernel -- the CTA-wide copies serialise)
 constexpr int kMaxLong = 64;
 constexpr int kMaxMid = 256;
-constexpr uint32_t kMidPiece = 512;                // a warp moves a literal in pieces of this many bytes
+constexpr uint32_t kMidPiece = 1024;               // a warp moves a literal in pieces of this many bytes (256: +2 %, 512: +1.5 % kernel time)
 static_assert(kDecMaxElems <= 2048 && kLongLiteral / kMidPiece <= 32, "mid_list packs element (11 bits) and piece (5 bits)");
 constexpr int kGroups = kDecThreads / 8;           // 8-lane groups, one element each
 constexpr uint32_t kExitMaxRel = 186;              // tbl value <= this: exit = sub-block end + value
