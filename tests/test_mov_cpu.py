@@ -233,3 +233,18 @@ def test_ffmpeg_decodes_our_frames(lib, tmp_path):
             pytest.skip("this OpenCV/FFmpeg build has no Hap decoder")
         ref = oracles.bc_decode(kind, tex, w, h)[..., :3][..., ::-1]
         assert np.abs(bgr.astype(int) - ref.astype(int)).max() <= 3, cc
+
+
+def test_reader_survives_damaged_movies_under_sanitizers(tmp_path):
+    """tests/emu/test_mov_fuzz.cc: the reader source under ASan + UBSan on 3000 truncated / bit-flipped / spliced
+    movies -- it refuses them or hands out frames that lie inside the file."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "mov_fuzz")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                    "-I", os.path.join(root, "hap_b200", "csrc"), "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "emu", "test_mov_fuzz.cc"), "-o", exe], check=True)
+    p = subprocess.run([exe, "3000"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    assert "without a fault" in p.stdout
