@@ -8,13 +8,19 @@
 // Work decomposition: ONE THREAD PER BLOCK.  SURVEY.md H1: at the bandwidth target a 4x4 block has
 // ~13 warp-instructions if a warp owns it but ~420 thread-instructions if a thread owns it; all 16
 // texels live in registers, every reduction is a private serial sum (no shuffles, no idle lanes),
-// and coalescing is restored by staging tiles through shared memory in the kernels (bc_encode.cuh).
+// and the four 16-byte row pieces of neighbouring threads are contiguous, so the loads are coalesced as
+// they are (bc_encode.cuh).
 //
-// Colour fit: principal axis of the block's covariance (power iteration), then REFINE rounds of
-// [project texels onto the current segment -> 4 clusters] + [2x2 least squares for the endpoints
-// given those clusters] -- the same normal equations cluster fit solves, for the partition the
-// current endpoints imply instead of all 969 -- then 5:6:5 rounding and a final nearest-index pass
-// against the decoder's integer palette.
+// The fits, all on the same pattern -- principal axis of the block's covariance, 4 clusters by projection,
+// the 2x2 least-squares system for the two endpoints given those clusters (the normal equations cluster
+// fit solves, for the partition the axis implies instead of all 969), endpoints onto the 5:6:5 grid by a
+// small search with the decoder's expanded values, indices against the decoder's palette:
+//   * scaled YCoCg chroma (encode_ycocg_chroma): 2-D, closed-form axis, one start, ~600 instructions;
+//   * RGB (encode_rgb_block): 3-D, power iteration, 2 x 2 starts scored after grid snapping, one Lloyd
+//     round on the winner, exact nearest-palette indices, ~2 600 instructions;
+//   * BC4 (encode_bc4_scaled): endpoints = min / max, indices by one biased fixed-point rounding per texel.
+// Instruction counts are the currency here: the kernels are bound by instruction issue, and every step was
+// held to the PSNR bar on the host build of this very source before it went to the GPU.
 //
 // Floating point is written with explicit fused multiply-adds (hap_fma) and the translation unit is
 // built with -fmad=false, so the CPU twin used by the tests (tests/emu/bc_twin.cc) reproduces the

@@ -4,15 +4,16 @@
 // (/root/reference/source/hap.c:448-476, call site :453).  The reference's loop is serial over chunks
 // and Snappy is serial inside a chunk; here a chunk is cut into independent 32 KiB FRAGMENTS (a raw
 // Snappy stream is varint(length) followed by elements, so fragment element streams concatenate
-// into one legal chunk stream as long as copies never reach outside their fragment), one CTA per
-// fragment, and inside the fragment every 4-byte word is handled by its own thread:
+// into one legal chunk stream as long as copies never reach outside their fragment), one resident CTA
+// per SM striding over the fragments, and inside a fragment every 4-byte word is handled by its own thread:
 //   1. first-occurrence hash of every aligned word (shared-memory table, atomicMin => deterministic);
 //   2. each word picks a source: the word one DXT block back when its whole block repeats the
 //      previous block (block RLE, decodes as one periodic fill), else the first earlier occurrence
 //      of the same word.  Choosing FIRST occurrences makes copies point at literal data, so the
 //      decoder's dependency depth stays ~1 (see snappy_decode.cuh);
 //   3. runs of words with one distance become copy elements (<= 64 bytes each), everything else
-//      literal runs; element sizes are prefix-summed and every word writes its own bytes.
+//      literal runs; element sizes are prefix-summed and every word writes its own bytes (for this
+//      last step the words are re-dealt so that the lanes of a warp write neighbouring bytes).
 // The output differs from Google's encoder byte-for-byte (the reference pins no Snappy bytes,
 // SURVEY.md 8c); parity is: the reference's HapDecode reproduces the input exactly.
 #pragma once
