@@ -196,6 +196,24 @@ int main(int argc, char **argv)
         mix.insert(mix.end(), noise.begin(), noise.begin() + 16384);
         cases.push_back({"mixed_chunk_fallback", {{mix, 0x01, 1, 2}}});
     }
+    // random shapes: sizes that are not multiples of the fragment or of the chunk count, 1..9 chunks, content
+    // stitched from picture blocks, repeated blocks, flat runs and noise (exercises partial fragments, chunk-count
+    // limiting, both fallbacks and the persistent grid's striding in combinations no hand-made case has)
+    for (int r = 0; r < 8; r++) {
+        const size_t blocks16 = 200 + rng() % 12000;
+        std::vector<uint8_t> v;
+        while (v.size() < blocks16 * 16) {
+            const int what = rng() % 5;
+            const size_t n = 16 * (1 + rng() % 700);
+            if (what == 0) { size_t at = (rng() % (ycocg.size() / 16 - n / 16 - 1)) * 16; v.insert(v.end(), ycocg.begin() + at, ycocg.begin() + at + n); }
+            else if (what == 1 && v.size() >= 4096) { size_t at = v.size() - 16 * (1 + rng() % 200); for (size_t i = 0; i < n; i++) v.push_back(v[at + i % 16]); }
+            else if (what == 2) { uint8_t b16[16]; for (auto &b : b16) b = (uint8_t)rng(); for (size_t i = 0; i < n; i++) v.push_back(b16[i % 16]); }
+            else if (what == 3) { for (size_t i = 0; i < n; i++) v.push_back((uint8_t)rng()); }
+            else { for (size_t i = 0; i < n; i++) v.push_back((uint8_t)((i / 16) & 0xFF)); }
+        }
+        v.resize(blocks16 * 16);
+        cases.push_back({"random_" + std::to_string(r), {{v, 0x01, 1, (unsigned)(1 + rng() % 9)}}});
+    }
     for (int mode = 0; mode < modes; mode++)
         for (auto &c : cases) {
             double ratio = 0;
