@@ -248,3 +248,34 @@ def test_reader_survives_damaged_movies_under_sanitizers(tmp_path):
                        env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     assert "without a fault" in p.stdout
+
+
+@pytest.mark.parametrize("who", ["oracle", "reference"])
+def test_ffmpeg_decodes_snappy_frames_of_oracle_and_reference(lib, tmp_path, who):
+    """Closes the triangle on the CPU: Snappy-compressed, chunked frames written by the oracle port and by the
+    unmodified reference build go through our movie writer and are decoded by FFmpeg's independent Hap decoder to the
+    picture the oracle's block decoder gets from the same texture."""
+    cv2 = pytest.importorskip("cv2")
+    import oracles
+    import twin
+    from hap_b200 import synth
+    from hap_b200.abi import HapCompressorSnappy
+    codec = oracles.oracle_abi() if who == "oracle" else oracles.ref_abi()
+    if codec is None:
+        pytest.skip("reference build unavailable")
+    w, h = 256, 128
+    img = synth.frame(w, h, 1).numpy()
+    for kind, fmt, cc, chunks in (("bc1", HapTextureFormat_RGB_DXT1, "Hap1", 1), ("ycocg", HapTextureFormat_YCoCg_DXT5, "HapY", 4)):
+        tex = twin.encode(kind, img)
+        r, f = codec.encode([tex], [fmt], [HapCompressorSnappy], [chunks])
+        assert r == 0 and mov.fourcc_for_frame(f) == (0, cc)
+        path = str(tmp_path / f"{who}_{cc}.mov")
+        with mov.MovWriter(path, cc, w, h, 600) as wr:
+            assert wr.write(f, 20) == 0 and wr.write(f, 20) == 0
+        cap = cv2.VideoCapture(path, cv2.CAP_FFMPEG)
+        ok, bgr = cap.read() if cap.isOpened() else (False, None)
+        cap.release()
+        if not ok:
+            pytest.skip("this OpenCV/FFmpeg build has no Hap decoder")
+        ref = oracles.bc_decode(kind, tex, w, h)[..., :3][..., ::-1]
+        assert np.abs(bgr.astype(int) - ref.astype(int)).max() <= 3, (who, cc)
