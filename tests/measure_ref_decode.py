@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
-"""How fast does K7 decode frames made by the REFERENCE encoder (unmodified hap.c + Google Snappy)?
+"""TEST INFRASTRUCTURE (it lives under tests/ because it drives the reference build, which only tests may touch).
+How fast does K7 decode frames made by the REFERENCE encoder (unmodified hap.c + Google Snappy)?
 bench.py times streams from our own encoder; players mostly meet files written by others.  Run on the GPU box:
 
-    python tools/measure_ref_decode.py [--frames 16] > gpurun_out/ref_decode.json
+    python tests/measure_ref_decode.py [--frames 16] > gpurun_out/ref_decode.json
 
 Uses oracle/_ref only to PRODUCE the input frames (on the host, outside every timed region)."""
 import argparse
@@ -12,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # oracles.py
 
 
 def main():

@@ -10,5 +10,5 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; head -c 400 gpurun_out/bench_default.json; echo
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:hapb200|hap_|snappy_|bc_' -c 400 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 2 --warmup 3 --profile --no-overlap > gpurun_out/launches_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:snappy_decode_chunks|snappy_encode_fragments|bc_encode_kernel|hap_place_fragments' -c 4 -f -o gpurun_out/prof_final python bench.py --steps 1 --warmup 3 --frames 55 --profile --no-overlap > gpurun_out/ncu_final.log 2>&1
-timeout 200 python tools/measure_ref_decode.py > gpurun_out/ref_stream_decode.json 2> gpurun_out/ref_stream_decode.err
+timeout 200 python tests/measure_ref_decode.py > gpurun_out/ref_stream_decode.json 2> gpurun_out/ref_stream_decode.err
 echo done
