@@ -66,7 +66,7 @@ struct StageScope {
     } while (0)
 
 struct Runtime {
-    std::mutex mu;          // serialises the host-pointer entry points (they share the legacy default stream)
+    std::mutex mu;          // serialises the calls that run on the legacy default stream (those with a device pointer among their buffers)
     bool ready = false;
     bool failed = false;
     cudaStream_t stream = nullptr;
