@@ -4,7 +4,9 @@ Frames of a stream are independent (HapVideoDRAFT.md:29-34), so frame f goes to 
 collective sits on the data path.  When a consumer needs the encoded stream in one place, the
 variable-size frames are gathered with one all-gather of lengths plus one padded all-gather of bytes
 (`gather_encoded_frames`); it works on NCCL (device tensors) and gloo (CPU tensors) alike.
-A single very large frame can instead be split into bands of whole chunks (`chunk_band_for_rank`).
+A single very large frame can instead be split into bands of whole chunks (`chunk_band_for_rank`): every rank
+encodes its band with the ordinary single-frame call, one gather brings the band frames together
+(`gather_band_frames`) and `assemble_banded_frame` splices them into the frame of the whole picture.
 """
 from __future__ import annotations
 
@@ -52,3 +54,114 @@ def gather_encoded_frames(local_frames: torch.Tensor, local_used: torch.Tensor, 
         r, i = f % world, f // world
         out.append(all_frames[r][i, : int(all_used[r][i])])
     return out
+
+
+# ---- one huge frame cut into bands of whole chunks (second case) ------------------------------------
+# Every rank runs the ordinary single-texture encode (HapEncode / HapB200EncodeRGBA) on ITS band of block rows with
+# ITS share of the chunk count; that yields a complete little Hap frame per band.  Chunks are independent Snappy
+# streams laid out back to back behind two tables (hap.c:430-476), so the frame of the whole picture is: one section
+# header, one Decode Instructions container whose tables are the bands' tables one after the other, the bands' chunk
+# payloads one after the other.  `assemble_banded_frame` does exactly that on the gathered band frames (host bytes);
+# `gather_band_frames` is the one exchange step (variable-size gather, NCCL or gloo).
+
+_SEC_DI, _SEC_COMPRESSORS, _SEC_SIZES, _SEC_OFFSETS = 0x01, 0x02, 0x03, 0x04
+_CHUNK_RAW, _CHUNK_SNAPPY, _COMPLEX = 0x0A, 0x0B, 0x0C
+
+
+def _section(buf: bytes, off: int, end: int):
+    """(header bytes, body length, type) of the section at off (hap.c:137-187); raises ValueError when it does not fit."""
+    if end - off < 4:
+        raise ValueError("truncated section header")
+    length = buf[off] | (buf[off + 1] << 8) | (buf[off + 2] << 16)
+    hdr = 4
+    if length == 0:
+        if end - off < 8:
+            raise ValueError("truncated 8-byte section header")
+        length = int.from_bytes(buf[off + 4: off + 8], "little")
+        hdr = 8
+    if length > end - off - hdr:
+        raise ValueError("section longer than its buffer")
+    return hdr, length, buf[off + 3]
+
+
+def _put_section_header(length: int, typ: int, force8: bool = False) -> bytes:
+    if length < (1 << 24) and not force8 and length != 0:
+        return bytes([length & 255, (length >> 8) & 255, (length >> 16) & 255, typ])
+    return bytes([0, 0, 0, typ]) + length.to_bytes(4, "little")
+
+
+def split_single_texture_frame(frame: bytes):
+    """One single-texture Hap frame -> (format nibble, [(compressor 0x0A|0x0B, chunk payload bytes), ...]).
+    A verbatim section (0xA?) comes back as one raw chunk; an 0xB? section as one Snappy chunk."""
+    hdr, length, typ = _section(frame, 0, len(frame))
+    comp, fmt = typ >> 4, typ & 0xF
+    body = frame[hdr: hdr + length]
+    if comp == _CHUNK_RAW or comp == _CHUNK_SNAPPY:
+        return fmt, [(comp, bytes(body))]
+    if comp != _COMPLEX:
+        raise ValueError("not a single-texture Hap frame")
+    dh, dlen, dtyp = _section(body, 0, len(body))
+    if dtyp != _SEC_DI:
+        raise ValueError("complex section without Decode Instructions")
+    compressors = sizes = offsets = None
+    off, end = dh, dh + dlen
+    while off < end:
+        sh, slen, styp = _section(body, off, end)
+        data = body[off + sh: off + sh + slen]
+        if styp == _SEC_COMPRESSORS:
+            compressors = list(data)
+        elif styp == _SEC_SIZES:
+            sizes = [int.from_bytes(data[i: i + 4], "little") for i in range(0, len(data) - 3, 4)]
+        elif styp == _SEC_OFFSETS:
+            offsets = [int.from_bytes(data[i: i + 4], "little") for i in range(0, len(data) - 3, 4)]
+        off += sh + slen
+    if compressors is None or sizes is None or len(compressors) != len(sizes) or (offsets is not None and len(offsets) != len(sizes)):
+        raise ValueError("inconsistent Decode Instructions tables")
+    payload = body[end:]
+    chunks, at = [], 0
+    for i, (c, n) in enumerate(zip(compressors, sizes)):
+        if offsets is not None:
+            at = offsets[i]
+        if c not in (_CHUNK_RAW, _CHUNK_SNAPPY) or at + n > len(payload):
+            raise ValueError("bad chunk table entry")
+        chunks.append((c, bytes(payload[at: at + n])))
+        at += n
+    return fmt, chunks
+
+
+def assemble_banded_frame(band_frames: List[bytes]) -> bytes:
+    """Single-texture Hap frames of consecutive bands of one picture -> the Hap frame of the whole picture
+    (a Complex section: hap.c:430-476; chunk i of the result is chunk i of the concatenated bands)."""
+    fmt, chunks = None, []
+    for bf in band_frames:
+        f, ch = split_single_texture_frame(bytes(bf))
+        if fmt is not None and f != fmt:
+            raise ValueError("bands of different texture formats")
+        fmt = f
+        chunks.extend(ch)
+    if fmt is None or not chunks:
+        raise ValueError("no bands")
+    k = len(chunks)
+    comp_table = _put_section_header(k, _SEC_COMPRESSORS) + bytes(c for c, _ in chunks)
+    size_table = _put_section_header(4 * k, _SEC_SIZES) + b"".join(len(p).to_bytes(4, "little") for _, p in chunks)
+    di = _put_section_header(len(comp_table) + len(size_table), _SEC_DI) + comp_table + size_table
+    body = di + b"".join(p for _, p in chunks)
+    return _put_section_header(len(body), (_COMPLEX << 4) | fmt) + body
+
+
+def gather_band_frames(band_frame: torch.Tensor, used: int, dst: int = 0):
+    """band_frame: uint8 tensor holding this rank's band frame in its first `used` bytes (device tensor with NCCL,
+    CPU tensor with gloo).  Returns on rank `dst` the list of all ranks' band frames as bytes, in rank order (= band
+    order); None elsewhere.  One all_gather of lengths, one all_gather of padded payloads."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = torch.tensor([used], dtype=torch.int64, device=band_frame.device)
+    lens = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(lens, n)
+    cap = max(int(x.item()) for x in lens)
+    pad = torch.zeros(cap, dtype=torch.uint8, device=band_frame.device)
+    pad[:used] = band_frame[:used]
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    if rank != dst:
+        return None
+    return [bytes(parts[r][: int(lens[r].item())].cpu().numpy().tobytes()) for r in range(world)]
