@@ -295,3 +295,36 @@ def test_concurrent_host_calls_are_reentrant(lib):
 
     with ThreadPoolExecutor(8) as pool:
         assert all(pool.map(work, range(len(payloads))))
+
+
+def test_banded_single_frame_encode_assembles_to_one_frame(lib):
+    """SURVEY.md 8e, second case, on one GPU: a picture cut into three bands of block rows, each band encoded on its own
+    (as each rank would), the band frames spliced by sharding.assemble_banded_frame; the result decodes here and in
+    the oracle to the bands' textures one after the other, with the bands' chunk counts added up."""
+    import hap_b200.lib as L
+    from hap_b200 import sharding
+    w, h = 512, 384
+    img = synth.frame(w, h, 5).numpy()
+    rows = [(0, 128), (128, 256), (256, 384)]
+    ks = [2, 1, 3]
+    band_frames, band_tex = [], []
+    for (y0, y1), k in zip(rows, ks):
+        band = np.ascontiguousarray(img[y0:y1])
+        r, f = lib.encode_rgba(band, w, y1 - y0, L.HapB200Codec_HapY, hap_b200.HapCompressorSnappy, k)
+        assert r == 0
+        n = lib.texture_bytes(w, y1 - y0, L.HapB200Codec_HapY)
+        r, tex, fmt, _ = lib.decode(f, 0, n)
+        assert r == 0 and fmt == hap_b200.HapTextureFormat_YCoCg_DXT5
+        band_frames.append(f)
+        band_tex.append(tex)
+    whole = sharding.assemble_banded_frame(band_frames)
+    want = b"".join(band_tex)
+    assert lib.chunk_count(whole, 0) == (0, sum(lib.chunk_count(f, 0)[1] for f in band_frames))
+    r, tex, fmt, calls = lib.decode(whole, 0, len(want))
+    assert r == 0 and tex == want and fmt == hap_b200.HapTextureFormat_YCoCg_DXT5
+    ro, tex_o, _, _ = oracles.oracle_abi().decode(whole, 0, len(want))
+    assert ro == 0 and tex_o == want
+    # and the whole picture's texture is the same blocks: bands are whole block rows
+    r, f_all = lib.encode_rgba(img, w, h, L.HapB200Codec_HapY, hap_b200.HapCompressorSnappy, 6)
+    r2, tex_all, _, _ = lib.decode(f_all, 0, len(want))
+    assert r == 0 and r2 == 0 and tex_all == want
