@@ -14,7 +14,6 @@ OUT = os.path.join(HERE, "libhap_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-DHAPB200_DECODE_PHASE_CYCLES",   # per-phase cycle counters of the decode kernel (5 atomics per window)
     "-fmad=false",             # FMAs are written explicitly (bc_block.cuh) so the CPU twin matches bit for bit
     "-Xcompiler", "-fPIC",
     "-shared", "--cudart", "shared",
@@ -39,17 +38,18 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(s) <= t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = OUT) -> str:
+    """extra_flags / out: variant builds for A/B measurements (loaded through HAPB200_LIBRARY); the product is OUT."""
+    if not force and out == OUT and up_to_date():
         return OUT
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, os.path.join(SRC, "hap_api.cu")]
+    cmd = [nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(SRC, "hap_api.cu")]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         sys.stderr.write(p.stdout + p.stderr)
         raise RuntimeError("nvcc failed")
     if verbose:
         print(p.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -169,7 +169,8 @@ struct BcDecodeGeom {
 template <int KIND>
 __global__ void __launch_bounds__(kBcThreads) bc_decode_kernel(const uint8_t *__restrict__ blocks,
                                                                 const uint8_t *__restrict__ alpha_blocks,
-                                                                BcDecodeGeom G, uint8_t *__restrict__ rgba)
+                                                                BcDecodeGeom G, uint8_t *__restrict__ rgba,
+                                                                const uint32_t *__restrict__ frame_results)
 {
     const uint32_t nblocks = G.blocks_x * G.blocks_y;
     const uint32_t bi = blockIdx.x * kBcThreads + threadIdx.x;
@@ -177,7 +178,12 @@ __global__ void __launch_bounds__(kBcThreads) bc_decode_kernel(const uint8_t *__
     const uint32_t by = bi / G.blocks_x, bx = bi - by * G.blocks_x;
     const uint8_t *in = blocks + (uint64_t)blockIdx.y * G.in_stride;
     uint32_t px[16];
-    if (KIND == kBcDxt1 || KIND == kBcRgtc1) {
+    // frame_results (optional): HapResult per frame of the decode that filled `blocks`.  A frame that failed has no
+    // texture in its slot (the slot holds whatever the memory pool handed out): its picture is written as zeros.
+    if (frame_results && frame_results[blockIdx.y] != 0u /* HapResult_No_Error */) {
+#pragma unroll
+        for (int t = 0; t < 16; t++) px[t] = 0;
+    } else if (KIND == kBcDxt1 || KIND == kBcRgtc1) {
         uint2 v = reinterpret_cast<const uint2 *>(in)[bi];
         decode_block(KIND, v.x, v.y, 0, 0, px);
     } else {

@@ -277,7 +277,7 @@ uint32_t launch_block_encode(const uint8_t *rgba, uint32_t frames, uint64_t fram
 
 uint32_t launch_block_decode(const uint8_t *blocks, const uint8_t *alpha, uint32_t frames, uint64_t blocks_stride,
                              uint64_t alpha_stride, uint32_t width, uint32_t height, const CodecInfo &ci, uint8_t *rgba,
-                             uint64_t frame_stride, uint64_t row_bytes, cudaStream_t st)
+                             uint64_t frame_stride, uint64_t row_bytes, cudaStream_t st, const uint32_t *frame_results = nullptr)
 {
     BcDecodeGeom g;
     g.blocks_x = width / 4;
@@ -289,17 +289,17 @@ uint32_t launch_block_decode(const uint8_t *blocks, const uint8_t *alpha, uint32
     g.frame_bytes = frame_stride;
     dim3 grid((g.blocks_x * g.blocks_y + kBcThreads - 1) / kBcThreads, frames);
     switch (ci.bc_kind) {
-    case kBcDxt1: HAP_KLAUNCH(kStBcDecode, bc_decode_kernel<kBcDxt1>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
-    case kBcDxt5: HAP_KLAUNCH(kStBcDecode, bc_decode_kernel<kBcDxt5>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
-    case kBcRgtc1: HAP_KLAUNCH(kStBcDecode, bc_decode_kernel<kBcRgtc1>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
-    default: HAP_KLAUNCH(kStBcDecode, bc_decode_kernel<kBcYCoCg>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba); break;
+    case kBcDxt1: HAP_KLAUNCH(kStBcDecode, bc_decode_kernel<kBcDxt1>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba, frame_results); break;
+    case kBcDxt5: HAP_KLAUNCH(kStBcDecode, bc_decode_kernel<kBcDxt5>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba, frame_results); break;
+    case kBcRgtc1: HAP_KLAUNCH(kStBcDecode, bc_decode_kernel<kBcRgtc1>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba, frame_results); break;
+    default: HAP_KLAUNCH(kStBcDecode, bc_decode_kernel<kBcYCoCg>, grid, dim3(kBcThreads), 0, st, blocks, alpha, g, rgba, frame_results); break;
     }
     return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
 }
 
 // device frames -> texture `index` of each; jobs scratch is allocated here
 uint32_t launch_decode_batch(const uint8_t *in, uint32_t frames, uint64_t in_stride, const unsigned long long *in_bytes,
-                             uint32_t index, uint32_t max_chunks, uint8_t *out, uint64_t out_stride,
+                             uint32_t index, uint32_t max_chunks, uint8_t *out, uint64_t out_stride, uint64_t out_capacity,
                              unsigned long long *used, uint32_t *formats, uint32_t *results, cudaStream_t st)
 {
     const uint64_t njobs = (uint64_t)frames * max_chunks;
@@ -307,7 +307,7 @@ uint32_t launch_decode_batch(const uint8_t *in, uint32_t frames, uint64_t in_str
     DevBuf jobs(st), whole(st);
     if (!jobs.alloc(njobs * sizeof(ChunkJob)) || !whole.alloc((size_t)frames * 4)) { cudaGetLastError(); return HapResult_Internal_Error; }
     HAP_KLAUNCH(kStParse, hap_parse_frames_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, in, in_stride, in_bytes, frames, index,
-                max_chunks, out, out_stride, jobs.as<ChunkJob>(), used, formats, results, whole.as<uint32_t>());
+                max_chunks, out, out_stride, out_capacity, jobs.as<ChunkJob>(), used, formats, results, whole.as<uint32_t>());
     HAP_KLAUNCH(kStSnappyDecode, snappy_decode_chunks_kernel, dim3((unsigned)njobs), dim3(kDecThreads), sizeof(DecodeSmem), st,
                 jobs.as<ChunkJob>(), (int)njobs);
     HAP_KLAUNCH(kStCollect, hap_collect_status_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, jobs.as<ChunkJob>(), frames,
@@ -860,8 +860,8 @@ unsigned int HapB200DecodeBatch(const void *in, unsigned int frames, unsigned lo
         return HapResult_Bad_Arguments;
     if (!runtime_ok()) return HapResult_Internal_Error;
     cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
-    uint32_t r = launch_decode_batch((const uint8_t *)in, frames, inStride, inBytes, index, maxChunks, (uint8_t *)out, outStride, used,
-                                     formats, results, st);
+    uint32_t r = launch_decode_batch((const uint8_t *)in, frames, inStride, inBytes, index, maxChunks, (uint8_t *)out, outStride, outStride,
+                                     used, formats, results, st);
     if (r == HapResult_No_Error && !stream && cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); r = HapResult_Internal_Error; }
     return r;
 }
@@ -886,16 +886,18 @@ unsigned int HapB200DecodeRGBABatch(const void *in, unsigned int frames, unsigne
     uint32_t r = HapResult_No_Error;
     for (uint32_t ti = 0; ti < ci.textures && r == HapResult_No_Error; ti++) {
         uint32_t *res = ti == 0 ? results : res1.as<uint32_t>();
-        // the decoded size must equal the texture size: offer exactly that much room per frame
+        // the decoded size must equal the texture size: offer exactly that much room per frame (the slot stride is
+        // wider: both textures of a frame share a slot, so a texture that over-declares its size must not reach its
+        // neighbour or the next frame's slot)
         r = launch_decode_batch((const uint8_t *)in, frames, inStride, inBytes, ti, maxChunks, dxt.as<uint8_t>() + (ti ? align16(t0) : 0),
-                                dxt_stride, used.as<unsigned long long>(), formats.as<uint32_t>(), res, st);
+                                dxt_stride, ti ? t1 : t0, used.as<unsigned long long>(), formats.as<uint32_t>(), res, st);
         if (r != HapResult_No_Error) break;
         HAP_KLAUNCH(kStCollect, hap_check_texture_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, frames, used.as<unsigned long long>(),
                     formats.as<uint32_t>(), res, (unsigned long long)(ti ? t1 : t0), ci.fmt[ti], results);
     }
     if (r == HapResult_No_Error)
         r = launch_block_decode(dxt.as<uint8_t>(), dxt.as<uint8_t>() + align16(t0), frames, dxt_stride, dxt_stride, width, height, ci,
-                                (uint8_t *)rgba, frameStride, rowBytes, st);
+                                (uint8_t *)rgba, frameStride, rowBytes, st, results);
     if (r == HapResult_No_Error && !stream && cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); r = HapResult_Internal_Error; }
     return r;
 }

@@ -13,12 +13,14 @@ namespace hapb200 {
 constexpr uint32_t kHapChunkSkip = 0;  // ChunkJob.compressor of an unused slot
 
 // frame f: in + f*in_stride, in_bytes[f] bytes.  jobs: [frames][max_chunks].
+// Frame f's texture goes to out + f*out_stride and may use out_capacity bytes there (the slot of a batch is often
+// wider than what one texture may fill: two textures of a Hap Q Alpha frame share a slot).
 // results[f] = HapResult of the prepass; whole_section[f] = 1 when the texture is one 0xB? stream
 // (its errors map to Internal_Error, hap.c:891-903).
 __global__ void hap_parse_frames_kernel(const uint8_t *__restrict__ in, uint64_t in_stride,
                                         const unsigned long long *__restrict__ in_bytes, uint32_t frames,
                                         uint32_t index, uint32_t max_chunks, uint8_t *__restrict__ out,
-                                        uint64_t out_stride, ChunkJob *__restrict__ jobs,
+                                        uint64_t out_stride, uint64_t out_capacity, ChunkJob *__restrict__ jobs,
                                         unsigned long long *__restrict__ used, uint32_t *__restrict__ formats,
                                         uint32_t *__restrict__ results, uint32_t *__restrict__ whole_section)
 {
@@ -68,7 +70,7 @@ __global__ void hap_parse_frames_kernel(const uint8_t *__restrict__ in, uint64_t
                         fj[i].compressor = (cc == kHapChunkSnappy || cc == kHapChunkRaw) ? cc : 0xFFu;  // 0xFF -> Bad_Frame in K7
                         out_run += usz;
                     }
-                    if (r == HapResult_No_Error && out_run > out_stride) r = HapResult_Buffer_Too_Small;
+                    if (r == HapResult_No_Error && out_run > out_capacity) r = HapResult_Buffer_Too_Small;
                     if (r == HapResult_No_Error) produced = out_run;
                     else for (int i = 0; i < t.count; i++) fj[i].compressor = kHapChunkSkip;
                 }
@@ -78,7 +80,7 @@ __global__ void hap_parse_frames_kernel(const uint8_t *__restrict__ in, uint64_t
             whole = 1;
             if (max_chunks < 1) r = HapResult_Bad_Arguments;
             else if (!snappy_preamble(sec, loc.len, usz)) r = HapResult_Internal_Error;  // hap.c:891-894
-            else if (usz > out_stride) r = HapResult_Buffer_Too_Small;
+            else if (usz > out_capacity) r = HapResult_Buffer_Too_Small;
             else {
                 fj[0].src = sec; fj[0].src_bytes = loc.len; fj[0].dst = dst; fj[0].dst_bytes = usz;
                 fj[0].compressor = kHapChunkSnappy;
@@ -86,7 +88,7 @@ __global__ void hap_parse_frames_kernel(const uint8_t *__restrict__ in, uint64_t
             }
         } else if (compressor == kHapChunkRaw) {
             if (max_chunks < 1) r = HapResult_Bad_Arguments;
-            else if (loc.len > out_stride) r = HapResult_Buffer_Too_Small;
+            else if (loc.len > out_capacity) r = HapResult_Buffer_Too_Small;
             else {
                 fj[0].src = sec; fj[0].src_bytes = loc.len; fj[0].dst = dst; fj[0].dst_bytes = loc.len;
                 fj[0].compressor = kHapChunkRaw;

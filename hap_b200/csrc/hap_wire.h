@@ -115,15 +115,21 @@ HAP_HD uint32_t parse_decode_instructions(const uint8_t *sec, uint32_t sec_len, 
     if (r != HapResult_No_Error) return r;
     t.data = s.hdr + s.len;
     uint32_t pos = s.hdr, left = s.len;
+    // byte lengths of the tables as found (0xFFFFFFFF = table absent): the entry counts derived from them must all
+    // describe `count` chunks EXACTLY.  hap.c:709-716 only compares counts that are non-zero, so a compressor table of
+    // length 0 or a size table shorter than 4 bytes would leave `count` to the other table and the per-chunk reads
+    // (hap.c:794-807) would run past the short table; that inherited hole is closed here (-> Bad_Frame).
+    uint32_t comp_len = 0xFFFFFFFFu, size_len = 0xFFFFFFFFu, offs_len = 0xFFFFFFFFu;
     while (left > 0) {
         Section in;
         r = read_section_header(sec + pos, left, in);
         if (r != HapResult_No_Error) return r;
         pos += in.hdr;
         uint32_t c = 0;
-        if (in.type == kSecCompressorTable) { t.compressors = pos; t.has_compressors = true; c = in.len; }
-        else if (in.type == kSecSizeTable) { t.sizes = pos; t.has_sizes = true; c = in.len / 4; }
-        else if (in.type == kSecOffsetTable) { t.offsets = pos; c = in.len / 4; }
+        if (in.type == kSecCompressorTable) { t.compressors = pos; t.has_compressors = true; c = in.len; comp_len = in.len; }
+        else if (in.type == kSecSizeTable) { t.sizes = pos; t.has_sizes = true; c = in.len / 4; size_len = in.len; }
+        else if (in.type == kSecOffsetTable) { t.offsets = pos; c = in.len / 4; offs_len = in.len; }
+        // any other type: ignored, like hap.c:701-704 (this is where a private index section travels, hap_index.h)
         if (c != 0) {
             if (t.count != 0 && (int)c != t.count) return HapResult_Bad_Frame;
             t.count = (int)c;
@@ -132,6 +138,10 @@ HAP_HD uint32_t parse_decode_instructions(const uint8_t *sec, uint32_t sec_len, 
         left -= in.hdr + in.len;
     }
     if (!t.has_compressors || !t.has_sizes) return HapResult_Bad_Frame;
+    if (t.count < 0) return HapResult_Bad_Frame;
+    const uint64_t k = (uint64_t)t.count;
+    if (comp_len != k || size_len / 4 != k) return HapResult_Bad_Frame;
+    if (offs_len != 0xFFFFFFFFu && offs_len / 4 != k) return HapResult_Bad_Frame;
     return HapResult_No_Error;
 }
 

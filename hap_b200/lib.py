@@ -70,6 +70,21 @@ class HapB200(HapABI):
         self.lib.HapB200StageTimes(ms, n, 8)
         return {s: (float(ms[i]), int(n[i])) for i, s in enumerate(self.STAGES)}
 
+    @staticmethod
+    def stage_algorithmic_bytes(frames, rgba_bytes, texture_bytes, mean_frame_bytes):
+        """Algorithmic bytes one launch of each stage moves for a batch of `frames` frames."""
+        F = frames
+        return {
+            "bc_encode": F * (rgba_bytes + texture_bytes),                 # RGBA read once + DXT written once
+            "snappy_encode": F * texture_bytes + F * mean_frame_bytes,     # DXT read + element streams written
+            "plan": F * 4096.0,
+            "place": 2 * F * mean_frame_bytes,                             # element streams read + frame written
+            "parse": F * 256.0,
+            "snappy_decode": F * mean_frame_bytes + F * texture_bytes,     # frame read + texture written
+            "collect": F * 64.0,
+            "bc_decode": F * (texture_bytes + rgba_bytes),
+        }
+
     def decode_phase_cycles(self, reset=True):
         out = (C.c_ulonglong * 16)()
         self.lib.HapB200DebugDecodePhaseCycles(out, 16, 1 if reset else 0)

@@ -7,6 +7,10 @@ tests/test_synth.py.  Kinds:
          (partly compressible: Snappy ratio ~0.6 on the Hap Q payload)
   flat   constant 0x336699FF (maximum compressibility, exercises the RLE paths)
   noise  hash bytes (incompressible, exercises both raw fallbacks of hap.c:460 and :478)
+Content classes for the block-encoder quality bar (tests only; the benchmark stream is `video`):
+  gradient  steep two-axis colour ramps without grain (where a 4-colour palette per block hurts most)
+  texture   grain of 5 bits on every pixel over slow ramps (camera footage at high gain)
+  edges     hard-edged graphics: bars, checkers and 1-pixel lines in saturated colours on flat ground
 """
 from __future__ import annotations
 
@@ -45,6 +49,9 @@ def frame(width: int, height: int, index: int = 0, kind: str = "video", alpha: s
         out = (h >> 24).to(torch.uint8)
         out[..., 3] = 255
         return out
+    if kind in ("gradient", "texture", "edges"):
+        out = _content_class(kind, x, y, c, h, index, width, height)
+        return _apply_alpha(out, alpha, x, y, width, height)
     if kind != "video":
         raise ValueError(kind)
     k1 = torch.tensor([1, 2, 3, 1], dtype=torch.int64, device=dev).view(1, 1, 4)
@@ -62,6 +69,33 @@ def frame(width: int, height: int, index: int = 0, kind: str = "video", alpha: s
     letter = (y < bar) | (y >= height - bar)
     v = torch.where(letter, torch.full_like(v, 16), v)
     out = v.to(torch.uint8)
+    return _apply_alpha(out, alpha, x, y, width, height)
+
+
+def _content_class(kind, x, y, c, h, index, width, height):
+    if kind == "gradient":
+        k1 = torch.tensor([7, 3, 5, 1], dtype=torch.int64, device=x.device).view(1, 1, 4)
+        k2 = torch.tensor([2, 9, 4, 1], dtype=torch.int64, device=x.device).view(1, 1, 4)
+        v = (_tri8((x * k1 * 512) // width + 16 * index) + _tri8((y * k2 * 512) // height)) // 2
+        return v.clamp(0, 255).to(torch.uint8)
+    if kind == "texture":
+        k1 = torch.tensor([1, 2, 1, 1], dtype=torch.int64, device=x.device).view(1, 1, 4)
+        v = 64 + _tri8((x * k1 * 512) // width) // 4 + _tri8((y * 512) // height) // 4 + (h >> 27) - 16
+        return v.clamp(0, 255).to(torch.uint8)
+    # edges
+    pal = torch.tensor([[230, 30, 30, 255], [30, 200, 60, 255], [40, 60, 230, 255], [240, 240, 240, 255], [20, 20, 20, 255],
+                        [250, 200, 20, 255]], dtype=torch.int64, device=x.device)
+    cell = ((x // 37) + (y // 23) * 7 + index) % 6
+    stripe = ((x + 2 * y) // 5) % 2
+    line = ((x % 61) == 0) | ((y % 47) == 0)
+    idx = torch.where(line, torch.full_like(cell, 3), torch.where(stripe == 1, cell, torch.full_like(cell, 4)))
+    checker = (((x // 3) + (y // 3)) % 2) == 1
+    region = (y * 3 // max(height, 1)) == 1
+    idx = torch.where(region & checker, (cell + 1) % 6, idx)
+    return pal[idx[..., 0]].to(torch.uint8)
+
+
+def _apply_alpha(out, alpha, x, y, width, height):
     if alpha == "opaque":
         out[..., 3] = 255
     elif alpha == "ramp":

@@ -160,3 +160,50 @@ def psnr(a: np.ndarray, b: np.ndarray, channels=(0, 1, 2)) -> float:
     d = a[..., list(channels)].astype(np.float64) - b[..., list(channels)].astype(np.float64)
     mse = float((d * d).mean())
     return 99.0 if mse == 0 else 10.0 * np.log10(255.0 * 255.0 / mse)
+
+
+# ---- threaded drivers of the CPU baseline (oracle/mt_driver.c) ---------------------------------------
+
+class MtDriver:
+    """The reference's own parallel mechanisms, driven from C (oracle/mt_driver.c): frame-parallel HapEncode
+    (hap.c:448-476 is serial inside a frame and has no callback), HapDecode with a pthread-pool HapDecodeCallback
+    (hap.c:861) and frame-parallel HapDecode.  kind = "reference" (oracle/_ref, unmodified hap.c + Google Snappy) or
+    "port" (oracle/liboracle.so).  Buffers are numpy uint8 arrays; nothing is copied inside the timed calls."""
+
+    def __init__(self):
+        _ensure_built()
+        if os.path.exists(REF_SO):
+            try:
+                self.lib, self.prefix, self.kind = C.CDLL(REF_SO), "refdrv_", "reference"
+            except OSError:
+                self.lib, self.prefix, self.kind = C.CDLL(ORACLE_SO), "orcdrv_", "port"
+        else:
+            self.lib, self.prefix, self.kind = C.CDLL(ORACLE_SO), "orcdrv_", "port"
+        vp, u, ul = C.c_void_p, C.c_uint, C.c_ulong
+        self._enc = getattr(self.lib, self.prefix + "encode_frames_mt")
+        self._enc.restype = u
+        self._enc.argtypes = [u, u, C.POINTER(vp), C.POINTER(ul), C.POINTER(u), C.POINTER(u), C.POINTER(u), vp, ul, C.POINTER(ul), u]
+        self._decf = getattr(self.lib, self.prefix + "decode_frames_mt")
+        self._decf.restype = u
+        self._decf.argtypes = [u, vp, ul, C.POINTER(ul), vp, ul, u]
+        self._dec1 = getattr(self.lib, self.prefix + "decode_mt")
+        self._dec1.restype = u
+        self._dec1.argtypes = [vp, ul, u, vp, ul, C.POINTER(ul), C.POINTER(u), u]
+
+    def encode_frames(self, textures, tex_bytes, fmt, compressor, chunks, out, out_stride, threads):
+        """textures: list (one per frame) of numpy arrays; out: numpy uint8 [frames*out_stride].  Returns (result, used[])"""
+        n = len(textures)
+        ins = (C.c_void_p * n)(*[t.ctypes.data for t in textures])
+        used = (C.c_ulong * n)()
+        r = self._enc(n, 1, ins, (C.c_ulong * 1)(tex_bytes), (C.c_uint * 1)(fmt), (C.c_uint * 1)(compressor), (C.c_uint * 1)(chunks),
+                      out.ctypes.data, out_stride, used, threads)
+        return int(r), list(used)
+
+    def decode_frames(self, frames_buf, in_stride, in_bytes, out, out_stride, threads):
+        n = len(in_bytes)
+        return int(self._decf(n, frames_buf.ctypes.data, in_stride, (C.c_ulong * n)(*in_bytes), out.ctypes.data, out_stride, threads))
+
+    def decode_one_chunk_parallel(self, frame_addr, nbytes, out_addr, cap, threads):
+        used, fmt = C.c_ulong(0), C.c_uint(0)
+        r = self._dec1(frame_addr, nbytes, 0, out_addr, cap, C.byref(used), C.byref(fmt), threads)
+        return int(r), int(used.value)

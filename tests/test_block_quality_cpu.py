@@ -37,3 +37,20 @@ def test_flat_and_noise_blocks_are_sane():
     for kind in ("bc1", "bc3", "ycocg", "bc4"):
         blk = twin.encode(kind, noise)
         assert len(blk) == 256 * (8 if kind in ("bc1", "bc4") else 16)
+
+
+# Content classes (hap_b200/synth.py) on small frames, host build of the encoder source.  north_star bar 0.1 dB; the wider
+# bars are the measured deficits of the current encoders on 512x256 frames (video: bc1/bc3 -0.19; gradient: bc1/bc3 -0.12;
+# edges: ycocg -0.13), kept here so that they cannot grow unnoticed.  Full 1080p frames: tests/test_gpu_parity_fullsize.py.
+CLASS_BARS = {("ycocg", "edges"): 0.20, ("bc1", "video"): 0.25, ("bc3", "video"): 0.25, ("bc1", "gradient"): 0.20, ("bc3", "gradient"): 0.20}
+
+
+@pytest.mark.parametrize("cls", ["video", "gradient", "texture", "edges"])
+@pytest.mark.parametrize("kind", ["ycocg", "bc1", "bc3"])
+def test_psnr_per_content_class(kind, cls):
+    w, h = 512, 256
+    img = synth.frame(w, h, 0, kind=cls, alpha="ramp").numpy()
+    ch = (0, 1, 2, 3) if kind == "bc3" else (0, 1, 2)
+    pa = oracles.psnr(img, oracles.bc_decode(kind, twin.encode(kind, img), w, h), ch)
+    pb = oracles.psnr(img, oracles.bc_decode(kind, oracles.bc_encode_clusterfit(kind, img, 8), w, h), ch)
+    assert pa >= pb - CLASS_BARS.get((kind, cls), 0.10), (kind, cls, pa, pb)

@@ -328,3 +328,44 @@ def test_banded_single_frame_encode_assembles_to_one_frame(lib):
     r, f_all = lib.encode_rgba(img, w, h, L.HapB200Codec_HapY, hap_b200.HapCompressorSnappy, 6)
     r2, tex_all, _, _ = lib.decode(f_all, 0, len(want))
     assert r == 0 and r2 == 0 and tex_all == want
+
+
+def test_rgba_batch_texture_cannot_overrun_its_share_of_the_slot(lib):
+    """in HapB200DecodeRGBABatch both textures of a Hap Q Alpha frame share one scratch slot.  A
+    hostile frame whose ALPHA texture declares more bytes than an RGTC1 plane has (but no more than the slot is wide)
+    used to pass the size check and write over the next frame's colour texture.  It must be refused per frame, and the
+    neighbouring frame must decode to the same picture as when it is decoded alone."""
+    import hap_b200.lib as L
+    w, h, k = 128, 64, 2
+    codec = L.HapB200Codec_HapM
+    img = synth.frame(w, h, 0, alpha="ramp", device="cuda")
+    cap = (lib.max_encoded_length_rgba(w, h, codec, k) + 15) // 16 * 16
+    one = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    used1 = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert lib.encode_rgba_batch(img.data_ptr(), 1, img.numel(), w, h, codec, 1, k, one.data_ptr(), cap, used1.data_ptr()) == 0
+    good = one[: int(used1[0])].cpu().numpy().tobytes()
+    t0, t1 = lib.texture_bytes(w, h, codec, 0), lib.texture_bytes(w, h, codec, 1)
+    r, tex0, _, _ = lib.decode(good, 0, t0)
+    assert r == 0
+    # hostile twin: same colour section, alpha section = a verbatim (0xA1) section of t0 + t1 - 16 bytes
+    fat = bytes([0x77]) * (t0 + t1 - 16)
+    r, sec0 = lib.encode([tex0], [YCOCG], [0], [1])
+    assert r == 0
+    sec1 = len(fat).to_bytes(3, "little") + bytes([0xA1]) + fat
+    body = sec0 + sec1
+    hostile = len(body).to_bytes(3, "little") + bytes([0x0D]) + body
+    assert lib.texture_count(hostile) == (0, 2) and lib.texture_format(hostile, 1) == (0, RGTC1)
+    big = max(cap, (len(hostile) + 15) // 16 * 16)
+    buf = torch.zeros(2 * big, dtype=torch.uint8, device="cuda")
+    buf[: len(hostile)] = torch.frombuffer(bytearray(hostile), dtype=torch.uint8).cuda()
+    buf[big: big + len(good)] = torch.frombuffer(bytearray(good), dtype=torch.uint8).cuda()
+    used = torch.tensor([len(hostile), len(good)], dtype=torch.int64, device="cuda")
+    rgba = torch.full((2, h, w, 4), 0xEE, dtype=torch.uint8, device="cuda")
+    res = torch.full((2,), 9, dtype=torch.int32, device="cuda")
+    assert lib.decode_rgba_batch(buf.data_ptr(), 2, big, used.data_ptr(), k, codec, w, h, rgba.data_ptr(), w * h * 4, res.data_ptr()) == 0
+    assert res.tolist()[0] in (2, 3) and res.tolist()[1] == 0, res.tolist()
+    alone = torch.zeros((1, h, w, 4), dtype=torch.uint8, device="cuda")
+    r1 = torch.full((1,), 9, dtype=torch.int32, device="cuda")
+    assert lib.decode_rgba_batch(one.data_ptr(), 1, cap, used1.data_ptr(), k, codec, w, h, alone.data_ptr(), w * h * 4, r1.data_ptr()) == 0
+    assert r1.tolist() == [0] and torch.equal(rgba[1], alone[0])
+    assert int(rgba[0].max()) == 0          # the refused frame's picture is zeros, not recycled scratch

@@ -109,3 +109,29 @@ def test_compute_paths_fail_loudly_without_a_gpu(lib):
     x = bytes([0x55]) * 64
     assert lib.encode([x], [DXT1], [HapCompressorSnappy], [1])[0] == 4  # HapResult_Internal_Error, no CPU fallback
     assert lib.decode(bytes.fromhex(golden()["kat_a"]["frame"]), 0, 64)[0] == 4
+
+
+def _sec(typ, body):
+    assert len(body) < (1 << 24)
+    return len(body).to_bytes(3, "little") + bytes([typ]) + body
+
+
+def test_decode_instruction_tables_must_all_describe_the_same_chunks(lib):
+    """a compressor table of length 0 (or a size table shorter than 4 bytes) leaves the chunk count
+    to the other table in hap.c:709-716; the per-chunk reads then run past the short table.  Here: Bad_Frame, on the
+    header walk and on HapDecode alike, before anything is launched."""
+    data = bytes(64)
+    sizes3 = b"".join((16).to_bytes(4, "little") for _ in range(3))
+    cases = {
+        "empty_compressor_table": _sec(0x02, b"") + _sec(0x03, sizes3),
+        "short_size_table": _sec(0x02, bytes([0x0A] * 3)) + _sec(0x03, b"\x10\x00"),
+        "short_offset_table": _sec(0x02, bytes([0x0A] * 3)) + _sec(0x03, sizes3) + _sec(0x04, b"\x00\x00"),
+        "offset_table_of_two": _sec(0x02, bytes([0x0A] * 3)) + _sec(0x03, sizes3) + _sec(0x04, bytes(8)),
+    }
+    for name, tables in cases.items():
+        frame = _sec(0xCB, _sec(0x01, tables) + data)
+        assert lib.chunk_count(frame, 0)[0] == 3, name
+        assert lib.decode(frame, 0, 64)[0] == 3, name
+    # the well-formed sibling (three raw chunks) is accepted by the header walk; an unknown section is skipped
+    good = _sec(0xCB, _sec(0x01, _sec(0x02, bytes([0x0A] * 3)) + _sec(0x7B, b"private") + _sec(0x03, sizes3)) + bytes(48))
+    assert lib.chunk_count(good, 0) == (0, 3)
