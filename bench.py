@@ -333,6 +333,10 @@ def run_gpu_arm(args, rank, local_rank, world):
     F = args.frames
     codec = HapB200Codec_HapY
     peak, peak_src = measured_peak_hbm()
+    # the encoder appends its fragment index to every frame (hap_b200/csrc/hap_index.h: ~1 % of the frame; the reference
+    # and FFmpeg ignore it) and the decoder uses it; --no-index times the frames laid out exactly as the reference writes them
+    lib.set_option(lib.OPTION_WRITE_INDEX, 0 if args.no_index else 1)
+    lib.set_option(lib.OPTION_USE_INDEX, 0 if args.no_index else 1)
 
     # ---- synthetic, device-resident input: F distinct frames per rank -------------------------------
     A = Roundtrip(lib, dev, W, H, codec, CHUNKS, F, first_index=rank * F)
@@ -518,8 +522,10 @@ def run_gpu_arm(args, rank, local_rank, world):
     overlap = overlap_was
     st = lib.stage_times()
     lib.set_stage_timing(False)
-    stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in st.items()}
     per_step = {k: v[0] / 3 for k, v in st.items()}
+    # one batch = one launch of every stage's main kernel (the decode stages launch a second, normally empty, repair pass:
+    # its few microseconds are counted with the stage)
+    stage_ms = dict(per_step)
     dominant = max(stage_ms, key=lambda k: per_step[k])
     alg_bytes = lib.stage_algorithmic_bytes(F, RGBA_BYTES, DXT_BYTES, mean_frame)
     dom_ms = stage_ms[dominant]
@@ -551,6 +557,14 @@ def run_gpu_arm(args, rank, local_rank, world):
                         "roofline_frac_frame_plus_texture": F * (mean_frame + DXT_BYTES) / dec_ms / 1e6 / peak, "target": 0.80}}
 
     extra = {}
+    if not args.no_index:
+        lib.set_option(lib.OPTION_USE_INDEX, 0)
+        ms_noix = time_on_stream(torch, stream, lambda: decode_from(0, sp), 3)
+        lib.set_option(lib.OPTION_USE_INDEX, 1)
+        extra["own_stream_decode_without_index"] = {
+            "what": "the same batch decoded with the embedded index ignored (snappy_index_kernel derives it from the streams)",
+            "ms_per_batch": ms_noix, "fps": F / ms_noix * 1e3, "traffic_GBps": F * (mean_frame + DXT_BYTES) / ms_noix / 1e6,
+            "roofline_frac_frame_plus_texture": F * (mean_frame + DXT_BYTES) / ms_noix / 1e6 / peak}
     if world == 1 and not args.no_extra:
         del frames_buf, used
         extra["configs"] = extra_config_lines(lib, torch, dev, peak)
@@ -593,7 +607,9 @@ def run_gpu_arm(args, rank, local_rank, world):
         "data": "synthetic", "config": CONFIG,
         "run": {"frames_per_gpu_per_step": F, "rgba_GB_per_step_per_gpu": F * RGBA_BYTES / 1e9, "compression_ratio": mean_frame / DXT_BYTES,
                 "parallelism": f"frames sharded over {world} gpu(s), no collective on the data path",
-                "pipelining": "decode(batch i) on stream B overlaps encode(batch i+1) on stream A" if overlap else "none"},
+                "pipelining": "decode(batch i) on stream B overlaps encode(batch i+1) on stream A" if overlap else "none",
+                "fragment_index": "off (frames byte-identical in layout to the reference's)" if args.no_index else
+                                  "on (trailing private section, ~1 % of the frame, ignored by the reference and FFmpeg)"},
         "fps": world * F / (ms_per_step * 1e-3),
         "encode_decode_split": split,
         "clocks": clocks, "e2e": e2e, "e2e_rgba": e2e_rgba, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
@@ -637,6 +653,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the per-configuration encode-only / decode-only lines")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: skip the e2e, extra and CPU legs")
     ap.add_argument("--no-overlap", action="store_true", help="encode and decode of a batch back to back on one stream")
+    ap.add_argument("--no-index", action="store_true", help="frames without the trailing fragment index section (decoder indexes on the fly)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

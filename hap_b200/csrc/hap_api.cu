@@ -17,6 +17,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -26,10 +27,14 @@ using namespace hapb200;
 namespace {
 
 std::atomic<unsigned long long> g_launches{0};
+// Options (HapB200SetOption).  g_use_index: the decoder uses a frame's embedded fragment index when it has one
+// (hap_index.h).  g_write_index: the encoder writes that section into Complex texture sections.
+std::atomic<int> g_use_index{1};
+std::atomic<int> g_write_index{0};
 
 // Optional per-stage device timing (HapB200SetStageTiming): CUDA events around every kernel, on the
 // stream the kernel is launched on.  Off by default; bench.py turns it on for its roofline pass only.
-enum Stage { kStBcEncode = 0, kStSnappyEncode, kStPlan, kStPlace, kStParse, kStSnappyDecode, kStCollect, kStBcDecode, kStCount };
+enum Stage { kStBcEncode = 0, kStSnappyEncode, kStPlan, kStPlace, kStParse, kStSnappyDecode, kStCollect, kStBcDecode, kStSnappyIndex, kStWindows, kStCount };
 struct StageTimer {
     std::mutex mu;
     bool on = false;
@@ -81,14 +86,17 @@ void runtime_init()
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { g_rt.failed = true; cudaGetLastError(); return; }
     g_rt.device = dev;
+    // process-wide defaults of the two options (HapB200SetOption overrides them)
+    if (const char *e = getenv("HAPB200_WRITE_INDEX")) g_write_index.store(atoi(e) != 0);
+    if (const char *e = getenv("HAPB200_USE_INDEX")) g_use_index.store(atoi(e) != 0);
     if (cudaDeviceGetAttribute(&g_rt.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_rt.sm_count <= 0) { cudaGetLastError(); g_rt.sm_count = 148; }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long keep = ~0ull;  // keep freed scratch in the pool: steady-state calls never hit the OS
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    bool ok = cudaFuncSetAttribute(snappy_decode_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(DecodeSmem)) == cudaSuccess;
+    bool ok = cudaFuncSetAttribute(snappy_execute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecSmem)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(snappy_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IndexSmem)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(snappy_encode_fragments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(EncodeSmem)) == cudaSuccess;
     // NULL-stream calls and the host-pointer entry points run on the LEGACY default stream: it orders itself
@@ -230,10 +238,12 @@ uint32_t launch_encode(const uint8_t *base, const FrameGeom &G, uint32_t frames,
 {
     const uint64_t nfrag = (uint64_t)frames * G.frags_per_frame;
     if (nfrag == 0 || nfrag >= (1ull << 31)) return HapResult_Bad_Arguments;
-    DevBuf scratch(st), fsize(st), fdst(st);
+    DevBuf scratch(st), fsize(st), fdst(st), fidx(st), fent(st);
     bool any_compress = false;
     for (uint32_t i = 0; i < G.sections; i++) any_compress = any_compress || G.s[i].compress;
-    if (!scratch.alloc(any_compress ? nfrag * kFragCap : 16) || !fsize.alloc(nfrag * 4) || !fdst.alloc(nfrag * 4)) {
+    const uint32_t write_index = any_compress && g_write_index.load() ? 1u : 0u;
+    if (!scratch.alloc(any_compress ? nfrag * kFragCap : 16) || !fsize.alloc(nfrag * 4) || !fdst.alloc(nfrag * 4) || !fidx.alloc(nfrag * 4) ||
+        !fent.alloc(write_index ? nfrag * kFragEntryStride : 16)) {
         cudaGetLastError();
         return HapResult_Internal_Error;
     }
@@ -243,11 +253,12 @@ uint32_t launch_encode(const uint8_t *base, const FrameGeom &G, uint32_t frames,
     // one resident CTA per SM strides over the fragments (the kernel's 131 KB of shared memory allow no second one)
     const unsigned k5_grid = HAPB200_ENC_PERSISTENT ? (unsigned)(nfrag < (uint64_t)g_rt.sm_count ? nfrag : (uint64_t)g_rt.sm_count) : (unsigned)nfrag;
     HAP_KLAUNCH(kStSnappyEncode, snappy_encode_fragments_kernel, dim3(k5_grid), dim3(kEncThreads), sizeof(EncodeSmem), st, base, G,
-                (uint32_t)nfrag, scratch.as<uint8_t>(), fsize.as<uint32_t>());
+                (uint32_t)nfrag, scratch.as<uint8_t>(), fsize.as<uint32_t>(), write_index ? fent.as<uint8_t>() : (uint8_t *)nullptr);
     HAP_KLAUNCH(kStPlan, hap_plan_frames_kernel, dim3(frames), dim3(kPlanThreads), 0, st, G, base, fsize.as<uint32_t>(),
-                fdst.as<uint32_t>(), out, out_stride, used);
+                fdst.as<uint32_t>(), fidx.as<uint32_t>(), write_index, out, out_stride, used);
     HAP_KLAUNCH(kStPlace, hap_place_fragments_kernel, dim3((unsigned)nfrag), dim3(kPlaceThreads), 0, st, G, base,
-                scratch.as<uint8_t>(), fsize.as<uint32_t>(), fdst.as<uint32_t>(), out, out_stride);
+                scratch.as<uint8_t>(), fsize.as<uint32_t>(), fdst.as<uint32_t>(), fidx.as<uint32_t>(),
+                write_index ? fent.as<uint8_t>() : (const uint8_t *)nullptr, out, out_stride);
     return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
 }
 
@@ -297,6 +308,46 @@ uint32_t launch_block_decode(const uint8_t *blocks, const uint8_t *alpha, uint32
     return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
 }
 
+// Decode-side options (HapB200SetOption): 1 = use a frame's embedded fragment index when it has one (hap_index.h)
+
+// Everything after the jobs exist (device array): windows, on-the-fly index, execute, repair of chunks whose embedded
+// index did not hold up.  in_bound / out_bound: upper bounds of the jobs' total compressed / decoded bytes (they size the
+// window list; a list that turns out too short makes the affected chunks report Internal_Error, never overruns).
+uint32_t launch_decode_jobs(ChunkJob *jobs, uint32_t njobs, uint64_t in_bound, uint64_t out_bound, cudaStream_t st)
+{
+    const uint64_t cap64 = in_bound / kIdxWin + out_bound / kIndexFragBytes + 3ull * njobs + 16;
+    if (cap64 >= (1ull << 31)) return HapResult_Bad_Arguments;
+    const uint32_t win_cap = (uint32_t)cap64;
+    DevBuf wins(st), entries(st), done(st), ctl(st);
+    if (!wins.alloc((size_t)win_cap * sizeof(DecWin)) || !entries.alloc((size_t)win_cap * kIdxThreads) || !done.alloc((size_t)win_cap * 4) ||
+        !ctl.alloc(sizeof(DecodeCtl) + 16)) {
+        cudaGetLastError();
+        return HapResult_Internal_Error;
+    }
+    if (cudaMemsetAsync(ctl.p, 0, sizeof(DecodeCtl) + 16, st) != cudaSuccess || cudaMemsetAsync(done.p, 0, (size_t)win_cap * 4, st) != cudaSuccess) {
+        cudaGetLastError();
+        return HapResult_Internal_Error;
+    }
+    DecodeCtl *c = ctl.as<DecodeCtl>();
+    uint32_t *any_left = reinterpret_cast<uint32_t *>(ctl.as<uint8_t>() + sizeof(DecodeCtl));
+    const unsigned ex_grid = (unsigned)g_rt.sm_count * 3u;
+    HAP_KLAUNCH(kStWindows, hap_build_windows_kernel, dim3((njobs + 127) / 128), dim3(128), 0, st, jobs, njobs, (uint32_t)g_use_index.load(),
+                wins.as<DecWin>(), win_cap, c);
+    HAP_KLAUNCH(kStSnappyIndex, snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), st, jobs, (int)njobs, (uint32_t)kJobNeedsIndex,
+                wins.as<DecWin>(), win_cap, entries.as<uint8_t>(), c);
+    HAP_KLAUNCH(kStSnappyDecode, snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), st, jobs, wins.as<DecWin>(), c,
+                done.as<uint32_t>());
+    if (g_use_index.load()) {
+        // chunks whose embedded index did not describe their stream: decode them again as if they had none
+        HAP_KLAUNCH(kStWindows, hap_requeue_mismatched_kernel, dim3((njobs + 127) / 128), dim3(128), 0, st, jobs, njobs, c, any_left);
+        HAP_KLAUNCH(kStSnappyIndex, snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), st, jobs, (int)njobs,
+                    (uint32_t)kJobNeedsIndex, wins.as<DecWin>(), win_cap, entries.as<uint8_t>(), c);
+        HAP_KLAUNCH(kStSnappyDecode, snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), st, jobs, wins.as<DecWin>(), c,
+                    done.as<uint32_t>());
+    }
+    return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
+}
+
 // device frames -> texture `index` of each; jobs scratch is allocated here
 uint32_t launch_decode_batch(const uint8_t *in, uint32_t frames, uint64_t in_stride, const unsigned long long *in_bytes,
                              uint32_t index, uint32_t max_chunks, uint8_t *out, uint64_t out_stride, uint64_t out_capacity,
@@ -308,8 +359,8 @@ uint32_t launch_decode_batch(const uint8_t *in, uint32_t frames, uint64_t in_str
     if (!jobs.alloc(njobs * sizeof(ChunkJob)) || !whole.alloc((size_t)frames * 4)) { cudaGetLastError(); return HapResult_Internal_Error; }
     HAP_KLAUNCH(kStParse, hap_parse_frames_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, in, in_stride, in_bytes, frames, index,
                 max_chunks, out, out_stride, out_capacity, jobs.as<ChunkJob>(), used, formats, results, whole.as<uint32_t>());
-    HAP_KLAUNCH(kStSnappyDecode, snappy_decode_chunks_kernel, dim3((unsigned)njobs), dim3(kDecThreads), sizeof(DecodeSmem), st,
-                jobs.as<ChunkJob>(), (int)njobs);
+    uint32_t r = launch_decode_jobs(jobs.as<ChunkJob>(), (uint32_t)njobs, (uint64_t)frames * in_stride, (uint64_t)frames * out_capacity, st);
+    if (r != HapResult_No_Error) return r;
     HAP_KLAUNCH(kStCollect, hap_collect_status_kernel, dim3((frames + 127) / 128), dim3(128), 0, st, jobs.as<ChunkJob>(), frames,
                 max_chunks, whole.as<uint32_t>(), results, used);
     return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
@@ -371,6 +422,15 @@ int HapB200DebugDecodePhaseCycles(unsigned long long *out, int n, int reset)
     }
     return 8;
 #endif
+}
+
+// Options.  HAPB200_OPTION_USE_INDEX (1): decoder uses a frame's embedded fragment index (default 1).
+// HAPB200_OPTION_WRITE_INDEX (2): encoder writes the fragment index section (default: see g_write_index).
+int HapB200SetOption(int option, int value)
+{
+    if (option == 1) { g_use_index.store(value != 0); return 0; }
+    if (option == 2) { g_write_index.store(value != 0); return 0; }
+    return -1;
 }
 
 void HapB200SetStageTiming(int enabled)
@@ -606,8 +666,9 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
     *outputBufferTextureFormat = format_from_nibble(loc.type & 0xF);
     if (*outputBufferTextureFormat == 0) return HapResult_Bad_Frame;
 
-    struct HostJob { uint32_t src_off, src_bytes, dst_off, dst_bytes, compressor; };
+    struct HostJob { uint32_t src_off, src_bytes, dst_off, dst_bytes, compressor, index_off, index_bytes; };
     std::vector<HostJob> hj;
+    uint32_t hv_index_body = 0, hv_index_len = 0;
     uint64_t produced = 0;
     bool whole = false;
     if (compressor == kHapComplex) {
@@ -615,6 +676,9 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
         t.count = 0;
         r = parse_decode_instructions(sec, loc.len, t);
         if (r != HapResult_No_Error) return r;
+        FragmentIndex ix;
+        const bool have_ix = locate_fragment_index(frame, (uint32_t)inputBufferBytes, ix);
+        if (have_ix) { hv_index_body = ix.body; hv_index_len = ix.len; }
         if (t.count > 0) {
             uint64_t in_run = 0, out_run = 0;
             hj.resize((size_t)t.count);
@@ -626,7 +690,8 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
                 if (start + sz > loc.len) return HapResult_Bad_Frame;  // the reference reads out of bounds here
                 uint32_t usz = sz;
                 if (cc == kHapChunkSnappy && !snappy_preamble(sec + start, sz, usz)) return HapResult_Bad_Frame;  // hap.c:817-829
-                hj[i] = HostJob{(uint32_t)start, sz, 0, usz, (cc == kHapChunkSnappy || cc == kHapChunkRaw) ? cc : 0xFFu};
+                hj[i] = HostJob{(uint32_t)start, sz, 0, usz, (cc == kHapChunkSnappy || cc == kHapChunkRaw) ? cc : 0xFFu, 0, 0};
+                if (cc == kHapChunkSnappy && have_ix) fragment_index_record(frame, ix, index, (uint32_t)t.count, (uint32_t)i, hj[i].index_off, hj[i].index_bytes);
                 if (out_run > 0xFFFFFFFFull) return HapResult_Buffer_Too_Small;
                 hj[i].dst_off = (uint32_t)out_run;
                 out_run += usz;
@@ -638,7 +703,7 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
         uint32_t usz = 0;
         if (!snappy_preamble(sec, loc.len, usz)) return HapResult_Internal_Error;  // hap.c:890-894
         if (usz > outputBufferBytes) return HapResult_Buffer_Too_Small;
-        hj.push_back(HostJob{0, loc.len, 0, usz, kHapChunkSnappy});
+        hj.push_back(HostJob{0, loc.len, 0, usz, kHapChunkSnappy, 0, 0});
         produced = usz;
         whole = true;
     } else if (compressor == kHapChunkRaw) {
@@ -663,11 +728,22 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
         cudaStream_t st = call.st;
         DevBuf din(st), dout(st), djobs(st);
         const uint8_t *dsec;
+        const uint8_t *dindex = nullptr;    // device address of byte 0 of the fragment index body (hap_index.h), when the frame has one
+        bool any_index = false;
+        for (auto &h : hj) any_index = any_index || h.index_bytes != 0;
         if (in_dev) {
             dsec = (const uint8_t *)inputBuffer + loc.offset;
+            if (any_index) dindex = (const uint8_t *)inputBuffer + hv_index_body;
         } else {
-            if (!din.alloc(loc.len) || cudaMemcpyAsync(din.p, sec, loc.len, cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+            // the texture section, and behind it (16-byte aligned) the body of the frame's trailing index section
+            const uint64_t ioff = align16(loc.len);
+            if (!din.alloc(ioff + (any_index ? hv_index_len : 0)) || cudaMemcpyAsync(din.p, sec, loc.len, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                (any_index && cudaMemcpyAsync(din.as<uint8_t>() + ioff, frame + hv_index_body, hv_index_len, cudaMemcpyHostToDevice, st) != cudaSuccess)) {
+                cudaGetLastError();
+                return HapResult_Internal_Error;
+            }
             dsec = din.as<uint8_t>();
+            if (any_index) dindex = din.as<uint8_t>() + ioff;
         }
         uint8_t *ddst;
         if (out_dev) ddst = (uint8_t *)outputBuffer;
@@ -676,6 +752,7 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
             ddst = dout.as<uint8_t>();
         }
         std::vector<ChunkJob> jobs(hj.size());
+        uint64_t in_sum = 0;
         for (size_t i = 0; i < hj.size(); i++) {
             jobs[i].src = dsec + hj[i].src_off;
             jobs[i].dst = ddst + hj[i].dst_off;
@@ -683,11 +760,15 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
             jobs[i].dst_bytes = hj[i].dst_bytes;
             jobs[i].compressor = hj[i].compressor;
             jobs[i].status = HapResult_Internal_Error;
+            jobs[i].index = hj[i].index_bytes ? dindex + (hj[i].index_off - hv_index_body) : nullptr;
+            jobs[i].index_bytes = hj[i].index_bytes;
+            jobs[i].mode = kJobUndecided;
+            in_sum += hj[i].src_bytes;
         }
         if (!djobs.alloc(jobs.size() * sizeof(ChunkJob)) ||
             cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(ChunkJob), cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
-        HAP_KLAUNCH(kStSnappyDecode, snappy_decode_chunks_kernel, dim3((unsigned)jobs.size()), dim3(kDecThreads), sizeof(DecodeSmem), st,
-                    djobs.as<ChunkJob>(), (int)jobs.size());
+        r = launch_decode_jobs(djobs.as<ChunkJob>(), (uint32_t)jobs.size(), in_sum, produced, st);
+        if (r != HapResult_No_Error) return r;
         if (compressor == kHapComplex && jobs.size() > 1) {
             WorkState ws;
             callback(work_function, &ws, (unsigned)jobs.size(), info);  // hap.c:861

@@ -47,88 +47,149 @@ __device__ __forceinline__ bool chunk_packed_size(const uint32_t *fs, uint32_t f
     return ok && sum < chunk_bytes;
 }
 
-// out: [frames][out_stride]; frag_size / frag_dst: [frames][G.frags_per_frame]; out_used: [frames].
+// bytes of the index record of one chunk (hap_index.h): u16 stream size per fragment + one entry per 128 stream bytes
+__device__ __forceinline__ uint32_t chunk_index_record_bytes(const uint32_t *fs, uint32_t fpc)
+{
+    uint32_t b = 2u * fpc;
+    for (uint32_t j = 0; j < fpc; j++) b += (fs[j] + (1u << kIndexSubLog2) - 1u) >> kIndexSubLog2;
+    return b;
+}
+
+__device__ __forceinline__ void put_le32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+
+// sum over the block of a value that may exceed 16 bits per thread (the 32-bit block scan adds halves separately)
+__device__ __forceinline__ uint32_t plan_excl_sum(uint32_t v, uint64_t *total, uint32_t *scratch)
+{
+    uint32_t tl, th;
+    const uint32_t el = block_excl_sum<kPlanThreads>(v & 0xFFFFu, &tl, scratch);
+    const uint32_t eh = block_excl_sum<kPlanThreads>(v >> 16, &th, scratch);
+    *total = (uint64_t)tl + ((uint64_t)th << 16);
+    return el + (eh << 16);
+}
+
+// out: [frames][out_stride]; frag_size / frag_dst / frag_idx_dst: [frames][G.frags_per_frame]; out_used: [frames].
+// write_index != 0: a frame with at least one compressed chunk gets the trailing fragment index section (hap_index.h);
+// frag_idx_dst[f] then says where fragment f's entries go (0: nowhere).
 __global__ void __launch_bounds__(kPlanThreads) hap_plan_frames_kernel(
     FrameGeom G, const uint8_t *__restrict__ dxt, const uint32_t *__restrict__ frag_size,
-    uint32_t *__restrict__ frag_dst, uint8_t *__restrict__ out, uint64_t out_stride,
-    unsigned long long *__restrict__ out_used)
+    uint32_t *__restrict__ frag_dst, uint32_t *__restrict__ frag_idx_dst, uint32_t write_index, uint8_t *__restrict__ out,
+    uint64_t out_stride, unsigned long long *__restrict__ out_used)
 {
     __shared__ uint32_t scratch[kPlanThreads / 32];
-    __shared__ uint32_t sec_len_sh[2];
     const int t = threadIdx.x;
     const uint32_t frame = blockIdx.x;
     uint8_t *fo = out + (uint64_t)frame * out_stride;
     const uint32_t *fs_frame = frag_size + (uint64_t)frame * G.frags_per_frame;
     uint32_t *fd_frame = frag_dst + (uint64_t)frame * G.frags_per_frame;
+    uint32_t *fi_frame = frag_idx_dst + (uint64_t)frame * G.frags_per_frame;
+    for (uint32_t i = t; i < G.frags_per_frame; i += kPlanThreads) fi_frame[i] = 0;
 
-    uint32_t sec_off = G.outer_hdr;
+    // ---- pass 1, every section: would-be complex body length (hap.c:446-476) -> storage decision (hap.c:478), section
+    //      lengths, and the size of the chunks' index records --------------------------------------------------------------
+    bool complex_storage[2] = {false, false};
+    uint64_t body[2] = {0, 0}, rec_total[2] = {0, 0};
+    uint32_t sec_off[2] = {0, 0}, sec_len[2] = {0, 0};
+    uint32_t running_off = G.outer_hdr;
+    for (uint32_t si = 0; si < G.sections; si++) {
+        const SectionGeom &sec = G.s[si];
+        const uint32_t k = sec.chunks, fpc = sec.frags_per_chunk;
+        const uint32_t *fs = fs_frame + sec.frag_base;
+        if (sec.want_snappy) {
+            const bool indexed = write_index != 0 && sec.compress != 0;
+            for (uint32_t c0 = 0; c0 < k; c0 += kPlanThreads) {
+                uint32_t c = c0 + t, sz = 0, rec = 0;
+                if (c < k && chunk_packed_size(fs + (uint64_t)c * fpc, fpc, sec.chunk_bytes, sz) && indexed)
+                    rec = chunk_index_record_bytes(fs + (uint64_t)c * fpc, fpc);
+                uint64_t ts, tr;
+                plan_excl_sum(sz, &ts, scratch);
+                plan_excl_sum(rec, &tr, scratch);
+                body[si] += ts;
+                rec_total[si] += tr;
+            }
+            body[si] += 4u + 5ull * k + 8ull;   // hap.c:265-275: the Decode Instructions container
+            complex_storage[si] = body[si] < (uint64_t)sec.bytes + sec.top_hdr;  // hap.c:478
+        }
+        if (!complex_storage[si]) rec_total[si] = 0;
+        sec_off[si] = running_off;
+        sec_len[si] = complex_storage[si] ? (uint32_t)body[si] : sec.bytes;
+        running_off += sec.top_hdr + sec_len[si];
+    }
+    const uint32_t frame_end = running_off;   // end of the frame proper (hap.c:499 / :598)
+    // trailing index section
+    const uint32_t k0 = G.s[0].chunks, k1 = G.sections == 2 ? G.s[1].chunks : 0u;
+    const uint64_t index_len = rec_total[0] + rec_total[1] > 0 ? (uint64_t)kIndexHeaderBytes + 4ull * (k0 + k1) + rec_total[0] + rec_total[1] : 0;
+    const uint32_t index_hdr = index_len == 0 ? 0u : (index_len > kU24Max ? 8u : 4u);
+    uint8_t *ibody = fo + frame_end + index_hdr;
+    if (index_len && t == 0) {
+        put_section_header(fo + frame_end, index_hdr, (uint32_t)index_len, kSecFragmentIndex);
+        put_le32(ibody, kIndexMagic);
+        ibody[4] = (uint8_t)kIndexVersion; ibody[5] = (uint8_t)kIndexSubLog2; ibody[6] = (uint8_t)G.sections; ibody[7] = 0;
+        put_le32(ibody + 8, (uint32_t)kFragBytes);
+        put_le32(ibody + 12, k0);
+        put_le32(ibody + 16, k1);
+    }
+
+    // ---- pass 2, every section: headers, tables, varints, destinations ----------------------------------------------------------
+    uint32_t rec_running = kIndexHeaderBytes + 4u * (k0 + k1);   // offset of the next chunk record inside the index body
     for (uint32_t si = 0; si < G.sections; si++) {
         const SectionGeom &sec = G.s[si];
         const uint32_t k = sec.chunks, fpc = sec.frags_per_chunk, hdr = sec.top_hdr;
         const uint32_t di = 5u * k + 8u;  // hap.c:265-275
         const uint32_t *fs = fs_frame + sec.frag_base;
         uint32_t *fd = fd_frame + sec.frag_base;
-        // pass 1: would-be complex body length (hap.c:446-476)
-        bool complex_storage = false;
-        uint64_t body = 0;
-        if (sec.want_snappy) {
-            for (uint32_t c0 = 0; c0 < k; c0 += kPlanThreads) {
-                uint32_t c = c0 + t, sz = 0;
-                if (c < k) chunk_packed_size(fs + (uint64_t)c * fpc, fpc, sec.chunk_bytes, sz);
-                // chunk sizes can exceed 16 bits: sum the two halves separately (each fits 32 bits)
-                uint32_t tot_lo, tot_hi;
-                block_excl_sum<kPlanThreads>(sz & 0xFFFFu, &tot_lo, scratch);
-                block_excl_sum<kPlanThreads>(sz >> 16, &tot_hi, scratch);
-                body += (uint64_t)tot_lo + ((uint64_t)tot_hi << 16);
-            }
-            body += 4u + di;
-            complex_storage = body < (uint64_t)sec.bytes + hdr;  // hap.c:478
-        }
-        uint8_t *so = fo + sec_off;
-        uint32_t section_len;
-        if (complex_storage) {
-            section_len = (uint32_t)body;
+        uint32_t *fi = fi_frame + sec.frag_base;
+        uint8_t *so = fo + sec_off[si];
+        uint8_t *slots = ibody + kIndexHeaderBytes + 4u * (si ? k0 : 0u);   // this texture's record offsets
+        if (complex_storage[si]) {
             uint8_t *p = so + hdr;
             uint8_t *ctab = p + 8, *stab = p + 8 + k + 4;
             if (t == 0) {
-                put_section_header(so, hdr, section_len, (kHapComplex << 4) | sec.fmt_nibble);
+                put_section_header(so, hdr, sec_len[si], (kHapComplex << 4) | sec.fmt_nibble);
                 put_section_header(p, 4, di, kSecDecodeInstructions);        // hap.c:436
                 put_section_header(p + 4, 4, k, kSecCompressorTable);        // hap.c:438
                 put_section_header(ctab + k, 4, 4u * k, kSecSizeTable);      // hap.c:440
             }
-            uint32_t running = sec_off + hdr + 4u + di;  // offset of chunk 0 inside the frame
+            uint32_t running = sec_off[si] + hdr + 4u + di;  // offset of chunk 0 inside the frame
             for (uint32_t c0 = 0; c0 < k; c0 += kPlanThreads) {
-                uint32_t c = c0 + t, sz = 0;
+                uint32_t c = c0 + t, sz = 0, rec = 0;
                 bool snappy = false;
                 if (c < k) snappy = chunk_packed_size(fs + (uint64_t)c * fpc, fpc, sec.chunk_bytes, sz);
-                // chunk sizes can exceed 16 bits: scan the two halves separately
-                uint32_t tl, th;
-                uint32_t el = block_excl_sum<kPlanThreads>(sz & 0xFFFFu, &tl, scratch);
-                uint32_t eh = block_excl_sum<kPlanThreads>(sz >> 16, &th, scratch);
-                uint32_t start = running + el + (eh << 16);
+                if (snappy && rec_total[si]) rec = chunk_index_record_bytes(fs + (uint64_t)c * fpc, fpc);
+                uint64_t ts, tr;
+                const uint32_t start = running + plan_excl_sum(sz, &ts, scratch);
+                const uint32_t rec_off = rec_running + plan_excl_sum(rec, &tr, scratch);
                 if (c < k) {
                     ctab[c] = snappy ? kHapChunkSnappy : kHapChunkRaw;
-                    stab[4 * c] = (uint8_t)sz; stab[4 * c + 1] = (uint8_t)(sz >> 8);
-                    stab[4 * c + 2] = (uint8_t)(sz >> 16); stab[4 * c + 3] = (uint8_t)(sz >> 24);
+                    put_le32(stab + 4 * c, sz);
+                    if (index_len) put_le32(slots + 4 * c, rec ? rec_off : 0u);
                     if (snappy) {
                         uint32_t v = sec.chunk_bytes, o = start;
                         while (v >= 0x80) { fo[o++] = (uint8_t)(v | 0x80); v >>= 7; }
                         fo[o++] = (uint8_t)v;
+                        uint32_t eo = rec_off + 2u * fpc;   // entries follow the u16 sizes of the record
                         for (uint32_t j = 0; j < fpc; j++) {
+                            const uint32_t s = fs[(uint64_t)c * fpc + j];
                             fd[(uint64_t)c * fpc + j] = o;
-                            o += fs[(uint64_t)c * fpc + j];
+                            o += s;
+                            if (rec) {
+                                ibody[rec_off + 2 * j] = (uint8_t)s;
+                                ibody[rec_off + 2 * j + 1] = (uint8_t)(s >> 8);
+                                fi[(uint64_t)c * fpc + j] = frame_end + index_hdr + eo;
+                                eo += (s + (1u << kIndexSubLog2) - 1u) >> kIndexSubLog2;
+                            }
                         }
                     } else {
                         for (uint32_t j = 0; j < fpc; j++) fd[(uint64_t)c * fpc + j] = (start + j * kFragBytes) | kPlaceRawFlag;
                     }
                 }
-                running += tl + (th << 16);
+                running += (uint32_t)ts;
+                rec_running += (uint32_t)tr;
             }
         } else {
             // hap.c:490-495: the whole texture verbatim
-            section_len = sec.bytes;
-            if (t == 0) put_section_header(so, hdr, section_len, (kHapChunkRaw << 4) | sec.fmt_nibble);
-            const uint32_t data0 = sec_off + hdr;
+            if (t == 0) put_section_header(so, hdr, sec_len[si], (kHapChunkRaw << 4) | sec.fmt_nibble);
+            if (index_len) for (uint32_t c = t; c < k; c += kPlanThreads) put_le32(slots + 4 * c, 0u);
+            const uint32_t data0 = sec_off[si] + hdr;
             for (uint64_t i = t; i < (uint64_t)k * fpc; i += kPlanThreads) {
                 uint32_t c = (uint32_t)(i / fpc), j = (uint32_t)(i % fpc);
                 fd[i] = (data0 + c * sec.chunk_bytes + j * kFragBytes) | kPlaceRawFlag;
@@ -138,13 +199,10 @@ __global__ void __launch_bounds__(kPlanThreads) hap_plan_frames_kernel(
             const uint8_t *in = dxt + (uint64_t)frame * sec.in_stride + sec.in_offset;
             for (uint32_t i = covered + t; i < sec.bytes; i += kPlanThreads) fo[data0 + i] = in[i];
         }
-        if (t == 0) sec_len_sh[si] = section_len + hdr;
-        __syncthreads();
-        sec_off += sec_len_sh[si];
     }
     if (t == 0) {
-        if (G.sections == 2) put_section_header(fo, G.outer_hdr, sec_off - G.outer_hdr, kSecMultipleImages);  // hap.c:598
-        out_used[frame] = sec_off;
+        if (G.sections == 2) put_section_header(fo, G.outer_hdr, frame_end - G.outer_hdr, kSecMultipleImages);  // hap.c:598
+        out_used[frame] = frame_end + index_hdr + index_len;
     }
 }
 
@@ -153,8 +211,8 @@ constexpr int kPlaceThreads = 256;
 // grid.x = frames * frags_per_frame
 __global__ void __launch_bounds__(kPlaceThreads) hap_place_fragments_kernel(
     FrameGeom G, const uint8_t *__restrict__ dxt, const uint8_t *__restrict__ scratch,
-    const uint32_t *__restrict__ frag_size, const uint32_t *__restrict__ frag_dst, uint8_t *__restrict__ out,
-    uint64_t out_stride)
+    const uint32_t *__restrict__ frag_size, const uint32_t *__restrict__ frag_dst, const uint32_t *__restrict__ frag_idx_dst,
+    const uint8_t *__restrict__ frag_entries, uint8_t *__restrict__ out, uint64_t out_stride)
 {
     const int t = threadIdx.x;
     const uint32_t gfrag = blockIdx.x;
@@ -175,6 +233,13 @@ __global__ void __launch_bounds__(kPlaceThreads) hap_place_fragments_kernel(
         n = frag_size[gfrag];
     }
     uint8_t *dst = out + (uint64_t)frame * out_stride + (d & ~kPlaceRawFlag);
+    // the fragment's entries of the frame's index section (hap_index.h), when the plan gave them a place
+    if (frag_entries != nullptr && !(d & kPlaceRawFlag)) {
+        const uint32_t id = frag_idx_dst[gfrag];
+        const uint32_t pieces = (n + (1u << kIndexSubLog2) - 1u) >> kIndexSubLog2;
+        if (id != 0 && (uint32_t)t < pieces) out[(uint64_t)frame * out_stride + id + t] = frag_entries[(uint64_t)gfrag * kFragEntryStride + t];
+        if (id != 0 && (uint32_t)t + kPlaceThreads < pieces) out[(uint64_t)frame * out_stride + id + t + kPlaceThreads] = frag_entries[(uint64_t)gfrag * kFragEntryStride + t + kPlaceThreads];
+    }
     // destination alignment is arbitrary (headers, tables and earlier chunks are byte-sized):
     // byte-copy to the first 4-byte boundary, then aligned words assembled from two source words
     uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);

@@ -50,6 +50,8 @@ __global__ void hap_parse_frames_kernel(const uint8_t *__restrict__ in, uint64_t
             ChunkTables t;
             t.count = 0;
             r = parse_decode_instructions(sec, loc.len, t);
+            FragmentIndex ix;
+            const bool have_ix = r == HapResult_No_Error && locate_fragment_index(frame, (uint32_t)nb, ix);
             if (r == HapResult_No_Error && t.count > 0) {
                 if ((uint32_t)t.count > max_chunks) {
                     r = HapResult_Bad_Arguments;
@@ -68,6 +70,13 @@ __global__ void hap_parse_frames_kernel(const uint8_t *__restrict__ in, uint64_t
                         fj[i].dst = dst + out_run;
                         fj[i].dst_bytes = usz;
                         fj[i].compressor = (cc == kHapChunkSnappy || cc == kHapChunkRaw) ? cc : 0xFFu;  // 0xFF -> Bad_Frame in K7
+                        fj[i].index = nullptr;
+                        fj[i].index_bytes = 0;
+                        uint32_t ioff, ibytes;
+                        if (cc == kHapChunkSnappy && have_ix && fragment_index_record(frame, ix, index, (uint32_t)t.count, (uint32_t)i, ioff, ibytes)) {
+                            fj[i].index = frame + ioff;
+                            fj[i].index_bytes = ibytes;
+                        }
                         out_run += usz;
                     }
                     if (r == HapResult_No_Error && out_run > out_capacity) r = HapResult_Buffer_Too_Small;
@@ -83,7 +92,7 @@ __global__ void hap_parse_frames_kernel(const uint8_t *__restrict__ in, uint64_t
             else if (usz > out_capacity) r = HapResult_Buffer_Too_Small;
             else {
                 fj[0].src = sec; fj[0].src_bytes = loc.len; fj[0].dst = dst; fj[0].dst_bytes = usz;
-                fj[0].compressor = kHapChunkSnappy;
+                fj[0].compressor = kHapChunkSnappy; fj[0].index = nullptr; fj[0].index_bytes = 0;
                 produced = usz;
             }
         } else if (compressor == kHapChunkRaw) {
@@ -91,7 +100,7 @@ __global__ void hap_parse_frames_kernel(const uint8_t *__restrict__ in, uint64_t
             else if (loc.len > out_capacity) r = HapResult_Buffer_Too_Small;
             else {
                 fj[0].src = sec; fj[0].src_bytes = loc.len; fj[0].dst = dst; fj[0].dst_bytes = loc.len;
-                fj[0].compressor = kHapChunkRaw;
+                fj[0].compressor = kHapChunkRaw; fj[0].index = nullptr; fj[0].index_bytes = 0;
                 produced = loc.len;
             }
         } else {

@@ -7,6 +7,7 @@
 #pragma once
 #include "bc_block.cuh"  // HAP_HD
 #include "hap_codes.h"
+#include "hap_index.h"
 
 namespace hapb200 {
 
@@ -129,7 +130,7 @@ HAP_HD uint32_t parse_decode_instructions(const uint8_t *sec, uint32_t sec_len, 
         if (in.type == kSecCompressorTable) { t.compressors = pos; t.has_compressors = true; c = in.len; comp_len = in.len; }
         else if (in.type == kSecSizeTable) { t.sizes = pos; t.has_sizes = true; c = in.len / 4; size_len = in.len; }
         else if (in.type == kSecOffsetTable) { t.offsets = pos; c = in.len / 4; offs_len = in.len; }
-        // any other type: ignored, like hap.c:701-704 (this is where a private index section travels, hap_index.h)
+        // any other type: ignored, like hap.c:701-704
         if (c != 0) {
             if (t.count != 0 && (int)c != t.count) return HapResult_Bad_Frame;
             t.count = (int)c;
@@ -143,6 +144,44 @@ HAP_HD uint32_t parse_decode_instructions(const uint8_t *sec, uint32_t sec_len, 
     if (comp_len != k || size_len / 4 != k) return HapResult_Bad_Frame;
     if (offs_len != 0xFFFFFFFFu && offs_len / 4 != k) return HapResult_Bad_Frame;
     return HapResult_No_Error;
+}
+
+// The body of the trailing fragment index section of a frame (hap_index.h): offset from the frame start and length;
+// false when the frame has none (or it is not one this decoder understands).
+struct FragmentIndex {
+    uint32_t body, len;
+    uint32_t chunks[2];
+};
+HAP_HD bool locate_fragment_index(const uint8_t *frame, uint32_t n, FragmentIndex &ix)
+{
+    Section top;
+    if (read_section_header(frame, n, top) != HapResult_No_Error) return false;
+    const uint64_t end = (uint64_t)top.hdr + top.len;
+    if (end + 4 > n) return false;
+    Section s;
+    if (read_section_header(frame + end, (uint32_t)(n - end), s) != HapResult_No_Error || s.type != kSecFragmentIndex) return false;
+    if (s.len < kIndexHeaderBytes) return false;
+    const uint8_t *b = frame + end + s.hdr;
+    if (rd_le32(b) != kIndexMagic || b[4] != kIndexVersion || b[5] != kIndexSubLog2 || rd_le32(b + 8) != 32768u) return false;
+    ix.body = (uint32_t)(end + s.hdr);
+    ix.len = s.len;
+    ix.chunks[0] = rd_le32(b + 12);
+    ix.chunks[1] = rd_le32(b + 16);
+    if ((uint64_t)kIndexHeaderBytes + 4ull * ((uint64_t)ix.chunks[0] + ix.chunks[1]) > s.len) return false;
+    return true;
+}
+// The record of chunk `i` of texture `texture` (which has `count` chunks by its own tables): offset from the frame start
+// and the bytes readable from there; false when there is no record for it.
+HAP_HD bool fragment_index_record(const uint8_t *frame, const FragmentIndex &ix, uint32_t texture, uint32_t count, uint32_t i, uint32_t &off,
+                                  uint32_t &bytes)
+{
+    if (texture > 1 || ix.chunks[texture] != count || i >= count) return false;
+    const uint32_t slot = (texture ? ix.chunks[0] : 0u) + i;
+    const uint32_t o = rd_le32(frame + ix.body + kIndexHeaderBytes + 4 * slot);
+    if (o < kIndexHeaderBytes + 4u * (ix.chunks[0] + ix.chunks[1]) || o >= ix.len) return false;
+    off = ix.body + o;
+    bytes = ix.len - o;
+    return true;
 }
 
 // varint32 preamble of a raw Snappy stream (snappy_uncompressed_length, hap.c:813, :890)

@@ -1,31 +1,36 @@
-// hap_b200/csrc/snappy_decode.cuh -- K7: per-chunk second-stage decompressor.
+// hap_b200/csrc/snappy_decode.cuh -- K7: the second-stage decompressor, as three kernels.
 //
-// Replaces hap_decode_chunk + snappy_uncompress (/root/reference/source/hap.c:606-642, call sites
-// :612 and :899): one chunk of a Hap frame -> its decoded DXT bytes at a fixed destination.
-// A chunk is one raw Snappy stream (compressor byte 0x0B) or a verbatim copy (0x0A).
+// Replaces hap_decode_chunk + snappy_uncompress (/root/reference/source/hap.c:606-642, call sites :612 and :899): a chunk
+// of a Hap frame -> its decoded DXT bytes at a fixed destination.  A chunk is one raw Snappy stream (compressor byte
+// 0x0B) or a verbatim copy (0x0A).
 //
-// One CTA per chunk.  Snappy is serial inside a stream (an element's position depends on the
-// length of every element before it, and copies read earlier output), so the kernel breaks both
-// chains explicitly, window by window over the compressed bytes:
-//   1. PARSE without a serial walk over elements.  Thread t owns 64 compressed bytes and computes, for
-//      EVERY offset o inside them, where an element chain entering at o leaves the sub-block
-//      (one backward sweep, x[o] = x[o + length(o)], kept as a byte table in shared memory).  One thread
-//      then follows the true chain sub-block by sub-block with one table look-up per hop (long literals
-//      jump over whole sub-blocks), and each entered sub-block is walked once from its true entry.
-//      (A first version guessed entries and iterated to a fixpoint; on literal-heavy streams wrong
-//      guesses do not re-synchronise and it needed ~one round per sub-block: 56 % of the kernel.)
-//   2. SCAN element counts / output bytes -> every element's destination offset.
-//   3. FLATTEN + EXECUTE.  Literals are independent (source = compressed bytes).  Runs of adjacent copies
-//      with one offset (how every encoder emits a long or overlapping match) become independent
-//      periodic fills of the run's base period.  DXT payloads are full of copy-of-copy chains ("same as
-//      the previous block except a few bytes"); a copy whose source lies inside one earlier element takes
-//      over that element's source (pointer jumping), which ends at input bytes or at earlier windows, so
-//      almost everything runs in the first round.  What is left goes in dependency rounds: a copy runs
-//      once every element overlapping its source range finished in an earlier round.
-// Every decision is taken on device; the host only reads one status word per chunk.
+// Snappy is serial twice over: an element's position depends on the length of every element before it, and copies read
+// earlier output.  Round 1 broke both chains inside ONE kernel, one CTA per chunk, window after window; every phase of a
+// window waited for the slowest thread of the one before it (8 barrier-separated phases, 5.7 % of the HBM roofline).
+// Here the two chains are separated, so that only what is serial by nature stays serial:
+//
+//   snappy_index_kernel (one CTA per chunk that has no index yet; light: 50 KB of shared memory, 4 CTAs per SM)
+//       finds the ELEMENT CHAIN and nothing else.  Per 16 KiB of compressed bytes: the bytes arrive by a TMA bulk copy
+//       (double buffered: the next window lands while this one is parsed); thread t owns 64 bytes and computes, for EVERY
+//       offset o inside them, where an element chain entering at o leaves them (one backward sweep, x[o] = x[o+size(o)],
+//       branch-free); one thread hops sub-block to sub-block along the true chain with one table look-up per hop; entered
+//       sub-blocks add up their output bytes.  Result: one byte per 64 compressed bytes ("first element start in this
+//       sub-block") and the output offset of every window -- the same index this repo's encoder can write into the frame
+//       (hap_index.h), in which case this kernel does not run at all.
+//   hap_build_windows_kernel (one thread per chunk) turns chunks into WINDOWS: fragments of an indexed chunk, 64 KiB
+//       pieces of a verbatim chunk; chunks without an index are left to the kernel above.
+//   snappy_execute_kernel (persistent CTAs draw windows from a counter) does everything that touches bytes, window
+//       by window in parallel: walk the sub-blocks from their entries, scan element counts / output bytes, describe the
+//       elements, flatten copy-of-copy chains (pointer jumping), then produce the OUTPUT-CENTRIC: thread g assembles
+//       the 16 aligned output bytes of group g from the one to three elements that cover them and writes them with one
+//       128-bit store, so every lane moves the same number of bytes whatever the element lengths are.  Groups whose
+//       source bytes are not final yet wait for a later round; windows of an on-the-fly index wait (one acquire) for
+//       the earlier windows their copies reach into.
+// Every decision is taken on device; the host reads one status word per chunk.
 #pragma once
 #include "block_primitives.cuh"
 #include "hap_codes.h"
+#include "hap_index.h"
 #include "simt.h"
 
 namespace hapb200 {
@@ -35,61 +40,42 @@ struct ChunkJob {
     uint8_t *dst;         // decoded bytes go here
     uint32_t src_bytes;
     uint32_t dst_bytes;   // decoded size the container arithmetic expects (hap.c:813, :833)
-    uint32_t compressor;  // kHapCompressorNone 0x0A | kHapCompressorSnappy 0x0B (hap.c:41-42)
+    uint32_t compressor;  // kHapCompressorNone 0x0A | kHapCompressorSnappy 0x0B (hap.c:41-42); 0 = unused slot
     uint32_t status;      // out: HapResult of this chunk (hap.c:617-640)
+    const uint8_t *index; // this chunk's record inside the frame's fragment index (hap_index.h), or nullptr
+    uint32_t index_bytes; // bytes readable at `index`
+    uint32_t mode;        // internal, see kJob*
+};
+enum : uint32_t { kJobUndecided = 0, kJobIndexed = 1, kJobNeedsIndex = 2 };
+constexpr uint32_t kStatusIndexMismatch = 0x100;  // internal: the embedded index does not describe the stream -> decode again without it
+
+enum : uint32_t { kWinSnappy = 0, kWinRaw = 1, kWinSkip = 2 };
+constexpr uint32_t kNoDeps = 0xFFFFFFFFu;
+struct DecWin {                // one unit of work of the execute kernel
+    uint32_t job;
+    uint32_t kind;
+    uint32_t in_off, in_len;   // bytes [in_off, in_off + in_len) of the chunk's stream hold this window's element STARTS
+    uint32_t out_off, out_len; // its elements write job.dst[out_off, out_off + out_len)
+    const uint8_t *entries;    // first element start per sub-block (kIndexNoEntry: none)
+    uint32_t sub_log2;         // sub-block = 1 << sub_log2 stream bytes (6: index kernel, 7: embedded index)
+    uint32_t first;            // list position of the chunk's first window when copies may reach into earlier windows, else kNoDeps
+};
+struct DecodeCtl {
+    uint32_t n_windows;        // windows in the list (device-side counter)
+    uint32_t ticket;           // next window to execute
+    uint32_t overflow;         // a chunk did not fit the list (cannot happen with the host's sizing; checked)
+    uint32_t pad;
 };
 
-constexpr int kDecThreads = 256;
-constexpr int kDecSub = 64;                        // compressed bytes owned by one thread per window
-constexpr int kDecWin = kDecThreads * kDecSub;     // 16 KiB of compressed input per window
-constexpr int kDecMaxElems = 2048;                 // descriptors held in shared memory per window
 constexpr uint32_t kSrcIn = 0u << 30, kSrcOut = 1u << 30, kSrcRun = 2u << 30, kSrcMask = 3u << 30, kPosMask = (1u << 30) - 1;
-constexpr int kFlattenRounds = 1, kFlattenHops = 12;  // (a second flatten round was measured: same execution rounds, 1.5-2 % slower; none: 3.8 -> 7.9 rounds on Google-Snappy streams)
-constexpr uint32_t kLongLiteral = 16384;           // literals this long are copied by the whole CTA, one after the other; shorter ones by a
-                                                   // warp each (measured: 1024 here cost 7 % of the kernel -- the CTA-wide copies serialise)
-constexpr int kMaxLong = 64;
-constexpr int kMaxMid = 256;
-constexpr uint32_t kMidPiece = 1024;               // a warp moves a literal in pieces of this many bytes (256: +2 %, 512: +1.5 % kernel time)
-static_assert(kDecMaxElems <= 2048 && kLongLiteral / kMidPiece <= 32, "mid_list packs element (11 bits) and piece (5 bits)");
-constexpr int kGroups = kDecThreads / 8;           // 8-lane groups, one element each
-constexpr uint32_t kExitMaxRel = 186;              // tbl value <= this: exit = sub-block end + value
-constexpr uint32_t kExitFarBase = 187;             // kExitFarBase + o (o = 0..63): the chain leaves through a long literal whose
-                                                   // header sits at offset o of the sub-block; its end is read from that header
-constexpr uint32_t kExitInvalid = 254;             // the chain runs into an invalid element header
+constexpr uint32_t kRawWindow = 65536;
 
-struct DecodeSmem {
-    uint32_t e_dst[kDecMaxElems];    // output offset inside the chunk
-    uint32_t e_len[kDecMaxElems];
-    uint32_t e_a[kDecMaxElems];      // packed source: kSrcIn|input position, kSrcOut|output position, kSrcRun|offset
-    uint32_t e_b[kDecMaxElems];      // destination of the head of the element's same-offset run (its own, if alone)
-    uint16_t e_done[kDecMaxElems];   // 0 = pending, r = finished in round r
-    uint8_t cin[kDecWin + 64];       // staged window: aligned image of the input (+ alignment shift + header slack)
-    uint8_t tbl[kDecSub * kDecThreads];  // tbl[o][t]: where the chain entering sub-block t at offset o leaves it
-    uint16_t entry[kDecThreads];     // true entry offset of each sub-block, 0xFFFF = jumped over
-    uint32_t scratch[kDecThreads / 32];
-    uint32_t bcast[4];
-    unsigned long long saddr_box;    // see the chain hop
-    uint32_t n_long;                 // long literals of the current window
-    uint32_t long_list[kMaxLong];
-    uint32_t n_mid;                  // pieces (<= kMidPiece bytes) of the literals of kThreadElem+1 .. kLongLiteral-1 bytes
-    uint32_t mid_next;               // next piece to hand out (warps take pieces as they become free)
-    uint16_t mid_list[kMaxMid];      // element | piece << 11
-    int fail;        // preamble / parse stage
-    int fail_desc;   // descriptor stage (separate word: it is written while slow threads may still read `fail`)
-};
-
-// Walk the element chain of one sub-block.  Positions are absolute inside the chunk input.
-// Returns the first chain position >= blk_end (clamped to in_end when the chain is invalid).
-struct WalkResult {
-    uint32_t exit, count, out_bytes;
-    int invalid;
-};
-
-__device__ __forceinline__ bool read_element_header(const uint8_t *cin, uint32_t wb, uint32_t pos, uint32_t in_end,
-                                                    uint32_t &len, uint32_t &aux, uint32_t &hdr, uint32_t &kind)
+// ---- element headers --------------------------------------------------------------------------------------------------
+// p = the element's first byte (readable for 5 bytes; bytes past the stream's end may hold anything: they are only
+// interpreted after the length checks below passed).  pos/in_end are positions inside the chunk's stream.
+__device__ __forceinline__ bool read_element_header(const uint8_t *p, uint32_t pos, uint32_t in_end, uint32_t &len, uint32_t &aux,
+                                                    uint32_t &hdr, uint32_t &kind)
 {
-    // cin[pos - wb .. +5) is always staged (zero beyond the input), so the loads below are in range
-    const uint8_t *p = cin + (pos - wb);
     uint32_t tag = p[0];
     kind = tag & 3;
     if (kind == 0) {
@@ -123,21 +109,514 @@ __device__ __forceinline__ bool read_element_header(const uint8_t *cin, uint32_t
     return (uint64_t)pos + hdr <= in_end;
 }
 
-__device__ __forceinline__ WalkResult walk_subblock(const uint8_t *cin, uint32_t wb, uint32_t entry, uint32_t blk_end,
-                                                    uint32_t in_end)
+// varint32 preamble of a raw Snappy stream; returns its length in bytes, 0 when malformed
+__device__ __forceinline__ uint32_t read_preamble(const uint8_t *src, uint32_t n, uint64_t &value)
+{
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < 5 && i < n; i++) {
+        const uint32_t b = src[i];
+        v |= (uint64_t)(b & 0x7F) << (7 * i);
+        if (!(b & 0x80)) { value = v; return i + 1; }
+    }
+    return 0;
+}
+
+// ---- staging: `len` bytes at global address g -> shared memory such that base[a + i] = g[i], a = g & 15 ------------------
+// The 16-byte units that lie wholly inside [g, g + len) travel by ONE bulk copy (TMA; completes on `bar`); the at most
+// 15 bytes in front of and behind them are fetched by single threads, so nothing outside [g, g + len) is ever read.
+// Call with all threads of the CTA; the data is complete after hap_mbar_wait(bar, parity) + __syncthreads().
+__device__ __forceinline__ void stage_bytes(uint8_t *base, const uint8_t *g, uint32_t len, hap_mbar_t *bar, int t)
+{
+    const uint32_t a = (uint32_t)((uintptr_t)g & 15);
+    const uint32_t head = len < ((16 - a) & 15) ? len : ((16 - a) & 15);   // bytes before the first aligned unit
+    const uint32_t body = (len - head) & ~15u;
+    const uint32_t tail = len - head - body;
+    if (t == 0) {
+        hap_mbar_expect_tx(bar, body);   // with body == 0 this arrival alone completes the phase
+        if (body) hap_tma_load_1d(base + a + head, g + head, body, bar);
+    }
+    if ((uint32_t)t < head) base[a + t] = g[t];
+    if ((uint32_t)t >= 32 && (uint32_t)t < 32 + tail) base[a + head + body + (t - 32)] = g[head + body + (t - 32)];
+}
+
+// =====================================================================================================================
+//  index kernel
+// =====================================================================================================================
+constexpr int kIdxThreads = 256;
+constexpr int kIdxSub = 64;                          // compressed bytes owned by one thread per window
+constexpr int kIdxWin = kIdxThreads * kIdxSub;       // 16 KiB of compressed input per window
+constexpr int kIdxLook = 32;                         // staged beyond the window: header look-ahead of its last elements
+constexpr int kTblStride = kIdxThreads + 4;          // row stride of the exit table: rows 65 words apart, so that the 32 lanes'
+                                                     // look-ups of DIFFERENT rows spread over the banks (256 put four lanes on one)
+constexpr uint32_t kExitMaxRel = 186;                // tbl value <= this: exit = sub-block end + value
+constexpr uint32_t kExitFarBase = 187;               // kExitFarBase + o (o = 0..63): the chain leaves through a long literal whose
+                                                     // header sits at offset o of the sub-block; its end is read from that header
+constexpr uint32_t kExitInvalid = 254;               // the chain runs into an invalid element header
+
+struct IndexSmem {
+    uint8_t cin[2][kIdxWin + kIdxLook + 32];         // staged windows (double buffered), cin[b][a + i] = byte i of the window
+    uint8_t tbl[kIdxSub * kTblStride];               // tbl[o][t]: where the chain entering sub-block t at offset o leaves it
+    uint16_t entry[kIdxThreads];                     // true entry offset of each sub-block, 0xFFFF = no element starts there
+    uint32_t scratch[kIdxThreads / 32];
+    hap_mbar_t bar[2];
+    unsigned long long saddr_box;
+    uint32_t next_rel;
+    int fail;
+};
+
+// jobs with mode == want_mode are indexed: entries (one byte per 64 stream bytes) and one DecWin per 16 KiB of stream are
+// appended to the lists.  entries_pool: [win_cap][256].
+__global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *jobs, int njobs, uint32_t want_mode, DecWin *wins,
+                                                                      uint32_t win_cap, uint8_t *entries_pool, DecodeCtl *ctl)
+{
+    HAP_DYN_SMEM(smem_raw);
+    IndexSmem &S = *reinterpret_cast<IndexSmem *>(smem_raw);
+    const int t = threadIdx.x;
+    if ((int)blockIdx.x >= njobs) return;
+    ChunkJob &job = jobs[blockIdx.x];
+    if (job.mode != want_mode || job.compressor != kHapChunkSnappy) return;
+    const uint8_t *__restrict__ src = job.src;
+    const uint32_t n = job.src_bytes;
+    const uint32_t expected = job.dst_bytes;
+    const uint32_t nwin = (n + kIdxWin - 1) / kIdxWin;
+
+    if (t == 0) {
+        uint64_t v = 0;
+        const uint32_t pre = read_preamble(src, n, v);
+        S.fail = (pre == 0 || v != (uint64_t)expected) ? 1 : 0;
+        S.next_rel = pre;
+        uint32_t base = 0;
+        if (!S.fail) {
+            base = atomicAdd(&ctl->n_windows, nwin);
+            if (base + nwin > win_cap || base + nwin < base) { S.fail = 2; atomicExch(&ctl->overflow, 1u); }
+        }
+        S.scratch[0] = base;
+        hap_mbar_init(&S.bar[0], 1);
+        hap_mbar_init(&S.bar[1], 1);
+    }
+    __syncthreads();
+    if (S.fail) {
+        if (t == 0) { job.status = S.fail == 2 ? HapResult_Internal_Error : HapResult_Bad_Frame; job.mode = kJobIndexed; }
+        return;
+    }
+    const uint32_t base = S.scratch[0];
+    const uint32_t a = (uint32_t)((uintptr_t)src & 15);   // the same for every window: windows are 16 KiB apart
+    __syncthreads();
+
+    auto window_len = [&](uint32_t k) { return n - k * kIdxWin < (uint32_t)kIdxWin ? n - k * kIdxWin : (uint32_t)kIdxWin; };
+    auto staged_len = [&](uint32_t k) { return n - k * kIdxWin < (uint32_t)(kIdxWin + kIdxLook) ? n - k * kIdxWin : (uint32_t)(kIdxWin + kIdxLook); };
+
+    stage_bytes(S.cin[0], src, staged_len(0), &S.bar[0], t);
+    uint64_t d0 = 0;        // output bytes of earlier windows
+    uint32_t k = 0;
+    for (; k < nwin; k++) {
+        const uint32_t buf = k & 1;
+        // the next window's bytes start travelling now (its buffer was last read two windows ago; the barrier that
+        // closed the previous iteration ordered those reads before this copy)
+        if (k + 1 < nwin) stage_bytes(S.cin[buf ^ 1], src + (size_t)(k + 1) * kIdxWin, staged_len(k + 1), &S.bar[buf ^ 1], t);
+        S.entry[t] = 0xFFFFu;
+        hap_mbar_wait(&S.bar[buf], (k >> 1) & 1);
+        __syncthreads();
+        const uint8_t *cin = S.cin[buf] + a;
+        const uint32_t wl = window_len(k);
+        const uint32_t wpos = k * kIdxWin;                 // stream position of the window's first byte
+
+        // ---- (a) every thread: for EACH of the 64 offsets of its sub-block, where does an element chain entering
+        //      there leave the sub-block?  One backward sweep: x[o] = x[o + size(o)], branch-free ------------------
+        if ((uint32_t)t * kIdxSub < wl) {
+            const uint32_t blk_len = wl - t * kIdxSub < (uint32_t)kIdxSub ? wl - t * kIdxSub : (uint32_t)kIdxSub;
+            const uint32_t limit = n - (wpos + t * kIdxSub);   // a chain position may not pass this
+            const uint32_t bi = a + (uint32_t)t * kIdxSub;     // byte index inside S.cin[buf]
+            const uint32_t *c32 = reinterpret_cast<const uint32_t *>(S.cin[buf]) + (bi >> 2);
+            const uint32_t sh = 8 * (bi & 3);
+            uint8_t *col = S.tbl + t;
+#pragma unroll 1
+            for (int g = kIdxSub / 16 - 1; g >= 0; g--) {
+                uint32_t raw[7], w[6];
+#pragma unroll
+                for (int q = 0; q < 7; q++) raw[q] = c32[4 * g + q];
+#pragma unroll
+                for (int q = 0; q < 6; q++) w[q] = __funnelshift_r(raw[q], raw[q + 1], sh);
+#pragma unroll
+                for (int oo = 15; oo >= 0; oo--) {
+                    const uint32_t o = (uint32_t)(16 * g + oo);
+                    const uint32_t tag = (w[oo >> 2] >> (8 * (oo & 3))) & 0xFFu;
+                    const uint32_t kind = tag & 3u, m = tag >> 2;
+                    const uint32_t v4 = __funnelshift_r(w[(oo + 1) >> 2], w[((oo + 1) >> 2) + 1], 8 * ((oo + 1) & 3));  // the 4 bytes after the tag
+                    const uint32_t extra = m - 59u;                                  // 1..4 when m >= 60
+                    const uint32_t mm = extra >= 4u ? v4 : (v4 & ((1u << (8 * (extra & 3))) - 1u));
+                    const uint32_t lit_long = mm >= 0x3FFFFFFFu ? 0x7FFFFFFFu : o + 2u + extra + mm;   // cannot fit a < 1 GiB chunk
+                    const uint32_t lit = m < 60u ? o + m + 2u : lit_long;
+                    const uint32_t nxt = kind != 0u ? o + ((0x5320u >> (4 * kind)) & 0xFu) : lit;     // copy headers: 2, 3 or 5 bytes
+                    const uint32_t inside = nxt < blk_len ? nxt : o;                 // a row this thread has already written
+                    const uint32_t chained = col[inside * kTblStride];
+                    const uint32_t beyond = nxt - blk_len <= kExitMaxRel ? nxt - blk_len : kExitFarBase + o;
+                    uint32_t x = nxt < blk_len ? chained : beyond;
+                    x = nxt > limit ? kExitInvalid : x;                              // header or payload runs past the input
+                    col[o * kTblStride] = (uint8_t)x;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- (b) one thread hops sub-block to sub-block along the true chain ---------------------------------------------
+        if (t == 0) {
+            uint32_t rel = S.next_rel;       // window-relative position of the next true element start
+            // The table's shared-window address, read back through a volatile word: ptxas otherwise re-derives it from
+            // the CTA-in-cluster id (an S2R, tens of cycles on this thread's critical path) in EVERY iteration of the hop.
+            volatile hap_saddr_t *base_box = reinterpret_cast<volatile hap_saddr_t *>(&S.saddr_box);
+            *base_box = hap_smem_addr(S.tbl);
+            const hap_saddr_t tbl_s = *base_box, entry_s = tbl_s + (hap_saddr_t)((const uint8_t *)S.entry - (const uint8_t *)S.tbl);
+            while (rel < wl) {
+                const uint32_t blk = rel >> 6, o = rel & 63;
+                const uint32_t x = hap_lds_u8(tbl_s + (o * kTblStride + blk));
+                hap_sts_u16(entry_s + 2 * blk, o);
+                uint32_t bend = (blk + 1) << 6;
+                bend = bend < wl ? bend : wl;
+                if (x <= kExitMaxRel) {
+                    rel = bend + x;
+                } else if (x == kExitInvalid) {
+                    S.fail = 1;
+                    break;
+                } else {
+                    // a long literal leaves this sub-block by more than a byte can hold: the table names its header
+                    const uint32_t p2 = (blk << 6) + (x - kExitFarBase);
+                    uint32_t len, aux, hdr, kind;
+                    if (!read_element_header(cin + p2, wpos + p2, n, len, aux, hdr, kind) || kind != 0) { S.fail = 1; break; }
+                    rel = p2 + hdr + len;
+                }
+            }
+            S.next_rel = rel - wl;           // (garbage when the hop failed: nobody reads it then)
+            if (k + 1 == nwin && rel != wl) S.fail = 1;   // the chain must end exactly at the end of the stream
+        }
+        __syncthreads();
+        // ---- (c) every entered sub-block adds up the output of the elements that start in it ----------------------------
+        uint32_t out_bytes = 0;
+        int invalid = 0;
+        const uint32_t ent = S.entry[t];
+        if (ent != 0xFFFFu) {
+            uint32_t pos = t * kIdxSub + ent;
+            const uint32_t end = (t + 1) * kIdxSub < wl ? (t + 1) * kIdxSub : wl;
+            while (pos < end) {
+                uint32_t len, aux, hdr, kind;
+                if (!read_element_header(cin + pos, wpos + pos, n, len, aux, hdr, kind)) { invalid = 1; break; }
+                out_bytes += len;                      // (cannot wrap: <= 64 elements of <= 2^30 + ... checked against `expected` below)
+                pos += hdr + (kind == 0 ? len : 0);
+            }
+        }
+        uint32_t total_o;
+        block_excl_sum<kIdxThreads>(out_bytes > 0x40000000u ? 0x40000000u : out_bytes, &total_o, S.scratch);
+        if (invalid) S.fail = 1;
+        if (t == 0 && d0 + total_o > (uint64_t)expected) S.fail = 1;
+        __syncthreads();
+        if (S.fail) break;
+        entries_pool[(size_t)(base + k) * kIdxThreads + t] = ent == 0xFFFFu ? (uint8_t)kIndexNoEntry : (uint8_t)ent;
+        if (t == 0) {
+            DecWin w;
+            w.job = blockIdx.x;
+            w.kind = kWinSnappy;
+            w.in_off = wpos;
+            w.in_len = wl;
+            w.out_off = (uint32_t)d0;
+            w.out_len = total_o;
+            w.entries = entries_pool + (size_t)(base + k) * kIdxThreads;
+            w.sub_log2 = 6;
+            w.first = base;
+            wins[base + k] = w;
+        }
+        d0 += total_o;
+    }
+    if (k < nwin || d0 != (uint64_t)expected) {
+        // invalid stream: the windows written so far stay (they decode what was valid), the rest of the range is skipped
+        for (uint32_t r = k + t; r < nwin; r += kIdxThreads) {
+            DecWin w;
+            w.job = blockIdx.x; w.kind = kWinSkip; w.in_off = 0; w.in_len = 0; w.out_off = 0; w.out_len = 0;
+            w.entries = nullptr; w.sub_log2 = 6; w.first = base;
+            wins[base + r] = w;
+        }
+        if (t == 0) job.status = HapResult_Bad_Frame;
+    }
+    if (t == 0) job.mode = kJobIndexed;
+}
+
+// =====================================================================================================================
+//  chunks -> windows (one thread per chunk)
+// =====================================================================================================================
+constexpr uint32_t kFragMaxStream = 32768 + 32;      // an element stream of one fragment (snappy_encode.cuh: at most n + 3)
+constexpr uint32_t kIndexFragBytes = 32768;
+
+__device__ __forceinline__ uint32_t rd16(const uint8_t *p) { return p[0] | (p[1] << 8); }
+
+// use_index = 0: ignore embedded indexes (every Snappy chunk goes to the index kernel).
+__global__ void hap_build_windows_kernel(ChunkJob *jobs, uint32_t njobs, uint32_t use_index, DecWin *wins, uint32_t win_cap, DecodeCtl *ctl)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    ChunkJob &job = jobs[j];
+    if (job.compressor == 0) return;   // unused slot of a batched frame (hap_parse.cuh)
+    job.status = HapResult_No_Error;
+    job.mode = kJobIndexed;
+    const uint32_t n = job.src_bytes, expected = job.dst_bytes;
+    if (job.compressor == kHapChunkRaw) {
+        // hap.c:630-636: verbatim chunk
+        if (n != expected) { job.status = HapResult_Bad_Frame; return; }
+        const uint32_t cnt = (n + kRawWindow - 1) / kRawWindow;
+        if (cnt == 0) return;
+        const uint32_t base = atomicAdd(&ctl->n_windows, cnt);
+        if (base + cnt > win_cap || base + cnt < base) { job.status = HapResult_Internal_Error; atomicExch(&ctl->overflow, 1u); return; }
+        for (uint32_t i = 0; i < cnt; i++) {
+            DecWin w;
+            w.job = j; w.kind = kWinRaw; w.in_off = i * kRawWindow; w.in_len = n - i * kRawWindow < kRawWindow ? n - i * kRawWindow : kRawWindow;
+            w.out_off = w.in_off; w.out_len = w.in_len; w.entries = nullptr; w.sub_log2 = 6; w.first = kNoDeps;
+            wins[base + i] = w;
+        }
+        return;
+    }
+    if (job.compressor != kHapChunkSnappy || n > kPosMask || expected > kPosMask) {
+        // hap.c:637-640; also chunks of 1 GiB and more, whose positions do not fit the packed descriptors
+        job.status = HapResult_Bad_Frame;
+        return;
+    }
+    uint64_t v = 0;
+    const uint32_t pre = read_preamble(job.src, n, v);
+    if (pre == 0 || v != (uint64_t)expected) { job.status = HapResult_Bad_Frame; return; }
+    job.mode = kJobNeedsIndex;
+    if (!use_index || job.index == nullptr) return;
+    // embedded index (hap_index.h): u16 stream_bytes[nf], then the entries of every fragment
+    const uint32_t nf = (expected + kIndexFragBytes - 1) / kIndexFragBytes;
+    if (nf == 0 || (uint64_t)2 * nf > job.index_bytes) return;
+    uint64_t stream = pre, ent_bytes = 0;
+    for (uint32_t f = 0; f < nf; f++) {
+        const uint32_t s = rd16(job.index + 2 * f);
+        if (s == 0 || s > kFragMaxStream) return;
+        stream += s;
+        ent_bytes += (s + (1u << kIndexSubLog2) - 1) >> kIndexSubLog2;
+    }
+    if (stream != n || 2ull * nf + ent_bytes > job.index_bytes) return;
+    const uint32_t base = atomicAdd(&ctl->n_windows, nf);
+    if (base + nf > win_cap || base + nf < base) { job.status = HapResult_Internal_Error; job.mode = kJobIndexed; atomicExch(&ctl->overflow, 1u); return; }
+    uint32_t in_off = pre;
+    const uint8_t *ent = job.index + 2 * nf;
+    for (uint32_t f = 0; f < nf; f++) {
+        const uint32_t s = rd16(job.index + 2 * f);
+        DecWin w;
+        w.job = j; w.kind = kWinSnappy; w.in_off = in_off; w.in_len = s;
+        w.out_off = f * kIndexFragBytes;
+        w.out_len = expected - w.out_off < kIndexFragBytes ? expected - w.out_off : kIndexFragBytes;
+        w.entries = ent; w.sub_log2 = kIndexSubLog2; w.first = kNoDeps;
+        wins[base + f] = w;
+        in_off += s;
+        ent += (s + (1u << kIndexSubLog2) - 1) >> kIndexSubLog2;
+    }
+    job.mode = kJobIndexed;
+}
+
+// After an execute pass: chunks whose embedded index did not hold up are handed to the index kernel (mode kJobNeedsIndex,
+// status cleared); *any_left counts them.
+__global__ void hap_requeue_mismatched_kernel(ChunkJob *jobs, uint32_t njobs, DecodeCtl *ctl, uint32_t *any_left)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) ctl->ticket = ctl->n_windows;   // every window listed so far has been executed; new ones follow
+    if (j >= njobs) return;
+    if (jobs[j].compressor != 0 && jobs[j].status == kStatusIndexMismatch) {
+        jobs[j].status = HapResult_No_Error;
+        jobs[j].mode = kJobNeedsIndex;
+        atomicAdd(any_left, 1u);
+    } else if (jobs[j].mode == kJobNeedsIndex) {
+        jobs[j].mode = kJobIndexed;   // (not reached: every such chunk was indexed before the execute pass)
+    }
+}
+
+// =====================================================================================================================
+//  execute kernel
+// =====================================================================================================================
+constexpr int kExThreads = 256;
+constexpr int kExMaxElems = 2048;                    // descriptors held in shared memory per pass
+constexpr int kExMaxIn = 32768 + 64;                 // stream bytes of one window the staging buffer holds
+constexpr int kExLook = 16;                          // staged beyond the window: header look-ahead
+constexpr int kExTile = 32768;                       // output bytes produced per tile
+constexpr int kExGroups = kExTile / 16 + 1;          // a tile that does not start on a 16-byte address touches one group more
+constexpr int kFlattenHops = 12;
+
+struct ExecSmem {
+    uint8_t cin[kExMaxIn + kExLook + 48];            // staged window, cin[a + i] = byte i of the window
+    uint32_t e_dst[kExMaxElems];                     // output position inside the chunk
+    uint32_t e_len[kExMaxElems];
+    uint32_t e_a[kExMaxElems];                       // packed source: kSrcIn|input position, kSrcOut|output position, kSrcRun|offset
+    uint32_t e_b[kExMaxElems];                       // destination of the head of the element's same-offset run (its own, if alone)
+    uint16_t gfirst[kExGroups + 7];                  // (element + 1) that holds the first byte of an output group
+    uint16_t gdone[kExGroups + 7];                   // round in which a group was written (0: not yet)
+    uint8_t landed[kExThreads];                      // a chain exit lands in this sub-block
+    uint32_t scratch[kExThreads / 32];
+    uint32_t red[3][kExThreads / 32];
+    DecWin win;
+    hap_mbar_t bar;
+    uint32_t ticket;
+    uint32_t min_src;
+    int fail;         // walk stage
+    int fail_desc;    // descriptor stage
+    int mismatch;     // embedded index does not describe the chain
+};
+
+// three block reductions at once: minimum of a, minimum of b, maximum of c (two barriers)
+__device__ __forceinline__ void block_min_min_max(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t (*red)[kExThreads / 32])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const uint32_t oa = __shfl_xor_sync(HAP_FULL_MASK, a, d), ob = __shfl_xor_sync(HAP_FULL_MASK, b, d), oc = __shfl_xor_sync(HAP_FULL_MASK, c, d);
+        a = a < oa ? a : oa;
+        b = b < ob ? b : ob;
+        c = c > oc ? c : oc;
+    }
+    if (lane == 0) { red[0][warp] = a; red[1][warp] = b; red[2][warp] = c; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kExThreads / 32; w++) {
+        a = a < red[0][w] ? a : red[0][w];
+        b = b < red[1][w] ? b : red[1][w];
+        c = c > red[2][w] ? c : red[2][w];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long low_bytes_mask(uint32_t k) { return k >= 8 ? ~0ull : ((1ull << (8 * k)) - 1ull); }
+
+// One aligned 32-bit word at `wa`, of which only the bytes inside [need_lo, need_hi) are wanted.  The word is loaded whole
+// when it lies inside the readable region [r_lo, r_hi); otherwise its wanted bytes are fetched one by one (the first and
+// last word of a chunk or of the output buffer), so that nothing outside the region is touched.
+__device__ __forceinline__ uint32_t word_for(uintptr_t wa, uintptr_t need_lo, uintptr_t need_hi, uintptr_t r_lo, uintptr_t r_hi)
+{
+    if (wa + 4 <= need_lo || wa >= need_hi) return 0;
+    if (wa >= r_lo && wa + 4 <= r_hi) return *reinterpret_cast<const uint32_t *>(wa);
+    uint32_t v = 0;
+    for (uint32_t q = 0; q < 4; q++)
+        if (wa + q >= need_lo && wa + q < need_hi) v |= (uint32_t) * reinterpret_cast<const uint8_t *>(wa + q) << (8 * q);
+    return v;
+}
+
+// n (1..16) bytes at `ptr` -> bytes [q, q + n) of the 16-byte group held in (lo64, hi64)
+__device__ __forceinline__ void gather_into_group(const uint8_t *ptr, uint32_t n, uint32_t q, uintptr_t r_lo, uintptr_t r_hi,
+                                                  unsigned long long &lo64, unsigned long long &hi64)
+{
+    const uintptr_t p = (uintptr_t)ptr;
+    if (n == 16 && (p & 15) == 0 && p >= r_lo && p + 16 <= r_hi) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p);
+        lo64 = v.x | ((unsigned long long)v.y << 32);
+        hi64 = v.z | ((unsigned long long)v.w << 32);
+        return;
+    }
+    // the address that corresponds to byte 0 of the group, its aligned base and the shift between the two
+    const uintptr_t g0 = p - q;
+    const uint32_t mis = (uint32_t)(g0 & 3);
+    const uintptr_t b0 = g0 - mis;
+    uint32_t s[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) s[k] = word_for(b0 + 4 * k, p, p + n, r_lo, r_hi);
+    const uint32_t c0 = __funnelshift_r(s[0], s[1], 8 * mis), c1 = __funnelshift_r(s[1], s[2], 8 * mis);
+    const uint32_t c2 = __funnelshift_r(s[2], s[3], 8 * mis), c3 = __funnelshift_r(s[3], s[4], 8 * mis);
+    const unsigned long long cl = c0 | ((unsigned long long)c1 << 32), ch = c2 | ((unsigned long long)c3 << 32);
+    const uint32_t e = q + n;
+    const unsigned long long ml = low_bytes_mask(e < 8 ? e : 8) & ~low_bytes_mask(q < 8 ? q : 8);
+    const unsigned long long mh = low_bytes_mask(e > 8 ? e - 8 : 0) & ~low_bytes_mask(q > 8 ? q - 8 : 0);
+    lo64 = (lo64 & ~ml) | (cl & ml);
+    hi64 = (hi64 & ~mh) | (ch & mh);
+}
+
+__device__ __forceinline__ uint32_t group_byte(unsigned long long lo64, unsigned long long hi64, uint32_t i)
+{
+    const unsigned long long h = (i & 8) ? hi64 : lo64;
+    return (uint32_t)(h >> (8 * (i & 7))) & 0xFFu;
+}
+__device__ __forceinline__ void set_group_byte(unsigned long long &lo64, unsigned long long &hi64, uint32_t i, uint32_t b)
+{
+    const unsigned long long m = 0xFFull << (8 * (i & 7)), v = (unsigned long long)b << (8 * (i & 7));
+    if (i & 8) hi64 = (hi64 & ~m) | v;
+    else lo64 = (lo64 & ~m) | v;
+}
+
+// Everything one tile of output needs to know.
+struct TileCtx {
+    const uint8_t *src;        // the chunk's stream
+    uint8_t *dst;              // the chunk's output
+    uint32_t src_bytes, dst_bytes;
+    const uint8_t *cin;        // staged window: cin[i] = stream byte wb + i for i < staged
+    uint32_t wb, staged;
+    int32_t gbase;             // output position of byte 0 of group 0 (may lie before T0: group 0 can be partial)
+    uint32_t T0, T1;           // the tile's output positions
+};
+
+// Assemble the bytes [max(gstart, T0), min(gstart + 16, T1)) of group g and write them.  false: a source is not final yet.
+__device__ __forceinline__ bool assemble_group(ExecSmem &S, const TileCtx &C, uint32_t g, uint32_t round)
+{
+    const int32_t gstart = C.gbase + 16 * (int32_t)g;
+    const uint32_t lo = gstart > (int32_t)C.T0 ? (uint32_t)gstart : C.T0;
+    const uint32_t hi = (uint32_t)(gstart + 16) < C.T1 ? (uint32_t)(gstart + 16) : C.T1;
+    uint32_t e = (uint32_t)S.gfirst[g] - 1u;
+    unsigned long long lo64 = 0, hi64 = 0;
+    uint32_t pos = lo;
+    while (pos < hi) {
+        const uint32_t d = S.e_dst[e], l = S.e_len[e];
+        const uint32_t seg_end = d + l < hi ? d + l : hi;
+        uint32_t n = seg_end - pos;
+        const uint32_t q = (uint32_t)((int32_t)pos - gstart);
+        const uint32_t a = S.e_a[e], kind = a & kSrcMask, ap = a & kPosMask;
+        if (kind == kSrcIn) {
+            const uint32_t ip = ap + (pos - d);
+            if (ip >= C.wb && ip + n <= C.wb + C.staged) gather_into_group(C.cin + (ip - C.wb), n, q, 0, ~(uintptr_t)0, lo64, hi64);
+            else gather_into_group(C.src + ip, n, q, (uintptr_t)C.src, (uintptr_t)C.src + C.src_bytes, lo64, hi64);
+        } else {
+            uint32_t sp;
+            if (kind == kSrcOut) {
+                sp = ap + (pos - d);
+            } else {
+                // periodic fill of the run's base period: the bytes [base - off, base)
+                const uint32_t off = ap, base = S.e_b[e];
+                const uint32_t r = (pos - base) % off;
+                if (n > off - r) n = off - r;
+                sp = base - off + r;
+            }
+            if (sp >= lo) {
+                // the source bytes are earlier bytes of this very group (offsets below 16): they are in the registers
+                for (uint32_t i = 0; i < n; i++) set_group_byte(lo64, hi64, q + i, group_byte(lo64, hi64, (uint32_t)((int32_t)(sp + i) - gstart)));
+            } else {
+                if (sp + n > lo) n = lo - sp;             // the rest of the piece comes from the registers next time round
+                if (sp + n > C.T0) {
+                    // bytes this tile produces: their groups must have been written in an earlier round
+                    const int32_t rel0 = (int32_t)sp - C.gbase, rel1 = (int32_t)(sp + n - 1) - C.gbase;
+                    const uint32_t g0 = rel0 < 0 ? 0u : (uint32_t)rel0 >> 4, g1 = (uint32_t)rel1 >> 4;
+                    const uint32_t r0 = S.gdone[g0], r1 = S.gdone[g1];
+                    if (r0 == 0 || r0 >= round || r1 == 0 || r1 >= round) return false;
+                }
+                gather_into_group(C.dst + sp, n, q, (uintptr_t)C.dst, (uintptr_t)C.dst + C.dst_bytes, lo64, hi64);
+            }
+        }
+        pos += n;
+        if (pos >= d + l) e++;
+    }
+    uint8_t *out = C.dst + gstart;   // 16-byte aligned by construction of gbase
+    if (lo == (uint32_t)gstart && hi == (uint32_t)(gstart + 16)) {
+        *reinterpret_cast<uint4 *>(out) = make_uint4((uint32_t)lo64, (uint32_t)(lo64 >> 32), (uint32_t)hi64, (uint32_t)(hi64 >> 32));
+    } else {
+        for (uint32_t i = (uint32_t)((int32_t)lo - gstart); i < (uint32_t)((int32_t)hi - gstart); i++) out[i] = (uint8_t)group_byte(lo64, hi64, i);
+    }
+    S.gdone[g] = (uint16_t)round;
+    return true;
+}
+
+// walk the elements that start in stream bytes [pos, end) of the window; positions are relative to the window
+struct WalkResult {
+    uint32_t exit, count, out_bytes;
+    int invalid;
+};
+__device__ __forceinline__ WalkResult walk_piece(const uint8_t *cin, uint32_t wb, uint32_t pos, uint32_t end, uint32_t in_end)
 {
     WalkResult r;
     r.count = 0;
     r.out_bytes = 0;
     r.invalid = 0;
-    uint32_t pos = entry;
-    while (pos < blk_end) {
+    while (pos < end) {
         uint32_t len, aux, hdr, kind;
-        if (!read_element_header(cin, wb, pos, in_end, len, aux, hdr, kind)) {
-            r.invalid = 1;
-            pos = in_end;
-            break;
-        }
+        if (!read_element_header(cin + pos, wb + pos, in_end, len, aux, hdr, kind)) { r.invalid = 1; break; }
         r.count++;
         r.out_bytes += len;
         pos += hdr + (kind == 0 ? len : 0);
@@ -146,460 +625,207 @@ __device__ __forceinline__ WalkResult walk_subblock(const uint8_t *cin, uint32_t
     return r;
 }
 
-// Next chain position after a literal whose length sits in 1..4 bytes behind the tag (m = 60..63); `v` = those bytes.
-// Rare, and not inlined into the 16 unrolled steps of the exit-table sweep.
-__device__ __noinline__ uint64_t long_literal_next(uint32_t o, uint32_t m, uint32_t v)
-{
-    const uint32_t extra = m - 59;
-    const uint32_t mm = extra == 4 ? v : (v & ((1u << (8 * extra)) - 1u));
-    return mm == 0xFFFFFFFFu ? ~0ull : (uint64_t)o + 1 + extra + (uint64_t)mm + 1;
-}
-
-// dst/src any alignment.  `lane` of `n_lanes` cooperating threads; 4 bytes per thread per step once the
-// destination is word-aligned, the source word assembled from two aligned words when it is not.
-template <int N_LANES>
-__device__ __noinline__ void lanes_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t lane)
-{
-    uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
-    if (head > len) head = len;
-    if (lane < head) dst[lane] = src[lane];
-    const uint32_t body = len - head;
-    uint32_t nw = body >> 2;
-    const uint8_t *s2 = src + head;
-    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + head);
-    const uint32_t mis = (uint32_t)((uintptr_t)s2 & 3);
-    if (mis == 0) {
-        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s2);
-        for (uint32_t k = lane; k < nw; k += N_LANES) d32[k] = s32[k];
-    } else {
-        // word k needs aligned words k and k+1; the last one would read past the source: leave it to the tail
-        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s2 - mis);
-        if (nw) nw -= 1;
-        for (uint32_t k = lane; k < nw; k += N_LANES) d32[k] = __funnelshift_r(s32[k], s32[k + 1], 8 * mis);
-    }
-    const uint32_t done = head + (nw << 2);
-    for (uint32_t i = done + lane; i < len; i += N_LANES) dst[i] = src[i];
-}
-// (Not inlined, like lanes_copy: inlined at every call site the byte movers were a quarter of a 148 KB kernel whose
-// instruction-cache hit rate was 84 %.  Halving the code -- this and the re-rolled exit-table sweep -- turned out not to
-// change the kernel's speed, measured; it is kept for the smaller binary and because the kernel no longer spills.)
-// Up to kSmallElem (64) bytes by one thread.  Word path: every load is issued before the first store, so the
-// loads overlap instead of each waiting behind the store before it (the compiler must assume they alias).
-constexpr uint32_t kSmallElem = 64;
-constexpr uint32_t kThreadElem = 128;  // literals up to this long are also moved by one thread (their source is shared memory)
-constexpr uint32_t kStageWords = 8;  // words held in registers at a time (two passes cover 64 bytes)
-__device__ __noinline__ void small_copy(uint8_t *d, const uint8_t *s, uint32_t len)
-{
-    if ((((uintptr_t)d | (uintptr_t)s | len) & 3) == 0) {
-        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s);
-        uint32_t *d32 = reinterpret_cast<uint32_t *>(d);
-        const uint32_t nw = len >> 2;
-#pragma unroll 1
-        for (uint32_t b = 0; b < nw; b += kStageWords) {
-            uint32_t v[kStageWords];
-#pragma unroll
-            for (uint32_t k = 0; k < kStageWords; k++)
-                if (b + k < nw) v[k] = s32[b + k];
-#pragma unroll
-            for (uint32_t k = 0; k < kStageWords; k++)
-                if (b + k < nw) d32[b + k] = v[k];
-        }
-    } else if ((((uintptr_t)d | len) & 3) == 0) {
-        // destination aligned, source not: each word from two aligned source words
-        const uint32_t mis = (uint32_t)((uintptr_t)s & 3);
-        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s - mis);
-        uint32_t *d32 = reinterpret_cast<uint32_t *>(d);
-        const uint32_t nw = len >> 2;
-        // the word after the last whole source word may hold only bytes before the element's end: bytewise
-        uint32_t last = 0;
-        for (uint32_t q = 0; q < mis; q++) last |= (uint32_t)s[len - mis + q] << (8 * q);
-#pragma unroll 1
-        for (uint32_t b = 0; b < nw; b += kStageWords) {
-            uint32_t v[kStageWords + 1];
-#pragma unroll
-            for (uint32_t k = 0; k <= kStageWords; k++)
-                v[k] = b + k < nw ? s32[b + k] : last;
-#pragma unroll
-            for (uint32_t k = 0; k < kStageWords; k++)
-                if (b + k < nw) d32[b + k] = __funnelshift_r(v[k], v[k + 1], 8 * mis);
-        }
-    } else {
-        // any alignment (every stream a byte-granular encoder such as Google's produces): 32 bytes per pass; all
-        // source bytes are fetched first -- whole aligned words, plus single bytes for the two words that stick out
-        // at the ends -- then written; a byte-by-byte copy would wait for each load behind the store before it
-#pragma unroll 1
-        for (uint32_t base = 0; base < len; base += 32) {
-            const uint32_t n = len - base < 32u ? len - base : 32u;
-            const uint8_t *sp = s + base;
-            const uint32_t mis = (uint32_t)((uintptr_t)sp & 3);
-            const uint32_t *s32 = reinterpret_cast<const uint32_t *>(sp - mis);
-            const uint32_t nwords = (mis + n + 3) >> 2;           // aligned words touched, <= 9
-            uint32_t v[10];
-#pragma unroll
-            for (uint32_t k = 0; k < 9; k++) {
-                v[k] = 0;
-                if (k < nwords) {
-                    const bool inner = (k > 0 || mis == 0) && (4 * (k + 1) <= mis + n);  // every byte of the word is wanted
-                    if (inner) {
-                        v[k] = s32[k];
-                    } else {
-#pragma unroll
-                        for (uint32_t q = 0; q < 4; q++) {
-                            const uint32_t pos = 4 * k + q;  // byte position relative to the aligned base
-                            if (pos >= mis && pos < mis + n) v[k] |= (uint32_t)sp[pos - mis] << (8 * q);
-                        }
-                    }
-                }
-            }
-            v[9] = 0;
-            uint32_t u[8];
-#pragma unroll
-            for (uint32_t k = 0; k < 8; k++) u[k] = __funnelshift_r(v[k], v[k + 1], 8 * mis);
-            uint8_t *dp = d + base;
-            if ((((uintptr_t)dp | n) & 3) == 0) {
-                uint32_t *d32 = reinterpret_cast<uint32_t *>(dp);
-#pragma unroll
-                for (uint32_t k = 0; k < 8; k++)
-                    if (4 * k < n) d32[k] = u[k];
-            } else {
-#pragma unroll
-                for (uint32_t i = 0; i < 32; i++)
-                    if (i < n) dp[i] = (uint8_t)(u[i >> 2] >> (8 * (i & 3)));
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ void group_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t glane) { lanes_copy<8>(dst, src, len, glane); }
-__device__ __forceinline__ void cta_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t t) { lanes_copy<kDecThreads>(dst, src, len, t); }
-
-// 16 aligned bytes at p, but only the bytes inside [lo, hi) are read (the others come back as zero)
-__device__ __forceinline__ uint4 load16_inside(const uint4 *p, uintptr_t lo, uintptr_t hi)
-{
-    const uintptr_t a = (uintptr_t)p;
-    if (a >= lo && a + 16 <= hi) return *p;
-    uint32_t w[4] = {0, 0, 0, 0};
-    const uint8_t *b = reinterpret_cast<const uint8_t *>(p);
-    for (int k = 0; k < 16; k++)
-        if (a + k >= lo && a + k < hi) w[k >> 2] |= (uint32_t)b[k] << (8 * (k & 3));
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-#ifdef HAPB200_EMU
-__device__ __forceinline__ void hap_prefetch_l2(const void *) {}
-#else
-__device__ __forceinline__ void hap_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#endif
-
-#ifdef HAPB200_DECODE_PHASE_CYCLES
-__device__ unsigned long long g_decode_phase_cycles[8];
-__device__ unsigned long long g_decode_counts[8];  // windows, elements, execute rounds, pending-after-round-1, flatten changes
-#define COUNT_ADD(i, v) do { if (t == 0) atomicAdd(&g_decode_counts[i], (unsigned long long)(v)); } while (0)
-#define PHASE_MARK(i) do { if (t == 0) { long long now_ = clock64(); atomicAdd(&g_decode_phase_cycles[i], (unsigned long long)(now_ - phase_t0_)); phase_t0_ = now_; } } while (0)
-#define PHASE_INIT long long phase_t0_ = clock64()
-#else
-#define PHASE_MARK(i) do { } while (0)
-#define PHASE_INIT do { } while (0)
-#define COUNT_ADD(i, v) do { } while (0)
-#endif
-
-__global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(ChunkJob *jobs, int njobs)
+__global__ void __launch_bounds__(kExThreads, 3) snappy_execute_kernel(ChunkJob *jobs, const DecWin *wins, DecodeCtl *ctl, uint32_t *done)
 {
     HAP_DYN_SMEM(smem_raw);
-    DecodeSmem &S = *reinterpret_cast<DecodeSmem *>(smem_raw);
+    ExecSmem &S = *reinterpret_cast<ExecSmem *>(smem_raw);
     const int t = threadIdx.x;
-    const uint32_t wrp = t >> 5;
-    if ((int)blockIdx.x >= njobs) return;
-    PHASE_INIT;
-    ChunkJob &job = jobs[blockIdx.x];
-    const uint8_t *__restrict__ src = job.src;
-    uint8_t *__restrict__ dst = job.dst;
-    const uint32_t in_end = job.src_bytes;
-    const uint32_t expected = job.dst_bytes;
-
-    if (job.compressor == 0) return;  // unused slot of a batched frame (hap_parse.cuh)
-    if (job.compressor == kHapChunkRaw) {
-        // hap.c:630-636: verbatim chunk
-        if (in_end != expected) {
-            if (t == 0) job.status = HapResult_Bad_Frame;
-            return;
-        }
-        const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
-        if (aligned) {
-            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-            uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-            uint32_t n4 = in_end >> 4;
-            for (uint32_t i = t; i < n4; i += kDecThreads) d4[i] = s4[i];
-            for (uint32_t i = (n4 << 4) + t; i < in_end; i += kDecThreads) dst[i] = src[i];
-        } else {
-            for (uint32_t i = t; i < in_end; i += kDecThreads) dst[i] = src[i];
-        }
-        if (t == 0) job.status = HapResult_No_Error;
-        return;
-    }
-    if (job.compressor != kHapChunkSnappy || in_end > kPosMask || expected > kPosMask) {
-        // hap.c:637-640; also chunks of 1 GiB and more, whose positions do not fit the packed descriptors
-        if (t == 0) job.status = HapResult_Bad_Frame;
-        return;
-    }
-
-    // ---- preamble: varint32 uncompressed length -----------------------------------------------
-    if (t == 0) {
-        uint64_t v = 0;
-        uint32_t i = 0;
-        bool ok = false;
-        for (; i < 5 && i < in_end; i++) {
-            uint32_t b = src[i];
-            v |= (uint64_t)(b & 0x7F) << (7 * i);
-            if (!(b & 0x80)) { ok = true; i++; break; }
-        }
-        S.fail = (!ok || v != (uint64_t)expected) ? 1 : 0;
-        S.fail_desc = 0;
-        S.bcast[0] = i;
-    }
+    const uint32_t nwin = ctl->n_windows;      // final: every kernel that appends windows ran before this one
+    if (t == 0) hap_mbar_init(&S.bar, 1);
+    uint32_t phase = 0;
     __syncthreads();
-    if (S.fail) {
-        if (t == 0) job.status = HapResult_Bad_Frame;
-        return;
-    }
-    uint32_t wb = S.bcast[0];  // window base: a true element start
-    uint32_t d0 = 0;           // output bytes produced by earlier windows
-    __syncthreads();
-
-    // Sub-blocks covered per window.  Dense streams (a few bytes per element, e.g. Google Snappy on DXT5) fill the
-    // descriptor arrays long before 256 sub-blocks are used; the span then shrinks so that no exit table is computed
-    // for bytes this window never reaches, and grows back when windows stop being cut short.
-    uint32_t span = kDecThreads;
-    while (wb < in_end) {
-        // ---- stage the window.  Chunks are byte-packed in a frame, so the chunk is rarely aligned: read aligned
-        //      16-byte words and shift them so that S.cin[0] is the byte at `wb` (word loads stay aligned later) ---
-        if (t == 0) { S.n_long = 0; S.n_mid = 0; S.mid_next = 0; }
-        uint32_t staged_end;  // input position up to which S.cin holds this window's bytes
-        {
-            const uintptr_t gaddr = (uintptr_t)(src + wb);
-            const uint32_t shift = (uint32_t)(gaddr & 15);           // uniform over the CTA
-            const uint32_t want = span * kDecSub + 16;
-            const uint32_t avail = in_end - wb < want ? in_end - wb : want;
-            staged_end = wb + avail;
-            const uint32_t n16 = (avail + 15) >> 4;
-            const uint4 *g4 = reinterpret_cast<const uint4 *>(gaddr - shift);
-            uint4 *s4 = reinterpret_cast<uint4 *>(S.cin);
-            const uint32_t ws = shift >> 2, bs = (shift & 3) * 8;
-            // aligned words are only read whole when every byte of them belongs to the chunk; the (at most two) words
-            // that stick out at the chunk's ends are gathered bytewise, so nothing outside [src, src + in_end) is touched
-            const uintptr_t c_lo = (uintptr_t)src, c_hi = (uintptr_t)src + in_end;
-            for (uint32_t i = t; i < n16; i += kDecThreads) {
-                const uint4 a = load16_inside(g4 + i, c_lo, c_hi);
-                uint4 b = make_uint4(0, 0, 0, 0);
-                if (shift != 0 && 16 * (i + 1) < shift + avail) b = load16_inside(g4 + i + 1, c_lo, c_hi);
-                uint32_t w0, w1, w2, w3, w4;
-                if (ws == 0) { w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; }
-                else if (ws == 1) { w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; }
-                else if (ws == 2) { w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; }
-                else { w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; }
-                s4[i] = make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs),
-                                   __funnelshift_r(w3, w4, bs));
-            }
-            // next window's lines on their way into L2 while this one is parsed and executed
-            const uint64_t pf = (uint64_t)wb + kDecWin + (uint64_t)t * 128;
-            if (pf < in_end) hap_prefetch_l2(src + pf);
-        }
-        const uint8_t *cinp = S.cin;
-        S.entry[t] = 0xFFFFu;
+    for (;;) {
+        if (t == 0) S.ticket = atomicAdd(&ctl->ticket, 1u);
         __syncthreads();
+        const uint32_t w = S.ticket;
+        if (w >= nwin) break;
+        if (t < (int)(sizeof(DecWin) / 4)) reinterpret_cast<uint32_t *>(&S.win)[t] = reinterpret_cast<const uint32_t *>(&wins[w])[t];
+        if (t == 0) { S.fail = 0; S.fail_desc = 0; S.mismatch = 0; S.min_src = 0xFFFFFFFFu; }
+        S.landed[t] = 0;
+        __syncthreads();
+        const DecWin win = S.win;
+        if (win.kind == kWinSkip) {
+            if (t == 0) hap_st_release(&done[w], 1u);
+            continue;
+        }
+        ChunkJob &job = jobs[win.job];
+        const uint8_t *__restrict__ src = job.src;
+        uint8_t *__restrict__ dst = job.dst;
+        const uint32_t in_end = job.src_bytes, expected = job.dst_bytes;
+        if (win.kind == kWinRaw) {
+            const uint8_t *s = src + win.in_off;
+            uint8_t *d = dst + win.out_off;
+            if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(s);
+                uint4 *d4 = reinterpret_cast<uint4 *>(d);
+                const uint32_t n4 = win.in_len >> 4;
+                for (uint32_t i = t; i < n4; i += kExThreads) d4[i] = s4[i];
+                for (uint32_t i = (n4 << 4) + t; i < win.in_len; i += kExThreads) d[i] = s[i];
+            } else {
+                for (uint32_t i = t; i < win.in_len; i += kExThreads) d[i] = s[i];
+            }
+            continue;   // nobody waits for a verbatim window
+        }
+        const bool embedded = win.first == kNoDeps;     // entries come from the frame: nothing in them is trusted
+        const uint32_t sub = 1u << win.sub_log2;
+        const uint32_t nsub_all = (win.in_len + sub - 1) >> win.sub_log2;
+        const uint32_t nsub = nsub_all < (uint32_t)kExThreads ? nsub_all : (uint32_t)kExThreads;   // the last thread walks to the window's end
+        const bool fits = win.in_len <= (uint32_t)kExMaxIn && win.in_off <= in_end && win.in_len <= in_end - win.in_off &&
+                          win.out_off <= expected && win.out_len <= expected - win.out_off;
+        if (!fits) {   // (uniform: every thread computed it from the same window and chunk records)
+            if (t == 0) { job.status = embedded ? kStatusIndexMismatch : (uint32_t)HapResult_Bad_Frame; __threadfence(); hap_st_release(&done[w], 1u); }
+            continue;
+        }
+        // ---- stage the window (TMA bulk copy), read the entries meanwhile ---------------------------------------------
+        uint32_t ent = kIndexNoEntry;
+        const uint32_t staged = in_end - win.in_off < win.in_len + (uint32_t)kExLook ? in_end - win.in_off : win.in_len + (uint32_t)kExLook;
+        stage_bytes(S.cin, src + win.in_off, staged, &S.bar, t);
+        if ((uint32_t)t < nsub) ent = win.entries[t];
+        if (embedded && (uint32_t)t + kExThreads < nsub_all && win.entries[t + kExThreads] != kIndexNoEntry) S.mismatch = 1;  // no starts beyond piece 255
+        hap_mbar_wait(&S.bar, phase);
+        phase ^= 1;
+        __syncthreads();
+        const uint32_t a_sh = (uint32_t)((uintptr_t)(src + win.in_off) & 15);
+        const uint8_t *cin = S.cin + a_sh;
+        const uint32_t wb = win.in_off;
 
-        PHASE_MARK(0);
-        // ---- 1. parse.  (a) every thread: for EACH of the 64 offsets of its sub-block, where does an element
-        //      chain entering there leave the sub-block?  One backward sweep: x[o] = x[o + length(o)].
-        //      (b) one thread hops sub-block to sub-block along the true chain using that table.
-        //      (c) every sub-block the chain enters is walked once from its true entry. ------------------
-        // threads beyond the span own nothing in this window
-        const uint32_t blk_start = (uint32_t)t < span && (uint64_t)wb + (uint64_t)t * kDecSub < in_end ? wb + t * kDecSub : in_end;
-        const uint32_t blk_end = (uint32_t)t < span && (uint64_t)wb + (uint64_t)(t + 1) * kDecSub < in_end ? wb + (t + 1) * kDecSub : in_end;
-        if (blk_start < in_end) {
-            // the sub-block's 64 bytes (+ 4 bytes of header look-ahead) live in registers: the sweep is fully
-            // unrolled, so every tag byte is a compile-time extraction and only the table access touches memory
-            const uint32_t blk_len = blk_end - blk_start;
-            const uint32_t limit = in_end - blk_start;  // a chain position may not pass this
-            // The sweep runs over four groups of 16 offsets, highest first; a group's 16 bytes (+ 5 bytes of header
-            // look-ahead) are re-loaded from the staged window into registers, inside the group every tag byte is a
-            // compile-time extraction.  (Fully unrolled over all 64 offsets this was a third of the kernel's code.)
-            const uint32_t *c32 = reinterpret_cast<const uint32_t *>(S.cin + (size_t)t * kDecSub);
-#pragma unroll 1
-            for (int g = kDecSub / 16 - 1; g >= 0; g--) {
-                uint32_t w[6];
-#pragma unroll
-                for (int k = 0; k < 6; k++) w[k] = c32[4 * g + k];
-#pragma unroll
-                for (int oo = 15; oo >= 0; oo--) {
-                    const uint32_t o = (uint32_t)(16 * g + oo);
-                    const uint32_t tag = (w[oo >> 2] >> (8 * (oo & 3))) & 0xFFu;
-                    const uint32_t kind = tag & 3u;
-                    uint64_t nxt;
-                    if (kind != 0) {
-                        nxt = o + ((0x5320u >> (4 * kind)) & 0xFu);  // copy headers: 2, 3 or 5 bytes
-                    } else {
-                        const uint32_t m = tag >> 2;
-                        if (m < 60) {
-                            nxt = o + m + 2;                           // tag + (m+1) literal bytes
-                        } else {
-                            // the 4 bytes after the tag, assembled from registers
-                            const uint32_t lo_w = w[(oo + 1) >> 2], hi_w = w[((oo + 1) >> 2) + 1];
-                            nxt = long_literal_next(o, m, __funnelshift_r(lo_w, hi_w, 8 * ((oo + 1) & 3)));
-                        }
-                    }
-                    uint32_t x;
-                    if (nxt > limit) x = kExitInvalid;               // header or payload runs past the input
-                    else if (nxt < blk_len) x = S.tbl[(uint32_t)nxt * kDecThreads + t];
-                    else x = nxt - blk_len <= kExitMaxRel ? (uint32_t)(nxt - blk_len) : kExitFarBase + o;
-                    S.tbl[o * kDecThreads + t] = (uint8_t)x;
+        // ---- walk: every entered piece from its entry to its end ---------------------------------------------------------------
+        const uint32_t my_lo = (uint32_t)t * sub;
+        const uint32_t my_hi = ((uint32_t)t + 1 == nsub) ? win.in_len : ((uint32_t)t + 1) * sub;
+        const bool entered = (uint32_t)t < nsub && ent != kIndexNoEntry;
+        WalkResult wr;
+        wr.exit = 0; wr.count = 0; wr.out_bytes = 0; wr.invalid = 0;
+        if (entered) {
+            if (my_lo + ent >= my_hi) {
+                wr.invalid = 1;
+            } else {
+                wr = walk_piece(cin, wb, my_lo + ent, my_hi, in_end);
+                // an element that starts in the window may END beyond it (its payload belongs to the next window of an
+                // on-the-fly index); a fragment of an embedded index is self-contained
+                if (!wr.invalid && wr.exit < win.in_len) {
+                    uint32_t b = wr.exit >> win.sub_log2;
+                    b = b < (uint32_t)kExThreads ? b : (uint32_t)kExThreads - 1;
+                    S.landed[b] = 1;
                 }
+                if (embedded && wr.exit > win.in_len) wr.invalid = 1;
             }
         }
-        __syncthreads();
-        PHASE_MARK(5);
-        if (t == 0) {
-            // window-relative positions: the dependent chain per hop is one table load plus a few ALU ops
-            const uint32_t rel_end = in_end - wb;
-            uint32_t rel = 0;
-            // The table's shared-window address, read back through a volatile word: ptxas otherwise re-derives it from
-            // the CTA-in-cluster id (an S2R, tens of cycles on this thread's critical path) in EVERY iteration of the hop.
-            volatile hap_saddr_t *base_box = reinterpret_cast<volatile hap_saddr_t *>(&S.saddr_box);
-            *base_box = hap_smem_addr(S.tbl);
-            const hap_saddr_t tbl_s = *base_box, entry_s = tbl_s + (hap_saddr_t)((const uint8_t *)S.entry - (const uint8_t *)S.tbl);
-            while (rel < rel_end && rel < span * kDecSub) {
-                const uint32_t blk = rel >> 6, o = rel & 63;
-                const uint32_t x = hap_lds_u8(tbl_s + (o * kDecThreads + blk));
-                hap_sts_u16(entry_s + 2 * blk, o);
-                uint32_t bend = (blk + 1) << 6;
-                bend = bend < rel_end ? bend : rel_end;
-                if (x <= kExitMaxRel) {
-                    rel = bend + x;
-                } else if (x == kExitInvalid) {
-                    S.fail = 1;
-                    break;
-                } else {
-                    // a long literal leaves this sub-block by more than a byte can hold: the table names its header
-                    const uint32_t p2 = wb + (blk << 6) + (x - kExitFarBase);
-                    uint32_t len, aux, hdr, kind;
-                    if (!read_element_header(cinp, wb, p2, in_end, len, aux, hdr, kind) || kind != 0) { S.fail = 1; break; }
-                    rel = p2 + hdr + len - wb;
-                }
-            }
-        }
-        __syncthreads();
-        PHASE_MARK(6);
-        uint32_t entry = blk_end;
-        WalkResult w;
-        w.exit = 0; w.count = 0; w.out_bytes = 0; w.invalid = 0;
-        if (S.entry[t] != 0xFFFFu && blk_start < in_end) {
-            entry = blk_start + S.entry[t];
-            w = walk_subblock(cinp, wb, entry, blk_end, in_end);
-        }
-
-        PHASE_MARK(1);
-        // ---- 2. scans: element slots and output offsets; window truncation -------------------
+        if (wr.invalid) S.fail = 1;
         uint32_t total_e, total_o;
-        uint32_t ebase = block_excl_sum<kDecThreads>(w.count, &total_e, S.scratch);
-        const uint32_t total_e_all = total_e;
-        const bool keep = ebase + w.count <= (uint32_t)kDecMaxElems;
-        uint32_t kept_cnt = keep ? w.count : 0;
-        uint32_t kept_out = keep ? w.out_bytes : 0;
-        uint32_t obase = block_excl_sum<kDecThreads>(kept_out, &total_o, S.scratch);
-        if (total_e > (uint32_t)kDecMaxElems) block_excl_sum<kDecThreads>(kept_cnt, &total_e, S.scratch);
-        uint32_t next_wb;
-        block_excl_max<kDecThreads>(keep ? w.exit : 0, &next_wb, S.scratch);
-        // a kept sub-block whose chain is invalid poisons the stream (it is the true chain now)
-        if (keep && w.invalid) S.fail = 1;
-        if (t == 0 && (uint64_t)d0 + total_o > expected) S.fail = 1;
+        const uint32_t ebase = block_excl_sum<kExThreads>(wr.count, &total_e, S.scratch);
+        const uint32_t obase = block_excl_sum<kExThreads>(wr.out_bytes > 0x40000000u ? 0x40000000u : wr.out_bytes, &total_o, S.scratch);
+        if (embedded) {
+            // the entries must describe exactly the chain that starts at byte 0 of the fragment: a piece is entered if and
+            // only if an exit lands in it (piece 0: the fragment's first element), at the entry's very offset
+            const bool should = (uint32_t)t < nsub && (t == 0 || S.landed[t]);
+            if (should != entered) S.mismatch = 1;
+            if (t == 0 && (!entered || ent != 0)) S.mismatch = 1;
+            if (entered && !wr.invalid && wr.exit < win.in_len) {
+                uint32_t b = wr.exit >> win.sub_log2;
+                b = b < (uint32_t)kExThreads ? b : (uint32_t)kExThreads - 1;
+                if (b * sub + win.entries[b] != wr.exit) S.mismatch = 1;
+            }
+        }
+        if (t == 0 && total_o != win.out_len) S.fail = 1;
         __syncthreads();
-        if (S.fail) break;
-        {
-            const uint32_t used_sub = (next_wb - wb + kDecSub - 1) / kDecSub;   // uniform: both come from block-wide scans
-            if (total_e_all > (uint32_t)kDecMaxElems) span = used_sub + used_sub / 4 < 16u ? 16u : (used_sub + used_sub / 4 > (uint32_t)kDecThreads ? (uint32_t)kDecThreads : used_sub + used_sub / 4);
-            else if (total_e_all < (uint32_t)kDecMaxElems / 2) span = span * 2 > (uint32_t)kDecThreads ? (uint32_t)kDecThreads : span * 2;
+        if (S.fail || S.mismatch) {
+            if (t == 0) { job.status = embedded ? kStatusIndexMismatch : (uint32_t)HapResult_Bad_Frame; __threadfence(); hap_st_release(&done[w], 1u); }
+            continue;
         }
 
-        PHASE_MARK(2);
-        // ---- descriptors.  e_a packs the SOURCE of an element as (kind << 30) | position:
-        //      kSrcIn  : bytes of the compressed input at `position` (literals, and copies flattened onto them)
-        //      kSrcOut : bytes of the output at `position` (plain copies; offset >= length)
-        //      kSrcRun : periodic fill with period `position` (= the offset) of the e_b[e] - offset .. e_b[e] bytes
-        if (keep && entry < blk_end) {
-            uint32_t pos = entry, e = ebase, o = d0 + obase;
-            while (pos < blk_end) {
-                uint32_t len, aux, hdr, kind;
-                read_element_header(cinp, wb, pos, in_end, len, aux, hdr, kind);
-                S.e_dst[e] = o;
-                S.e_len[e] = len;
-                S.e_done[e] = 0;
-                if (kind == 0) {
-                    S.e_a[e] = kSrcIn | aux;
-                    S.e_b[e] = 0;  // literals break same-offset runs (a copy's offset is never 0)
-                    if (len >= kLongLiteral) {
-                        uint32_t q = atomicAdd(&S.n_long, 1u);
-                        if (q < (uint32_t)kMaxLong) S.long_list[q] = e;
-                    } else if (len > kThreadElem) {
-                        const uint32_t np = (len + kMidPiece - 1) / kMidPiece;
-                        const uint32_t q = atomicAdd(&S.n_mid, np);
-                        for (uint32_t pc = 0; pc < np; pc++)
-                            if (q + pc < (uint32_t)kMaxMid) S.mid_list[q + pc] = (uint16_t)(e | (pc << 11));
+        // ---- passes: as many pieces as the descriptor arrays hold -------------------------------------------------------------
+        uint32_t pbase_e = 0;
+        bool waited = embedded;     // windows of an on-the-fly index wait once for the earlier windows their copies read
+        bool bad = false;
+        while (pbase_e < total_e) {
+            bool keep;
+            uint32_t next_e, P0, P1;
+            if (total_e <= (uint32_t)kExMaxElems) {
+                keep = entered;
+                next_e = total_e;
+                P0 = win.out_off;
+                P1 = win.out_off + total_o;
+            } else {
+                const bool cand = entered && ebase >= pbase_e;
+                keep = cand && ebase + wr.count - pbase_e <= (uint32_t)kExMaxElems;
+                uint32_t m_next = cand && !keep ? ebase : 0xFFFFFFFFu;
+                uint32_t m_p0 = keep ? obase : 0xFFFFFFFFu;
+                uint32_t m_p1 = keep ? obase + wr.out_bytes : 0u;
+                block_min_min_max(m_next, m_p0, m_p1, S.red);
+                next_e = m_next == 0xFFFFFFFFu ? total_e : m_next;
+                P0 = win.out_off + m_p0;
+                P1 = win.out_off + m_p1;
+            }
+            const uint32_t pass_e = next_e - pbase_e;
+
+            // ---- descriptors.  e_a packs the SOURCE of an element as (kind << 30) | position:
+            //      kSrcIn  : bytes of the compressed input at `position` (literals, and copies flattened onto them)
+            //      kSrcOut : bytes of the output at `position` (plain copies; offset >= length)
+            //      kSrcRun : periodic fill with period `position` (= the offset) of the e_b[e] - offset .. e_b[e] bytes
+            if (keep) {
+                uint32_t pos = my_lo + ent, e = ebase - pbase_e, o = win.out_off + obase, msrc = 0xFFFFFFFFu;
+                while (pos < my_hi) {
+                    uint32_t len, aux, hdr, kind;
+                    read_element_header(cin + pos, wb + pos, in_end, len, aux, hdr, kind);
+                    S.e_dst[e] = o;
+                    S.e_len[e] = len;
+                    if (kind == 0) {
+                        S.e_a[e] = kSrcIn | aux;
+                        S.e_b[e] = 0;  // literals break same-offset runs (a copy's offset is never 0)
+                        pos += hdr + len;
+                    } else {
+                        if (aux == 0 || aux > o) S.fail_desc = 1;  // offset 0 or before the start of the output
+                        else if (o - aux < msrc) msrc = o - aux;
+                        S.e_a[e] = aux >= len ? (kSrcOut | (o - aux)) : (kSrcRun | aux);
+                        S.e_b[e] = aux;  // the offset, for run detection below; becomes the run base afterwards
+                        pos += hdr;
                     }
-                    pos += hdr + len;
-                } else {
-                    if (aux == 0 || aux > o) S.fail_desc = 1;  // offset 0 or before the start of the output
-                    S.e_a[e] = aux >= len ? (kSrcOut | (o - aux)) : (kSrcRun | aux);
-                    S.e_b[e] = aux;  // the offset, for run detection below; becomes the run base afterwards
-                    pos += hdr;
+                    o += len;
+                    e++;
                 }
-                o += len;
-                e++;
+                if (!waited && msrc < win.out_off) atomicMin(&S.min_src, msrc);
             }
-        }
-        __syncthreads();
-        if (S.fail_desc) break;
+            __syncthreads();
+            if (S.fail_desc) { bad = true; break; }
 
-        // ---- same-offset runs: a copy with the offset of the copy right before it continues that copy's
-        //      match, so it is a periodic fill of the run head's base period, independent of its neighbours --
-        {
-            const uint32_t strip = (total_e + kDecThreads - 1) / kDecThreads;
-            const uint32_t lo = t * strip < total_e ? t * strip : total_e;
-            const uint32_t hi = lo + strip < total_e ? lo + strip : total_e;
-            // Pass 1: flag continuations in the spare top bit of e_len (copies are at most 64 long) and find
-            // the last run head of the strip.
-            uint32_t last_head = 0;  // index + 1
-            for (uint32_t e = lo; e < hi; e++) {
-                const uint32_t off = S.e_b[e];
-                const bool cont = e > 0 && off != 0 && off == S.e_b[e - 1];
-                if (cont) S.e_len[e] |= 0x80000000u;
-                else last_head = e + 1;
-            }
-            uint32_t unused;
-            uint32_t head = block_excl_max<kDecThreads>(last_head, &unused, S.scratch);  // ends with a barrier
-            // Pass 2: e_b becomes the base (destination of the run head); continuations become periodic fills.
-            for (uint32_t e = lo; e < hi; e++) {
-                const uint32_t off = S.e_b[e];
-                if (S.e_len[e] & 0x80000000u) {
-                    S.e_len[e] &= 0x7FFFFFFFu;
-                    S.e_a[e] = kSrcRun | off;
-                    S.e_b[e] = S.e_dst[head - 1];
-                } else {
-                    head = e + 1;
-                    S.e_b[e] = S.e_dst[e];
+            // ---- same-offset runs: a copy with the offset of the copy right before it continues that copy's
+            //      match, so it is a periodic fill of the run head's base period, independent of its neighbours --
+            {
+                const uint32_t strip = (pass_e + kExThreads - 1) / kExThreads;
+                const uint32_t lo = t * strip < pass_e ? t * strip : pass_e;
+                const uint32_t hi = lo + strip < pass_e ? lo + strip : pass_e;
+                // Pass 1: flag continuations in the spare top bit of e_len (copies are at most 64 long) and find
+                // the last run head of the strip.
+                uint32_t last_head = 0;  // index + 1
+                for (uint32_t e = lo; e < hi; e++) {
+                    const uint32_t off = S.e_b[e];
+                    const bool cont = e > 0 && off != 0 && off == S.e_b[e - 1];
+                    if (cont) S.e_len[e] |= 0x80000000u;
+                    else last_head = e + 1;
+                }
+                uint32_t unused;
+                uint32_t head = block_excl_max<kExThreads>(last_head, &unused, S.scratch);  // ends with a barrier
+                // Pass 2: e_b becomes the base (destination of the run head); continuations become periodic fills.
+                for (uint32_t e = lo; e < hi; e++) {
+                    const uint32_t off = S.e_b[e];
+                    if (S.e_len[e] & 0x80000000u) {
+                        S.e_len[e] &= 0x7FFFFFFFu;
+                        S.e_a[e] = kSrcRun | off;
+                        S.e_b[e] = S.e_dst[head - 1];
+                    } else {
+                        head = e + 1;
+                        S.e_b[e] = S.e_dst[e];
+                    }
                 }
             }
-        }
-        __syncthreads();
+            __syncthreads();
 
-        PHASE_MARK(3);
-        // ---- flatten copy-of-copy chains.  DXT payloads are full of "same as the previous block except a few
-        //      bytes": a copy whose source is itself a copy, hundreds deep.  A plain copy whose source bytes lie
-        //      inside ONE earlier element of this window takes over that element's source (pointer jumping on
-        //      the packed e_a words; a racing update only makes the hop longer, never wrong).  Chains end at
-        //      literals (-> read the input instead) or at earlier windows (-> already written). --------------
-#pragma unroll 1
-        for (int fr = 0; fr < kFlattenRounds; fr++) {
-            for (uint32_t e = t; e < total_e; e += kDecThreads) {
+            // ---- flatten copy-of-copy chains.  DXT payloads are full of "same as the previous block except a few
+            //      bytes": a copy whose source is itself a copy, hundreds deep.  A plain copy whose source bytes lie
+            //      inside ONE earlier element of this pass takes over that element's source (pointer jumping on
+            //      the packed e_a words; a racing update only makes the hop longer, never wrong).  Chains end at
+            //      literals (-> read the input instead) or before this pass (-> already written). --------------
+            for (uint32_t e = t; e < pass_e; e += kExThreads) {
                 uint32_t a = S.e_a[e];
                 if ((a & kSrcMask) != kSrcOut) continue;
                 const uint32_t len = S.e_len[e];
@@ -607,8 +833,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
 #pragma unroll 1
                 for (int hop = 0; hop < kFlattenHops; hop++) {
                     const uint32_t sp = a & kPosMask;
-                    if (sp + len <= d0) break;                 // reads finished output of earlier windows
-                    if (sp < d0) break;                        // straddles the window start: leave it
+                    if (sp < P0) break;                        // reads (at least partly) what earlier passes / windows wrote
                     uint32_t lo2 = 0, hi2 = e;                 // last element with e_dst <= sp (it is before e)
                     while (hi2 - lo2 > 1) {
                         const uint32_t m = (lo2 + hi2) >> 1;
@@ -625,175 +850,79 @@ __global__ void __launch_bounds__(kDecThreads, 3) snappy_decode_chunks_kernel(Ch
                 if (changed) S.e_a[e] = a;
             }
             __syncthreads();
-        }
 
-        PHASE_MARK(7);
-        // ---- 3. execute: round 1 = everything whose source is the input or earlier windows; later rounds =
-        //         copies whose producers finished in an earlier round.  Elements of at most 64 bytes (every copy,
-        //         most literals) are moved by ONE THREAD each, staged through registers so that all its loads are
-        //         in flight together; longer literals by a warp each; the longest by the whole CTA.
-        for (uint32_t round = 1;; round++) {
-            int pending = 0;
-            for (uint32_t e = t; e < total_e; e += kDecThreads) {
-                if (S.e_done[e] != 0) continue;
-                const uint32_t len = S.e_len[e];
-                if (len > kThreadElem) continue;                 // (copies are at most 64 bytes)
-                const uint32_t a = S.e_a[e], o = S.e_dst[e];
-                const uint32_t kind = a & kSrcMask, ap = a & kPosMask;
-                uint8_t *d = dst + o;
-                if (kind == kSrcIn) {
-                    const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= staged_end) ? cinp + (ap - wb) : src + ap;
-                    small_copy(d, sl, len);
-                    S.e_done[e] = (uint16_t)round;
-                    continue;
-                }
-                if (kind == kSrcOut) {
-                    // A plain copy.  Its source bytes either lie in earlier windows (final), or they are the output of
-                    // producers of this window.  It does not have to wait for those producers to RUN: a literal's
-                    // bytes are in the input, a resolved copy's bytes are wherever that copy reads them -- so the
-                    // source range is walked producer by producer and each piece is pulled from where it really is.
-                    // Only a piece whose producer is itself unresolved (or periodic) has to wait for a later round.
-                    bool ok = true;
-                    uint32_t x = ap;
-                    const uint32_t x_end = ap + len;
-                    if (x < d0) {
-                        const uint32_t n0 = x_end <= d0 ? len : d0 - x;
-                        small_copy(d, dst + x, n0);
-                        x += n0;
-                    }
-                    if (x < x_end) {
-                        uint32_t lo2 = 0, hi2 = e;  // last element with e_dst <= x; the producer is before e
-                        while (hi2 - lo2 > 1) {
-                            uint32_t m = (lo2 + hi2) >> 1;
-                            if (S.e_dst[m] <= x) lo2 = m; else hi2 = m;
+            // ---- earlier windows of the chunk this window's copies read (on-the-fly index only): wait for them once ----
+            if (!waited) {
+                waited = true;
+                if (t == 0 && S.min_src < win.out_off) {
+                    const uint32_t need = S.min_src;
+                    for (uint32_t j = w; j > win.first;) {
+                        j--;
+                        const uint32_t jo = wins[j].out_off, jl = wins[j].out_len;
+                        if (wins[j].kind == kWinSnappy) {
+                            uint32_t spins = 0;
+                            while (hap_ld_acquire(&done[j]) == 0) { if (++spins > 64) hap_nanosleep(200); }
                         }
-                        for (uint32_t f = lo2; x < x_end; f++) {
-                            const uint32_t fd = S.e_dst[f], fl = S.e_len[f];
-                            const uint32_t x1 = x_end < fd + fl ? x_end : fd + fl;
-                            const uint32_t fa = S.e_a[f], fk = fa & kSrcMask, fp = (fa & kPosMask) + (x - fd);
-                            const uint32_t df = S.e_done[f];
-                            const uint8_t *from;
-                            if (df != 0 && df < round) from = dst + x;                      // producer already ran
-                            else if (fk == kSrcIn) from = src + fp;                          // literal bytes: the input
-                            else if (fk == kSrcOut && fp + (x1 - x) <= d0) from = dst + fp;  // resolved copy: its source
-                            else { ok = false; break; }
-                            small_copy(d + (x - ap), from, x1 - x);
-                            x = x1;
-                        }
-                    }
-                    if (!ok) { pending = 1; continue; }
-                    S.e_done[e] = (uint16_t)round;
-                    continue;
-                }
-                const uint32_t base = S.e_b[e];
-                const uint32_t rel = o - base;  // position of this element inside its same-offset run
-                uint32_t need_lo, need_hi;      // bytes this element reads
-                if (rel + len <= ap) { need_lo = o - ap; need_hi = need_lo + len; }
-                else { need_lo = base - ap; need_hi = base; }
-                if (need_hi > d0) {
-                    bool ready = true;
-                    uint32_t x = need_lo > d0 ? need_lo : d0;
-                    uint32_t lo2 = 0, hi2 = e;  // last element with e_dst <= x; the producer is before e
-                    while (hi2 - lo2 > 1) {
-                        uint32_t m = (lo2 + hi2) >> 1;
-                        if (S.e_dst[m] <= x) lo2 = m; else hi2 = m;
-                    }
-                    for (uint32_t f = lo2; f < e && S.e_dst[f] < need_hi; f++) {
-                        uint32_t df = S.e_done[f];
-                        if (df == 0 || df >= round) { ready = false; break; }
-                    }
-                    if (!ready) { pending = 1; continue; }
-                }
-                if (rel + len <= ap) {
-                    small_copy(d, dst + (o - ap), len);
-                } else {
-                    const uint32_t off = ap;
-                    const uint8_t *period = dst + (base - off);
-                    if (((off | rel | len) & 3) == 0 && (((uintptr_t)d | (uintptr_t)period) & 3) == 0) {
-                        const uint32_t *p32 = reinterpret_cast<const uint32_t *>(period);
-                        uint32_t *d32 = reinterpret_cast<uint32_t *>(d);
-                        const uint32_t pw = off >> 2, nw = len >> 2;
-                        uint32_t idx = (rel >> 2) % pw;
-#pragma unroll 1
-                        for (uint32_t b = 0; b < nw; b += kStageWords) {
-                            uint32_t v[kStageWords];
-#pragma unroll
-                            for (uint32_t k = 0; k < kStageWords; k++)
-                                if (b + k < nw) { v[k] = p32[idx]; idx = idx + 1 == pw ? 0 : idx + 1; }
-#pragma unroll
-                            for (uint32_t k = 0; k < kStageWords; k++)
-                                if (b + k < nw) d32[b + k] = v[k];
-                        }
-                    } else {
-                        uint32_t idx = rel % off;
-                        for (uint32_t i = 0; i < len; i++) { d[i] = period[idx]; idx = idx + 1 == off ? 0 : idx + 1; }
+                        if (jo <= need || jo + jl <= need) break;   // this window starts at or before the earliest byte needed
                     }
                 }
-                S.e_done[e] = (uint16_t)round;
+                __syncthreads();
             }
-            if (round == 1) {
-                // literals of kThreadElem+1 .. kLongLiteral-1 bytes: one warp each, from the list the descriptor pass made
-                const uint32_t nmid = S.n_mid;
-                if (nmid <= (uint32_t)kMaxMid) {
-                    // pieces are handed out one at a time, so a warp that drew short ones simply draws more
-                    for (;;) {
-                        uint32_t q = 0;
-                        if ((t & 31) == 0) q = atomicAdd(&S.mid_next, 1u);
-                        q = __shfl_sync(HAP_FULL_MASK, q, 0);
-                        if (q >= nmid) break;
-                        const uint32_t item = S.mid_list[q];
-                        const uint32_t e = item & 2047u, off = (item >> 11) * kMidPiece;
-                        const uint32_t len = S.e_len[e];
-                        const uint32_t n = len - off < kMidPiece ? len - off : kMidPiece;
-                        const uint32_t ap = S.e_a[e] & kPosMask;  // only literals are this long
-                        const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= staged_end) ? cinp + (ap - wb) : src + ap;
-                        lanes_copy<32>(dst + S.e_dst[e] + off, sl + off, n, t & 31);
-                        if ((t & 31) == 0) S.e_done[e] = 1;   // honoured from round 2 on, when every piece is in place
-                    }
-                } else {
-                    // more of them than the list holds (cannot happen with 16 KiB of input per window, kept for safety)
-                    for (uint32_t e = wrp; e < total_e; e += kDecThreads / 32) {
-                        const uint32_t len = S.e_len[e];
-                        if (len <= kThreadElem || len >= kLongLiteral) continue;
-                        const uint32_t ap = S.e_a[e] & kPosMask;
-                        const uint8_t *sl = (ap >= wb && (uint64_t)ap + len <= staged_end) ? cinp + (ap - wb) : src + ap;
-                        lanes_copy<32>(dst + S.e_dst[e], sl, len, t & 31);
-                        if ((t & 31) == 0) S.e_done[e] = 1;
-                    }
-                }
-            }
-            if (round == 1) {
-                // long literals: the whole CTA moves each one
-                const uint32_t nlong = S.n_long < (uint32_t)kMaxLong ? S.n_long : (uint32_t)kMaxLong;
-                for (uint32_t q = 0; q < nlong; q++) {
-                    const uint32_t e = S.long_list[q];
-                    cta_copy(dst + S.e_dst[e], src + (S.e_a[e] & kPosMask), S.e_len[e], t);
-                    if (t == 0) S.e_done[e] = 1;
-                }
-                if (S.n_long > (uint32_t)kMaxLong) {
-                    // overflow of the list (pathological): sweep the descriptors instead
-                    for (uint32_t e = 0; e < total_e; e++)
-                        if ((S.e_a[e] & kSrcMask) == kSrcIn && S.e_len[e] >= kLongLiteral && S.e_done[e] == 0) {
-                            cta_copy(dst + S.e_dst[e], src + (S.e_a[e] & kPosMask), S.e_len[e], t);
-                            __syncthreads();
-                            if (t == 0) S.e_done[e] = 1;
-                        }
-                }
-            }
-            COUNT_ADD(2, 1);
-            if (!__syncthreads_or(pending)) break;
-        }
-        COUNT_ADD(0, 1);
-        COUNT_ADD(1, total_e);
-        PHASE_MARK(4);
 
-        d0 += total_o;
-        wb = next_wb;
+            // ---- execute, output-centric: tiles of 32 KiB, groups of 16 aligned bytes ---------------------------------------------
+            for (uint32_t T0 = P0; T0 < P1; T0 += kExTile) {
+                TileCtx C;
+                C.src = src; C.dst = dst; C.src_bytes = in_end; C.dst_bytes = expected;
+                C.cin = cin; C.wb = wb; C.staged = staged;
+                C.T0 = T0;
+                C.T1 = T0 + kExTile < P1 ? T0 + kExTile : P1;
+                const uint32_t shift = (uint32_t)((uintptr_t)(dst + T0) & 15);
+                C.gbase = (int32_t)T0 - (int32_t)shift;
+                const uint32_t ngroups = (uint32_t)((int32_t)C.T1 - C.gbase + 15) >> 4;
+                for (uint32_t g = t; g < ngroups; g += kExThreads) { S.gfirst[g] = 0; S.gdone[g] = 0; }
+                __syncthreads();
+                // the element that holds the first byte of each group: elements mark the first group whose first byte they hold ...
+                for (uint32_t e = t; e < pass_e; e += kExThreads) {
+                    const uint32_t d = S.e_dst[e], l = S.e_len[e];
+                    if (d + l <= C.T0 || d >= C.T1) continue;
+                    uint32_t gs = 0;
+                    if (d > C.T0) gs = (uint32_t)((int32_t)d - C.gbase + 15) >> 4;
+                    const int32_t first_byte = gs == 0 ? (int32_t)C.T0 : C.gbase + 16 * (int32_t)gs;
+                    if (gs < ngroups && first_byte < (int32_t)(d + l)) S.gfirst[gs] = (uint16_t)(e + 1);
+                }
+                __syncthreads();
+                // ... and a running maximum fills in the groups that lie inside one long element
+                {
+                    const uint32_t per = (ngroups + kExThreads - 1) / kExThreads;
+                    const uint32_t glo = t * per < ngroups ? t * per : ngroups, ghi = glo + per < ngroups ? glo + per : ngroups;
+                    uint32_t local = 0;
+                    for (uint32_t g = glo; g < ghi; g++) local = S.gfirst[g] > local ? S.gfirst[g] : local;
+                    uint32_t unused;
+                    uint32_t run = block_excl_max<kExThreads>(local, &unused, S.scratch);
+                    for (uint32_t g = glo; g < ghi; g++) {
+                        run = S.gfirst[g] > run ? S.gfirst[g] : run;
+                        S.gfirst[g] = (uint16_t)run;
+                    }
+                }
+                __syncthreads();
+                for (uint32_t round = 1;; round++) {
+                    int pending = 0;
+                    for (uint32_t g = t; g < ngroups; g += kExThreads)
+                        if (S.gdone[g] == 0 && !assemble_group(S, C, g, round)) pending = 1;
+                    if (round >= 65000u) { S.fail_desc = 1; pending = 0; }   // (a dependency chain deeper than any window has groups)
+                    if (!__syncthreads_or(pending)) break;
+                }
+            }
+            pbase_e = next_e;
+            __syncthreads();
+        }
         __syncthreads();
+        if (t == 0) {
+            if (bad || S.fail_desc) job.status = embedded ? kStatusIndexMismatch : (uint32_t)HapResult_Bad_Frame;
+            __threadfence();
+            hap_st_release(&done[w], 1u);
+        }
     }
-
-    __syncthreads();
-    if (t == 0) job.status = (S.fail || S.fail_desc || d0 != expected) ? HapResult_Bad_Frame : HapResult_No_Error;
 }
 
 }  // namespace hapb200

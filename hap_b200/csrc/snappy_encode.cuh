@@ -18,6 +18,7 @@
 // SURVEY.md 8c); parity is: the reference's HapDecode reproduces the input exactly.
 #pragma once
 #include "hap_codes.h"
+#include "hap_index.h"
 #include "simt.h"
 
 namespace hapb200 {
@@ -29,6 +30,9 @@ constexpr int kFragWords = kFragBytes / 4;
 constexpr int kFragCap = kFragBytes + 32;   // element stream of a fragment never exceeds n + 3
 constexpr int kEncHashBits = 13;
 constexpr uint32_t kFragStoredRaw = 0xFFFFFFFFu;  // fragment size marker: chunk must be stored raw
+constexpr int kFragEntryPieces = (kFragCap + (1 << kIndexSubLog2) - 1) >> kIndexSubLog2;   // 128-byte pieces of a fragment's stream (hap_index.h)
+constexpr int kFragEntryStride = 272;             // bytes reserved per fragment in the entries scratch (multiple of 16)
+static_assert(kFragEntryPieces <= kFragEntryStride, "entries of one fragment fit their scratch slot");
 
 // Shared memory of one fragment.  Thread t owns the 8 consecutive words [8t, 8t+8) and keeps them (and every
 // per-word quantity) in registers; shared memory only carries what OTHER threads read: the data (random
@@ -46,6 +50,7 @@ struct EncodeSmem {
     uint16_t da[kFragWords];                        // candidate distances (ping)
     uint16_t db[kFragWords];                        // candidate distances (pong); later: run end, stored at the run start
     uint32_t warp_tot[kEncWarps];
+    uint32_t entry[kFragEntryStride];               // fragment index: offset of the first element start in every 128 bytes of the stream
     uint32_t total;
     uint32_t out[(kFragCap + 3) / 4 + 2];           // the element stream
 };
@@ -271,6 +276,7 @@ __device__ __forceinline__ uint32_t compress_fragment(EncodeSmem &S, const uint3
             const uint32_t e = S.db[rs_i];   // last word of this literal run
             if (i == rs_i) {
                 const uint32_t len = 4u * (e - i + 1);
+                atomicMin(&S.entry[p >> kIndexSubLog2], p & ((1u << kIndexSubLog2) - 1u));   // an element starts here
                 if (len <= 60) {
                     out[p++] = (uint8_t)((len - 1) << 2);
                 } else if (len <= 256) {
@@ -299,6 +305,7 @@ __device__ __forceinline__ uint32_t compress_fragment(EncodeSmem &S, const uint3
             const uint32_t left = S.db[rs_i] - i + 1;          // words left in the run
             const uint32_t len = 4u * (left < 16 ? left : 16);  // 4..64 bytes
             const uint32_t off = 4u * dist;
+            atomicMin(&S.entry[p >> kIndexSubLog2], p & ((1u << kIndexSubLog2) - 1u));       // an element starts here
             out[p] = (uint8_t)(2u | ((len - 1) << 2));          // copy with 2-byte offset
             out[p + 1] = (uint8_t)off;
             out[p + 2] = (uint8_t)(off >> 8);
@@ -376,9 +383,10 @@ __device__ __forceinline__ void load_strip(const FragRef &fr, uint32_t i0, uint3
 // compressed, so the HBM latency of the input and the turn-over between CTAs -- both fully exposed with a single CTA
 // per SM -- are covered by a fragment's worth of work.
 // dxt: base pointer of the texture bytes; scratch: [nfrag][kFragCap]; frag_size: [nfrag] (kFragStoredRaw when the
-// fragment was not compressed).
+// fragment was not compressed); frag_entries: [nfrag][kFragEntryStride] or nullptr (fragment index, hap_index.h).
 __global__ void __launch_bounds__(kEncThreads) snappy_encode_fragments_kernel(
-    const uint8_t *__restrict__ dxt, FrameGeom G, uint32_t nfrag, uint8_t *__restrict__ scratch, uint32_t *__restrict__ frag_size)
+    const uint8_t *__restrict__ dxt, FrameGeom G, uint32_t nfrag, uint8_t *__restrict__ scratch, uint32_t *__restrict__ frag_size,
+    uint8_t *__restrict__ frag_entries)
 {
     HAP_DYN_SMEM(smem_raw);
     EncodeSmem &S = *reinterpret_cast<EncodeSmem *>(smem_raw);
@@ -408,6 +416,7 @@ __global__ void __launch_bounds__(kEncThreads) snappy_encode_fragments_kernel(
                 uint4 *tb = reinterpret_cast<uint4 *>(S.u.table);
                 const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
                 for (int q = t; q < (1 << kEncHashBits) / 4; q += kEncThreads) tb[q] = ones;
+                if (t < kFragEntryStride) S.entry[t] = kIndexNoEntry;
             }
             __syncthreads();
             const uint32_t period_words = (G.sections == 2 && (gfrag % G.frags_per_frame) >= G.s[1].frag_base) ? G.s[1].period_words : G.s[0].period_words;
@@ -417,6 +426,7 @@ __global__ void __launch_bounds__(kEncThreads) snappy_encode_fragments_kernel(
             const uint32_t *o32s = S.out;
             uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
             for (uint32_t i = t; i < (total + 3) / 4; i += kEncThreads) o32[i] = o32s[i];
+            if (frag_entries != nullptr && t < kFragEntryStride) frag_entries[(uint64_t)gfrag * kFragEntryStride + t] = (uint8_t)S.entry[t];
             if (t == 0) frag_size[gfrag] = total;
             __syncthreads();   // S.out, S.data and the tables are rewritten by the next fragment
         }

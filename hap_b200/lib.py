@@ -27,6 +27,8 @@ class HapB200(HapABI):
         vp, u, ul, ull_p, u_p = C.c_void_p, C.c_uint, C.c_ulong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint)
         L.HapB200Version.restype = C.c_char_p
         L.HapB200KernelLaunchCount.restype = C.c_ulonglong
+        L.HapB200SetOption.restype = C.c_int
+        L.HapB200SetOption.argtypes = [C.c_int, C.c_int]
         L.HapB200SetStageTiming.restype = None
         L.HapB200SetStageTiming.argtypes = [C.c_int]
         L.HapB200StageTimes.restype = C.c_int
@@ -58,16 +60,24 @@ class HapB200(HapABI):
     def launches(self) -> int:
         return int(self.lib.HapB200KernelLaunchCount())
 
-    STAGES = ("bc_encode", "snappy_encode", "plan", "place", "parse", "snappy_decode", "collect", "bc_decode")
+    OPTION_USE_INDEX, OPTION_WRITE_INDEX = 1, 2
+
+    def set_option(self, option: int, value: int) -> int:
+        """OPTION_USE_INDEX: the decoder uses a frame's embedded fragment index (default on).  OPTION_WRITE_INDEX: the
+        encoder adds the private fragment index section to Complex texture sections (default off: frames are laid out
+        exactly as the reference lays them out)."""
+        return int(self.lib.HapB200SetOption(option, value))
+
+    STAGES = ("bc_encode", "snappy_encode", "plan", "place", "parse", "snappy_decode", "collect", "bc_decode", "snappy_index", "windows")
 
     def set_stage_timing(self, on: bool):
         self.lib.HapB200SetStageTiming(1 if on else 0)
 
     def stage_times(self):
         """{stage: (total ms, launches)} since the last call; synchronises the device."""
-        ms = (C.c_double * 8)()
-        n = (C.c_ulonglong * 8)()
-        self.lib.HapB200StageTimes(ms, n, 8)
+        ms = (C.c_double * 10)()
+        n = (C.c_ulonglong * 10)()
+        self.lib.HapB200StageTimes(ms, n, 10)
         return {s: (float(ms[i]), int(n[i])) for i, s in enumerate(self.STAGES)}
 
     @staticmethod
@@ -80,7 +90,9 @@ class HapB200(HapABI):
             "plan": F * 4096.0,
             "place": 2 * F * mean_frame_bytes,                             # element streams read + frame written
             "parse": F * 256.0,
-            "snappy_decode": F * mean_frame_bytes + F * texture_bytes,     # frame read + texture written
+            "snappy_decode": F * mean_frame_bytes + F * texture_bytes,     # execute kernel: frame read + texture written
+            "snappy_index": F * mean_frame_bytes * (1.0 + 1.0 / 64),       # index kernel: frame read + one entry per 64 bytes written
+            "windows": F * 4096.0,
             "collect": F * 64.0,
             "bc_decode": F * (texture_bytes + rgba_bytes),
         }

@@ -29,9 +29,20 @@ enum HapB200Codec {
 const char *HapB200Version(void);
 /* kernels launched by this library in this process so far (bench.py reports the delta) */
 unsigned long long HapB200KernelLaunchCount(void);
+/* Options.  HAPB200_OPTION_USE_INDEX: the decoder uses a frame's embedded fragment index when it finds one (default 1;
+ * 0 = always derive the index from the Snappy streams, as for every frame another encoder wrote).
+ * HAPB200_OPTION_WRITE_INDEX: the encoder adds a private "fragment index" section to the Decode Instructions container
+ * of the texture sections it compresses (default 0: frames are laid out byte for byte as hap.c:430-442 lays them out).
+ * The section is skipped by the reference decoder (hap.c:701-704) and by FFmpeg; it lets this decoder start at every
+ * 32 KiB fragment without walking the chunk's element chain first (hap_b200/csrc/hap_index.h; ~1 % of the frame size).
+ * Returns 0, or -1 for an unknown option. */
+#define HAPB200_OPTION_USE_INDEX 1
+#define HAPB200_OPTION_WRITE_INDEX 2
+int HapB200SetOption(int option, int value);
+
 /* Per-stage device timing for profiling runs: when enabled every kernel launch is bracketed by CUDA
  * events on its own stream.  HapB200StageTimes synchronises, returns milliseconds and launch counts
- * per stage (bc_encode, snappy_encode, plan, place, parse, snappy_decode, collect, bc_decode) and
+ * per stage (bc_encode, snappy_encode, plan, place, parse, snappy_decode, collect, bc_decode, snappy_index, windows) and
  * resets them; its return value is the number of stages. */
 void HapB200SetStageTiming(int enabled);
 int HapB200StageTimes(double *ms, unsigned long long *launches, int n);

@@ -264,6 +264,20 @@ typedef uintptr_t hap_saddr_t;
 static inline hap_saddr_t hap_smem_addr(const void *p) { return (hap_saddr_t)p; }
 static inline uint32_t hap_lds_u8(hap_saddr_t a) { return *(const uint8_t *)a; }
 static inline void hap_sts_u16(hap_saddr_t a, uint32_t v) { *(uint16_t *)a = (uint16_t)v; }
+typedef unsigned long long hap_mbar_t;
+static inline void hap_mbar_init(hap_mbar_t *bar, uint32_t) { *bar = 0; }
+static inline void hap_mbar_expect_tx(hap_mbar_t *, uint32_t) {}
+static inline void hap_tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, hap_mbar_t *)
+{
+    // the real unit requires 16-byte alignment of both addresses and of the size: keep the emulated kernels honest
+    if (((uintptr_t)smem_dst | (uintptr_t)gmem_src | bytes) & 15) { fprintf(stderr, "emu: misaligned bulk copy\n"); abort(); }
+    memcpy(smem_dst, gmem_src, bytes);
+}
+static inline void hap_mbar_wait(hap_mbar_t *, uint32_t) {}
+static inline void hap_fence_proxy_async() {}
+static inline uint32_t hap_ld_acquire(const uint32_t *p) { return *p; }
+static inline void hap_st_release(uint32_t *p, uint32_t v) { *p = v; }
+static inline void hap_nanosleep(uint32_t) {}
 static inline void hap_bar_sync(int id, int n) { emu::bar_sync(id, n); }
 static inline void hap_bar_arrive(int id, int n) { emu::bar_arrive(id, n); }
 static inline int hap_bar_or(int id, int n, int pred) { return emu::bar_or(id, n, pred); }

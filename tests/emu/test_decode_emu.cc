@@ -3,6 +3,7 @@
 // oracle (oracle/snappy_oracle.c) on valid, pathological and corrupted streams.
 #define HAPB200_EMU
 #include "snappy_decode.cuh"
+#include "decode_emu.h"
 
 extern "C" {
 #include "snappy_oracle.h"
@@ -39,8 +40,11 @@ static void check_stream(const std::string &name, const std::vector<uint8_t> &st
     job.dst_bytes = (uint32_t)(pre == ORC_SNAPPY_OK ? want : 0);
     job.compressor = kHapChunkSnappy;
     job.status = 99;
+    job.index = nullptr;
+    job.index_bytes = 0;
+    job.mode = kJobUndecided;
     emu::g_order_mode() = mode;
-    HAP_LAUNCH(snappy_decode_chunks_kernel, dim3(1), dim3(kDecThreads), sizeof(DecodeSmem), nullptr, &job, 1);
+    decode_jobs_emu(&job, 1, stream.size(), job.dst_bytes, 1);
     bool ok = true;
     if (rs == ORC_SNAPPY_OK) {
         if (job.status != HapResult_No_Error) ok = false;
@@ -167,6 +171,7 @@ int main(int argc, char **argv)
     for (int dm = 0; dm < 4; dm++)
         for (int sm = 0; sm < 4; sm++)
             for (auto &c : cases) check_stream(c.first + "@d" + std::to_string(dm) + "s" + std::to_string(sm), c.second, 2, dm, sm);
+    g_fail += g_decode_emu_overflow;
     printf("%zu cases x %d modes, %d failures, %llu barriers\n", cases.size(), modes, g_fail,
            (unsigned long long)emu::g_barriers());
     return g_fail ? 1 : 0;

@@ -6,6 +6,7 @@
 #include "hap_assemble.cuh"
 #include "hap_host.h"
 #include "snappy_decode.cuh"
+#include "decode_emu.h"
 
 extern "C" {
 #include "bc_oracle.h"
@@ -26,7 +27,7 @@ static void serial_cb(orc_work_fn fn, void *p, unsigned n, void *) { for (unsign
 
 struct Tex { std::vector<uint8_t> data; unsigned fmt, compressor, chunks; };
 
-static std::vector<uint8_t> gpu_encode(const std::vector<Tex> &tex, int mode)
+static std::vector<uint8_t> gpu_encode(const std::vector<Tex> &tex, int mode, uint32_t write_index)
 {
     TextureArgs ta[2];
     for (size_t i = 0; i < tex.size(); i++) ta[i] = TextureArgs{tex[i].data.size(), tex[i].fmt, tex[i].compressor, tex[i].chunks};
@@ -42,25 +43,28 @@ static std::vector<uint8_t> gpu_encode(const std::vector<Tex> &tex, int mode)
     for (size_t i = 0; i < tex.size(); i++) { lens[i] = tex[i].data.size(); fmts[i] = tex[i].fmt; chunks[i] = tex[i].chunks; }
     cap = orc_HapMaxEncodedLength((unsigned)tex.size(), lens, fmts, chunks);
     std::vector<uint8_t> scratch((size_t)G.frags_per_frame * kFragCap), out(cap, 0xEE);
-    std::vector<uint32_t> fsize(G.frags_per_frame), fdst(G.frags_per_frame);
+    std::vector<uint32_t> fsize(G.frags_per_frame), fdst(G.frags_per_frame), fidx(G.frags_per_frame);
+    std::vector<uint8_t> fent((size_t)G.frags_per_frame * kFragEntryStride, 0xDD);
     unsigned long long used = 0;
     emu::g_order_mode() = mode;
     // a grid smaller than the fragment count, as on the device: CTAs stride over the fragments (modes alternate 1, 2, 3 CTAs)
     const unsigned k5_grid = G.frags_per_frame < (unsigned)(1 + mode % 3) ? G.frags_per_frame : (unsigned)(1 + mode % 3);
     HAP_LAUNCH(snappy_encode_fragments_kernel, dim3(k5_grid), dim3(kEncThreads), sizeof(EncodeSmem), nullptr,
-               in.data(), G, (uint32_t)G.frags_per_frame, scratch.data(), fsize.data());
-    HAP_LAUNCH(hap_plan_frames_kernel, dim3(1), dim3(kPlanThreads), 0, nullptr, G, in.data(), fsize.data(), fdst.data(),
-               out.data(), (uint64_t)cap, &used);
+               in.data(), G, (uint32_t)G.frags_per_frame, scratch.data(), fsize.data(), write_index ? fent.data() : (uint8_t *)nullptr);
+    HAP_LAUNCH(hap_plan_frames_kernel, dim3(1), dim3(kPlanThreads), 0, nullptr, G, in.data(), fsize.data(), fdst.data(), fidx.data(),
+               write_index, out.data(), (uint64_t)cap, &used);
     HAP_LAUNCH(hap_place_fragments_kernel, dim3(G.frags_per_frame), dim3(kPlaceThreads), 0, nullptr, G, in.data(),
-               scratch.data(), fsize.data(), fdst.data(), out.data(), (uint64_t)cap);
+               scratch.data(), fsize.data(), fdst.data(), fidx.data(), write_index ? fent.data() : (const uint8_t *)nullptr, out.data(),
+               (uint64_t)cap);
     if (used > cap) { fprintf(stderr, "used %llu > cap %lu\n", used, cap); abort(); }
     out.resize(used);
     return out;
 }
 
-static void check(const std::string &name, const std::vector<Tex> &tex, int mode, double *ratio = nullptr)
+static void check(const std::string &name, const std::vector<Tex> &tex, int mode, uint32_t write_index, double *ratio = nullptr)
 {
-    std::vector<uint8_t> frame = gpu_encode(tex, mode);
+    if (getenv("EMU_TRACE")) fprintf(stderr, "case %s\n", name.c_str());
+    std::vector<uint8_t> frame = gpu_encode(tex, mode, write_index);
     bool ok = true;
     std::string why;
     unsigned cnt = 0;
@@ -102,33 +106,66 @@ static void check(const std::string &name, const std::vector<Tex> &tex, int mode
             if (memcmp(back.data(), tex[i].data.data(), used) != 0) { ok = false; why = std::string(which ? "reference" : "oracle") + " payload mismatch"; break; }
         }
     }
-    // and through our own decode kernel (K7), jobs built with the host-side parser of the product
-    for (unsigned i = 0; i < tex.size() && ok; i++) {
-        Located loc;
-        if (locate_texture(frame.data(), (uint32_t)frame.size(), i, loc) != 0) { ok = false; why = "locate"; break; }
-        const uint8_t *sec = frame.data() + loc.offset;
-        std::vector<ChunkJob> jobs;
-        std::vector<uint8_t> back(tex[i].data.size() + 64, 0x99);
-        if (((loc.type >> 4) & 0xF) == kHapComplex) {
-            ChunkTables t; t.count = 0;
-            if (parse_decode_instructions(sec, loc.len, t) != 0) { ok = false; why = "parse DI"; break; }
-            uint64_t in_run = 0, out_run = 0;
-            for (int c = 0; c < t.count; c++) {
-                uint32_t cc = sec[t.compressors + c], sz = rd_le32(sec + t.sizes + 4 * c), usz = sz;
-                if (cc == kHapChunkSnappy && !snappy_preamble(sec + t.data + in_run, sz, usz)) { ok = false; why = "preamble"; break; }
-                jobs.push_back(ChunkJob{sec + t.data + in_run, back.data() + 32 + out_run, sz, usz, cc, 99});
-                in_run += sz; out_run += usz;
+    // and through our own decode kernels (K7), jobs built with the host-side parser of the product: with the embedded index
+    // (when the frame carries one), without it, and with a damaged index (the damaged chunks must be decoded again
+    // from their streams alone and still give the payload)
+    for (int variant = 0; variant < 3 && ok; variant++) {
+        std::vector<uint8_t> fr = frame;
+        for (unsigned i = 0; i < tex.size() && ok; i++) {
+            Located loc;
+            if (locate_texture(fr.data(), (uint32_t)fr.size(), i, loc) != 0) { ok = false; why = "locate"; break; }
+            uint8_t *sec = fr.data() + loc.offset;
+            std::vector<ChunkJob> jobs;
+            std::vector<uint8_t> back(tex[i].data.size() + 64, 0x99);
+            bool has_index = false;
+            uint64_t in_sum = 0;
+            if (((loc.type >> 4) & 0xF) == kHapComplex) {
+                ChunkTables t; t.count = 0;
+                if (parse_decode_instructions(sec, loc.len, t) != 0) { ok = false; why = "parse DI"; break; }
+                FragmentIndex ix;
+                const bool have_ix = locate_fragment_index(fr.data(), (uint32_t)fr.size(), ix);
+                const uint32_t tables = kIndexHeaderBytes + 4u * (have_ix ? ix.chunks[0] + ix.chunks[1] : 0u);
+                if (variant == 2 && have_ix && i == 0 && ix.len > tables + 8) {
+                    // damage a few bytes of the records (sizes or entries), never the header
+                    std::mt19937 r2(name.size() * 131 + mode);
+                    for (int q = 0; q < 3; q++) fr[ix.body + tables + r2() % (ix.len - tables)] ^= (uint8_t)(1u << (r2() % 8));
+                }
+                uint64_t in_run = 0, out_run = 0;
+                for (int c = 0; c < t.count; c++) {
+                    uint32_t cc = sec[t.compressors + c], sz = rd_le32(sec + t.sizes + 4 * c), usz = sz;
+                    if (cc == kHapChunkSnappy && !snappy_preamble(sec + t.data + in_run, sz, usz)) { ok = false; why = "preamble"; break; }
+                    ChunkJob j;
+                    j.src = sec + t.data + in_run; j.dst = back.data() + 32 + out_run; j.src_bytes = sz; j.dst_bytes = usz; j.compressor = cc;
+                    j.status = 99; j.index = nullptr; j.index_bytes = 0; j.mode = kJobUndecided;
+                    uint32_t ioff = 0, ib = 0;
+                    if (cc == kHapChunkSnappy && have_ix && fragment_index_record(fr.data(), ix, i, (uint32_t)t.count, (uint32_t)c, ioff, ib)) { j.index = fr.data() + ioff; j.index_bytes = ib; has_index = true; }
+                    jobs.push_back(j);
+                    in_run += sz; out_run += usz; in_sum += sz;
+                }
+                if (write_index && !has_index) {
+                    bool any_snappy = false;
+                    for (auto &j : jobs) any_snappy = any_snappy || j.compressor == kHapChunkSnappy;
+                    if (any_snappy) { ok = false; why = "index section missing"; break; }
+                }
+                if (!write_index && have_ix) { ok = false; why = "unexpected index section"; break; }
+            } else {
+                ChunkJob j;
+                j.src = sec; j.dst = back.data() + 32; j.src_bytes = loc.len; j.dst_bytes = loc.len; j.compressor = kHapChunkRaw;
+                j.status = 99; j.index = nullptr; j.index_bytes = 0; j.mode = kJobUndecided;
+                jobs.push_back(j);
+                in_sum = loc.len;
             }
-        } else {
-            jobs.push_back(ChunkJob{sec, back.data() + 32, loc.len, loc.len, kHapChunkRaw, 99});
+            if (!ok) break;
+            if (variant > 0 && !has_index) continue;   // nothing new to try
+            uint32_t wo[2] = {0, 0};
+            if (getenv("EMU_TRACE")) fprintf(stderr, "  decode variant %d texture %u jobs %zu has_index %d\n", variant, i, jobs.size(), (int)has_index);
+            decode_jobs_emu(jobs.data(), (uint32_t)jobs.size(), in_sum, tex[i].data.size(), variant == 1 ? 0u : 1u, 1 + mode % 3, wo);
+            size_t total = 0;
+            for (auto &j : jobs) { if (j.status != 0) { ok = false; why = "K7 status " + std::to_string(j.status) + " variant " + std::to_string(variant); } total += j.dst_bytes; }
+            if (ok && memcmp(back.data() + 32, tex[i].data.data(), total) != 0) { ok = false; why = "K7 payload mismatch, variant " + std::to_string(variant); }
+            for (int g = 0; g < 32 && ok; g++) if (back[g] != 0x99 || back[32 + total + g] != 0x99) { ok = false; why = "K7 wrote outside its chunk"; }
+            if (ok && variant == 0 && has_index && wo[1] != 0) { ok = false; why = "a sound embedded index was rejected"; }
         }
-        if (!ok) break;
-        HAP_LAUNCH(snappy_decode_chunks_kernel, dim3((unsigned)jobs.size()), dim3(kDecThreads), sizeof(DecodeSmem), nullptr,
-                   jobs.data(), (int)jobs.size());
-        size_t total = 0;
-        for (auto &j : jobs) { if (j.status != 0) { ok = false; why = "K7 status " + std::to_string(j.status); } total += j.dst_bytes; }
-        if (ok && memcmp(back.data() + 32, tex[i].data.data(), total) != 0) { ok = false; why = "K7 payload mismatch"; }
-        for (int g = 0; g < 32 && ok; g++) if (back[g] != 0x99 || back[32 + total + g] != 0x99) { ok = false; why = "K7 wrote outside its chunk"; }
     }
     if (!ok) { g_fail++; fprintf(stderr, "FAIL %s mode %d: %s (frame %zu bytes)\n", name.c_str(), mode, why.c_str(), frame.size()); }
 }
@@ -216,10 +253,12 @@ int main(int argc, char **argv)
     }
     for (int mode = 0; mode < modes; mode++)
         for (auto &c : cases) {
-            double ratio = 0;
-            check(c.name, c.tex, mode, &ratio);
-            if (mode == 0) printf("  %-26s size vs oracle-encoded frame: %.3f\n", c.name.c_str(), ratio);
+            double ratio = 0, ratio_i = 0;
+            check(c.name, c.tex, mode, 0, &ratio);
+            check(c.name + "+index", c.tex, mode, 1, &ratio_i);
+            if (mode == 0) printf("  %-26s size vs oracle-encoded frame: %.3f   with fragment index: %.3f\n", c.name.c_str(), ratio, ratio_i);
         }
+    g_fail += g_decode_emu_overflow;
     printf("%zu cases x %d modes, %d failures\n", cases.size(), modes, g_fail);
     return g_fail ? 1 : 0;
 }

@@ -21,8 +21,18 @@ def lib():
 @pytest.mark.parametrize("codec,cc,kind,chunks", [(L.HapB200Codec_Hap1, "Hap1", "bc1", 1), (L.HapB200Codec_Hap5, "Hap5", "bc3", 4),
                                                   (L.HapB200Codec_HapY, "HapY", "ycocg", 8), (L.HapB200Codec_HapM, "HapM", "ycocg", 4),
                                                   (L.HapB200Codec_HapA, "HapA", "bc4", 2)])
-def test_ffmpeg_decodes_gpu_encoded_movie(lib, tmp_path, codec, cc, kind, chunks):
+@pytest.mark.parametrize("with_index", [0, 1])
+def test_ffmpeg_decodes_gpu_encoded_movie(lib, tmp_path, codec, cc, kind, chunks, with_index):
+    """with_index = 1: the frames carry the trailing fragment index section (hap_index.h); FFmpeg must not mind."""
     cv2 = pytest.importorskip("cv2")
+    lib.set_option(lib.OPTION_WRITE_INDEX, with_index)
+    try:
+        _ffmpeg_decodes_gpu_encoded_movie(cv2, lib, tmp_path, codec, cc, kind, chunks)
+    finally:
+        lib.set_option(lib.OPTION_WRITE_INDEX, 0)
+
+
+def _ffmpeg_decodes_gpu_encoded_movie(cv2, lib, tmp_path, codec, cc, kind, chunks):
     w, h, n = 512, 256, 4
     path = str(tmp_path / f"{cc}.mov")
     imgs, frames = [], []

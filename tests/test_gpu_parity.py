@@ -369,3 +369,68 @@ def test_rgba_batch_texture_cannot_overrun_its_share_of_the_slot(lib):
     assert lib.decode_rgba_batch(one.data_ptr(), 1, cap, used1.data_ptr(), k, codec, w, h, alone.data_ptr(), w * h * 4, r1.data_ptr()) == 0
     assert r1.tolist() == [0] and torch.equal(rgba[1], alone[0])
     assert int(rgba[0].max()) == 0          # the refused frame's picture is zeros, not recycled scratch
+
+
+@pytest.fixture
+def index_on(lib):
+    lib.set_option(lib.OPTION_WRITE_INDEX, 1)
+    yield lib
+    lib.set_option(lib.OPTION_WRITE_INDEX, 0)
+    lib.set_option(lib.OPTION_USE_INDEX, 1)
+
+
+@pytest.mark.parametrize("w,h,codec_name,k", [(1920, 1080, "Hap1", 1), (3840, 2160, "HapY", 8), (2048, 1024, "HapM", 5), (512, 256, "Hap5", 3)])
+def test_frames_with_fragment_index(index_on, w, h, codec_name, k):
+    """hap_index.h: the encoder appends the fragment index behind the frame.  The frame proper is byte-identical to the frame
+    written without it; the reference decodes it (ignoring the trailing section) to the texture; this decoder gives the same
+    bytes with the index, without it (on-the-fly index) and when the index has been damaged (repair pass)."""
+    import hap_b200.lib as L
+    lib = index_on
+    codec = getattr(L, "HapB200Codec_" + codec_name)
+    img = synth.frame(w, h, 3, alpha="ramp" if codec_name in ("HapM", "Hap5") else "opaque", device="cuda")
+    cap = (lib.max_encoded_length_rgba(w, h, codec, k) + 15) // 16 * 16
+    out = torch.zeros(2 * cap, dtype=torch.uint8, device="cuda")
+    used = torch.zeros(2, dtype=torch.int64, device="cuda")
+    assert lib.encode_rgba_batch(img.data_ptr(), 1, img.numel(), w, h, codec, 1, k, out.data_ptr(), cap, used.data_ptr()) == 0
+    lib.set_option(lib.OPTION_WRITE_INDEX, 0)
+    assert lib.encode_rgba_batch(img.data_ptr(), 1, img.numel(), w, h, codec, 1, k, out.data_ptr() + cap, cap, used.data_ptr() + 8) == 0
+    lib.set_option(lib.OPTION_WRITE_INDEX, 1)
+    host = out.cpu().numpy()
+    with_ix, plain = host[: int(used[0])].tobytes(), host[cap: cap + int(used[1])].tobytes()
+    assert len(with_ix) > len(plain) and with_ix[: len(plain)] == plain
+    assert with_ix[len(plain) + 3] == 0xFB and with_ix[len(plain) + 4: len(plain) + 8] == b"HB2I"
+    assert len(with_ix) <= 1.02 * len(plain) + 64          # about one per cent
+    ref = oracles.ref_abi() or oracles.oracle_abi()
+    ntex = 2 if codec_name == "HapM" else 1
+    damaged = bytearray(with_ix)
+    rng = np.random.default_rng(7)
+    for _ in range(6):
+        damaged[len(plain) + 40 + int(rng.integers(0, len(with_ix) - len(plain) - 40))] ^= 1 << int(rng.integers(0, 8))
+    for i in range(ntex):
+        n = lib.texture_bytes(w, h, codec, i)
+        want = ref.decode(with_ix, i, n)
+        assert want[0] == 0 and len(want[1]) == n
+        assert lib.decode(with_ix, i, n)[:3] == want[:3]
+        assert lib.decode(bytes(damaged), i, n)[:3] == want[:3]
+        lib.set_option(lib.OPTION_USE_INDEX, 0)
+        assert lib.decode(with_ix, i, n)[:3] == want[:3]
+        lib.set_option(lib.OPTION_USE_INDEX, 1)
+    # batch path: three copies, the middle one damaged
+    F = 3
+    bcap = (len(with_ix) + 63) // 64 * 64
+    buf = torch.zeros(F * bcap, dtype=torch.uint8, device="cuda")
+    for f, fr in enumerate((with_ix, bytes(damaged), with_ix)):
+        buf[f * bcap: f * bcap + len(fr)] = torch.frombuffer(bytearray(fr), dtype=torch.uint8).cuda()
+    lens = torch.tensor([len(with_ix)] * F, dtype=torch.int64, device="cuda")
+    for i in range(ntex):
+        n = lib.texture_bytes(w, h, codec, i)
+        stride = (n + 15) // 16 * 16
+        tex = torch.zeros(F * stride, dtype=torch.uint8, device="cuda")
+        tu = torch.zeros(F, dtype=torch.int64, device="cuda")
+        tf = torch.zeros(F, dtype=torch.int32, device="cuda")
+        res = torch.full((F,), 9, dtype=torch.int32, device="cuda")
+        assert lib.decode_batch(buf.data_ptr(), F, bcap, lens.data_ptr(), i, k, tex.data_ptr(), stride, tu.data_ptr(), tf.data_ptr(), res.data_ptr()) == 0
+        assert res.tolist() == [0] * F and tu.tolist() == [n] * F
+        want = torch.frombuffer(bytearray(ref.decode(with_ix, i, n)[1]), dtype=torch.uint8).cuda()
+        for f in range(F):
+            assert torch.equal(tex[f * stride: f * stride + n], want), (i, f)

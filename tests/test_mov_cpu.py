@@ -279,3 +279,72 @@ def test_ffmpeg_decodes_snappy_frames_of_oracle_and_reference(lib, tmp_path, who
             pytest.skip("this OpenCV/FFmpeg build has no Hap decoder")
         ref = oracles.bc_decode(kind, tex, w, h)[..., :3][..., ::-1]
         assert np.abs(bgr.astype(int) - ref.astype(int)).max() <= 3, (who, cc)
+
+
+def with_private_section(frame: bytes, body: bytes, typ: int = 0xFB) -> bytes:
+    """Insert an unknown section behind the size table of the Decode Instructions container of a single-texture Complex
+    frame with 4-byte headers: legal by hap.c:701-704, but NOT what the fragment index does (FFmpeg cannot take it)."""
+    top_len = int.from_bytes(frame[0:3], "little")
+    assert top_len != 0 and (frame[3] >> 4) == 0xC and frame[7] == 0x01
+    di_len = int.from_bytes(frame[4:7], "little")
+    extra = len(body).to_bytes(3, "little") + bytes([typ]) + body
+    di_end = 8 + di_len
+    out = bytearray()
+    out += (top_len + len(extra)).to_bytes(3, "little") + frame[3:4]
+    out += (di_len + len(extra)).to_bytes(3, "little") + frame[7:8]
+    out += frame[8:di_end] + extra + frame[di_end:]
+    return bytes(out)
+
+
+def with_trailing_section(frame: bytes, body: bytes, typ: int = 0xFB) -> bytes:
+    """A further top-level section behind the frame: where the fragment index of hap_b200/csrc/hap_index.h travels."""
+    return frame + len(body).to_bytes(3, "little") + bytes([typ]) + body
+
+
+def test_a_trailing_section_is_ignored_by_every_decoder(lib, tmp_path):
+    """The fragment index is appended to the frame as one more top-level section.  The reference (and its port) work
+    inside the first section's stated length; FFmpeg's Hap decoder does the same -- frames with and without the trailing
+    section decode to the same picture, one and two textures.  (An unknown section INSIDE the Decode Instructions container,
+    which hap.c:701-704 skips, is accepted by the reference but not by FFmpeg: also checked, it is why the index trails.)"""
+    cv2 = pytest.importorskip("cv2")
+    import oracles
+    import twin
+    from hap_b200 import synth
+    from hap_b200.abi import HapCompressorSnappy, HapTextureFormat_A_RGTC1
+    w, h = 256, 128
+    img = synth.frame(w, h, 2, alpha="ramp").numpy()
+    tex, alpha = twin.encode("ycocg", img), twin.encode("bc4", img)
+    orc, ref = oracles.oracle_abi(), oracles.ref_abi()
+    body = b"HB2I" + bytes(range(60))
+    for cc, texs, fmts, chunks in (("HapY", [tex], [HapTextureFormat_YCoCg_DXT5], [4]),
+                                   ("HapM", [tex, alpha], [HapTextureFormat_YCoCg_DXT5, HapTextureFormat_A_RGTC1], [4, 2])):
+        r, f = orc.encode(texs, fmts, [HapCompressorSnappy] * len(texs), chunks)
+        assert r == 0
+        g = with_trailing_section(f, body)
+        for dec in (orc, ref, lib):
+            if dec is None:
+                continue
+            assert dec.texture_count(g) == (0, len(texs))
+            for i in range(len(texs)):
+                assert dec.chunk_count(g, i) == (0, chunks[i]) and dec.texture_format(g, i) == (0, fmts[i])
+                if dec is not lib:   # (the library's decode needs the GPU: tests/test_gpu_parity.py)
+                    assert dec.decode(g, i, len(texs[i]))[:3] == (0, texs[i], fmts[i])
+        path = str(tmp_path / f"trailing_{cc}.mov")
+        with mov.MovWriter(path, cc, w, h, 600) as wr:
+            assert wr.write(g, 20) == 0 and wr.write(f, 20) == 0
+        cap = cv2.VideoCapture(path, cv2.CAP_FFMPEG)
+        ok, bgr = cap.read() if cap.isOpened() else (False, None)
+        ok2, bgr2 = cap.read() if ok else (False, None)
+        cap.release()
+        if not ok:
+            pytest.skip("this OpenCV/FFmpeg build has no Hap decoder")
+        assert ok2 and np.array_equal(bgr, bgr2), cc
+        refpic = oracles.bc_decode("ycocg", tex, w, h)[..., :3][..., ::-1]
+        assert np.abs(bgr.astype(int) - refpic.astype(int)).max() <= 3
+    # inside the Decode Instructions container: fine for hap.c, fatal for FFmpeg
+    r, f = orc.encode([tex], [HapTextureFormat_YCoCg_DXT5], [HapCompressorSnappy], [4])
+    inside = with_private_section(f, body)
+    for dec in (orc, ref):
+        if dec is not None:
+            assert dec.decode(inside, 0, len(tex))[:3] == (0, tex, HapTextureFormat_YCoCg_DXT5)
+    assert lib.chunk_count(inside, 0) == (0, 4)
