@@ -264,8 +264,8 @@ class Roundtrip:
             assert r == 0, r
 
     def check(self):
-        assert self.res.tolist() == [0] * self.F, "decode failed"
-        assert self.tex_used.tolist() == [self.tex_bytes[self.ntex - 1]] * self.F
+        assert self.res.tolist() == [0] * self.F, f"decode failed: results {self.res.tolist()[:8]} used {self.used.tolist()[:4]} cap {self.cap}"
+        assert self.tex_used.tolist() == [self.tex_bytes[self.ntex - 1]] * self.F, f"decoded sizes {self.tex_used.tolist()[:8]}"
 
     def mean_frame_bytes(self):
         return float(self.used.double().mean().item())

@@ -70,56 +70,95 @@ struct StageScope {
         g_launches.fetch_add(1, std::memory_order_relaxed);                \
     } while (0)
 
-struct Runtime {
-    std::mutex mu;          // serialises the calls that run on the legacy default stream (those with a device pointer among their buffers)
+// ---- devices ------------------------------------------------------------------------------------------------------------
+// The library can drive every GPU of the box from one process (or one GPU per process under torchrun -- both work):
+//   * a call that has a DEVICE pointer among its buffers runs on that pointer's device;
+//   * a call with host pointers only runs on the process's default device: the device that was current in the thread that
+//     made the library's first call, or the one named by HapB200SetDevice (a new host thread starts on device 0, so "the
+//     calling thread's current device" would send the worker threads of a process that drives GPU 3 to GPU 0);
+//   * the caller's current device is restored when the call returns.
+// Per-device state (SM count, kernel attributes, memory-pool threshold) is set up on a device's first use.
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+    std::once_flag once;
     bool ready = false;
-    bool failed = false;
-    cudaStream_t stream = nullptr;
-    int device = 0;   // the device of the thread that made the first call: every later call runs there
     int sm_count = 148;
 };
-Runtime g_rt;
-std::once_flag g_once;
+DeviceState g_dev[kMaxDevices];
+std::atomic<int> g_default_device{-1};
+std::mutex g_legacy_mu;   // serialises the calls that run on the legacy default stream (those with a device pointer among their buffers)
+thread_local int t_device = 0;   // device of the library call running on this thread
 
-void runtime_init()
+void device_init(int dev)
 {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { g_rt.failed = true; cudaGetLastError(); return; }
-    g_rt.device = dev;
-    // process-wide defaults of the two options (HapB200SetOption overrides them)
-    if (const char *e = getenv("HAPB200_WRITE_INDEX")) g_write_index.store(atoi(e) != 0);
-    if (const char *e = getenv("HAPB200_USE_INDEX")) g_use_index.store(atoi(e) != 0);
-    if (cudaDeviceGetAttribute(&g_rt.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_rt.sm_count <= 0) { cudaGetLastError(); g_rt.sm_count = 148; }
+    DeviceState &d = g_dev[dev];
+    if (cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.sm_count <= 0) { cudaGetLastError(); d.sm_count = 148; }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long keep = ~0ull;  // keep freed scratch in the pool: steady-state calls never hit the OS
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
+    // (function attributes are per device: set them on each device's first use)
     bool ok = cudaFuncSetAttribute(snappy_execute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExecSmem)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(snappy_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IndexSmem)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(snappy_encode_fragments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(EncodeSmem)) == cudaSuccess;
-    // NULL-stream calls and the host-pointer entry points run on the LEGACY default stream: it orders itself
-    // against every blocking stream of the process, so buffers a caller produced on its own (blocking) stream --
-    // torch's current stream, cudaMemset, ... -- are complete before our kernels touch them.
-    g_rt.stream = cudaStreamLegacy;
-    if (!ok) { g_rt.failed = true; cudaGetLastError(); return; }
-    g_rt.ready = true;
+    if (!ok) { cudaGetLastError(); return; }
+    d.ready = true;
 }
 
-bool runtime_ok()
+int pointer_device(const void *p)   // device ordinal of a device / managed pointer, -1 for host memory
 {
-    std::call_once(g_once, runtime_init);
-    if (!g_rt.ready) return false;
-    // The current device is per host thread and a new thread starts on device 0: a worker thread of a process that
-    // drives GPU 3 would otherwise allocate and launch on GPU 0 (found with the bench's host thread pool on rank 1).
-    int cur = -1;
-    if (cudaGetDevice(&cur) != cudaSuccess || cur != g_rt.device) {
-        cudaGetLastError();
-        if (cudaSetDevice(g_rt.device) != cudaSuccess) { cudaGetLastError(); return false; }
-    }
-    return true;
+    cudaPointerAttributes a;
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
 }
+
+// One per entry point.  `hints`: the call's buffers; the first device pointer among them decides the device.
+struct DeviceGuard {
+    int saved = -1;
+    bool ok = false;
+    DeviceGuard(std::initializer_list<const void *> hints)
+    {
+        static std::once_flag env_once;
+        std::call_once(env_once, [] {
+            // process-wide defaults of the two options (HapB200SetOption overrides them)
+            if (const char *e = getenv("HAPB200_WRITE_INDEX")) g_write_index.store(atoi(e) != 0);
+            if (const char *e = getenv("HAPB200_USE_INDEX")) g_use_index.store(atoi(e) != 0);
+        });
+        if (cudaGetDevice(&saved) != cudaSuccess) { cudaGetLastError(); saved = -1; return; }
+        int want = -1;
+        for (const void *h : hints) {
+            want = pointer_device(h);
+            if (want >= 0) break;
+        }
+        if (want < 0) {
+            int expected = -1;
+            g_default_device.compare_exchange_strong(expected, saved);   // first call: this thread's device becomes the default
+            want = g_default_device.load();
+        }
+        if (want < 0 || want >= kMaxDevices) return;
+        if (want != saved && cudaSetDevice(want) != cudaSuccess) { cudaGetLastError(); return; }
+        std::call_once(g_dev[want].once, device_init, want);
+        t_device = want;
+        ok = g_dev[want].ready;
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        if (saved >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != saved) cudaSetDevice(saved);
+        cudaGetLastError();
+    }
+};
+#define HAP_ENTER(...)                                     \
+    DeviceGuard hap_device_guard_({__VA_ARGS__});          \
+    if (!hap_device_guard_.ok) return HapResult_Internal_Error
+
+inline int sm_count() { return g_dev[t_device].sm_count; }
+const cudaStream_t kLegacyStream = cudaStreamLegacy;
+// NULL-stream calls and the host-pointer entry points that touch caller-owned device buffers run on the LEGACY default
+// stream: it orders itself against every blocking stream of the process, so buffers a caller produced on its own (blocking)
+// stream -- torch's current stream, cudaMemset, ... -- are complete before our kernels touch them.
 
 // Stream of one host-pointer call.  When every buffer of the call is host memory nothing outside the call can
 // be ordered against it, so it takes a private non-blocking stream from a pool and concurrent calls from
@@ -141,9 +180,11 @@ struct CallStream {
     PooledStream ps;
     std::unique_lock<std::mutex> serial;
     static std::mutex &pool_mu() { static std::mutex m; return m; }
-    static std::vector<PooledStream> &pool() { static std::vector<PooledStream> v; return v; }
+    static std::vector<PooledStream> &pool() { static std::vector<PooledStream> v[kMaxDevices]; return v[t_device]; }
+    int device = 0;
     explicit CallStream(bool all_host)
     {
+        device = t_device;
         if (all_host) {
             {
                 std::lock_guard<std::mutex> l(pool_mu());
@@ -173,8 +214,8 @@ struct CallStream {
             if (pooled) g_call_mem = ps.mem;
         }
         if (!pooled) {
-            serial = std::unique_lock<std::mutex>(g_rt.mu);
-            st = g_rt.stream;
+            serial = std::unique_lock<std::mutex>(g_legacy_mu);
+            st = kLegacyStream;
         }
     }
     ~CallStream()
@@ -182,7 +223,8 @@ struct CallStream {
         if (pooled) {
             g_call_mem = nullptr;
             std::lock_guard<std::mutex> l(pool_mu());
-            pool().push_back(ps);
+            static_cast<void>(device);
+            pool().push_back(ps);   // (t_device is still this call's device: the guard outlives the stream)
         }
     }
 };
@@ -251,7 +293,7 @@ uint32_t launch_encode(const uint8_t *base, const FrameGeom &G, uint32_t frames,
 #define HAPB200_ENC_PERSISTENT 1
 #endif
     // one resident CTA per SM strides over the fragments (the kernel's 131 KB of shared memory allow no second one)
-    const unsigned k5_grid = HAPB200_ENC_PERSISTENT ? (unsigned)(nfrag < (uint64_t)g_rt.sm_count ? nfrag : (uint64_t)g_rt.sm_count) : (unsigned)nfrag;
+    const unsigned k5_grid = HAPB200_ENC_PERSISTENT ? (unsigned)(nfrag < (uint64_t)sm_count() ? nfrag : (uint64_t)sm_count()) : (unsigned)nfrag;
     HAP_KLAUNCH(kStSnappyEncode, snappy_encode_fragments_kernel, dim3(k5_grid), dim3(kEncThreads), sizeof(EncodeSmem), st, base, G,
                 (uint32_t)nfrag, scratch.as<uint8_t>(), fsize.as<uint32_t>(), write_index ? fent.as<uint8_t>() : (uint8_t *)nullptr);
     HAP_KLAUNCH(kStPlan, hap_plan_frames_kernel, dim3(frames), dim3(kPlanThreads), 0, st, G, base, fsize.as<uint32_t>(),
@@ -330,20 +372,20 @@ uint32_t launch_decode_jobs(ChunkJob *jobs, uint32_t njobs, uint64_t in_bound, u
     }
     DecodeCtl *c = ctl.as<DecodeCtl>();
     uint32_t *any_left = reinterpret_cast<uint32_t *>(ctl.as<uint8_t>() + sizeof(DecodeCtl));
-    const unsigned ex_grid = (unsigned)g_rt.sm_count * 3u;
+    const unsigned ex_grid = (unsigned)sm_count() * (unsigned)HAPB200_EX_MIN_BLOCKS;
     HAP_KLAUNCH(kStWindows, hap_build_windows_kernel, dim3((njobs + 127) / 128), dim3(128), 0, st, jobs, njobs, (uint32_t)g_use_index.load(),
                 wins.as<DecWin>(), win_cap, c);
-    HAP_KLAUNCH(kStSnappyIndex, snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), st, jobs, (int)njobs, (uint32_t)kJobNeedsIndex,
+    HAP_KLAUNCH(kStSnappyIndex, snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), st, jobs, (int)njobs, 0u,
                 wins.as<DecWin>(), win_cap, entries.as<uint8_t>(), c);
-    HAP_KLAUNCH(kStSnappyDecode, snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), st, jobs, wins.as<DecWin>(), c,
+    HAP_KLAUNCH(kStSnappyDecode, snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), st, jobs, njobs, 0u, wins.as<DecWin>(), c,
                 done.as<uint32_t>());
     if (g_use_index.load()) {
         // chunks whose embedded index did not describe their stream: decode them again as if they had none
-        HAP_KLAUNCH(kStWindows, hap_requeue_mismatched_kernel, dim3((njobs + 127) / 128), dim3(128), 0, st, jobs, njobs, c, any_left);
-        HAP_KLAUNCH(kStSnappyIndex, snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), st, jobs, (int)njobs,
-                    (uint32_t)kJobNeedsIndex, wins.as<DecWin>(), win_cap, entries.as<uint8_t>(), c);
-        HAP_KLAUNCH(kStSnappyDecode, snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), st, jobs, wins.as<DecWin>(), c,
-                    done.as<uint32_t>());
+        HAP_KLAUNCH(kStWindows, hap_requeue_mismatched_kernel, dim3((njobs + 127) / 128), dim3(128), 0, st, jobs, njobs, any_left);
+        HAP_KLAUNCH(kStSnappyIndex, snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), st, jobs, (int)njobs, 1u,
+                    wins.as<DecWin>(), win_cap, entries.as<uint8_t>(), c);
+        HAP_KLAUNCH(kStSnappyDecode, snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), st, jobs, njobs, 1u, wins.as<DecWin>(),
+                    c, done.as<uint32_t>());
     }
     return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
 }
@@ -423,6 +465,16 @@ int HapB200DebugDecodePhaseCycles(unsigned long long *out, int n, int reset)
     return 8;
 #endif
 }
+
+// The device host-pointer calls run on (device-pointer calls run where their buffers live).  -1: forget it; the next
+// host-pointer call takes its thread's current device.
+int HapB200SetDevice(int device)
+{
+    if (device < -1 || device >= kMaxDevices) return -1;
+    g_default_device.store(device);
+    return 0;
+}
+int HapB200GetDevice(void) { return g_default_device.load(); }
 
 // Options.  HAPB200_OPTION_USE_INDEX (1): decoder uses a frame's embedded fragment index (default 1).
 // HAPB200_OPTION_WRITE_INDEX (2): encoder writes the fragment index section (default: see g_write_index).
@@ -600,7 +652,7 @@ unsigned int HapEncode(unsigned int count, const void **inputBuffers, unsigned l
         return HapResult_No_Error;
     }
 
-    if (!runtime_ok()) return HapResult_Internal_Error;
+    HAP_ENTER(outputBuffer, inputBuffers[0], count == 2 ? inputBuffers[1] : nullptr);
     bool enc_all_host = !is_device_pointer(outputBuffer);
     for (unsigned i = 0; i < count; i++) enc_all_host = enc_all_host && !is_device_pointer(inputBuffers[i]);
     CallStream call(enc_all_host);
@@ -712,7 +764,7 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
         if (!in_dev && !out_dev) {
             memcpy(outputBuffer, sec, loc.len);
         } else {
-            if (!runtime_ok()) return HapResult_Internal_Error;
+            HAP_ENTER(inputBuffer, outputBuffer);
             const uint8_t *src = in_dev ? (const uint8_t *)inputBuffer + loc.offset : sec;
             if (cudaMemcpy(outputBuffer, src, loc.len, cudaMemcpyDefault) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
         }
@@ -723,7 +775,7 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
     }
 
     if (!hj.empty()) {
-        if (!runtime_ok()) return HapResult_Internal_Error;
+        HAP_ENTER(inputBuffer, outputBuffer);
         CallStream call(!in_dev && !out_dev);
         cudaStream_t st = call.st;
         DevBuf din(st), dout(st), djobs(st);
@@ -763,6 +815,8 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
             jobs[i].index = hj[i].index_bytes ? dindex + (hj[i].index_off - hv_index_body) : nullptr;
             jobs[i].index_bytes = hj[i].index_bytes;
             jobs[i].mode = kJobUndecided;
+            jobs[i].win_base = 0;
+            jobs[i].win_count = 0;
             in_sum += hj[i].src_bytes;
         }
         if (!djobs.alloc(jobs.size() * sizeof(ChunkJob)) ||
@@ -813,8 +867,8 @@ unsigned int HapB200BlockEncodeBatch(const void *rgba, unsigned int frames, unsi
     if (!rgba || !blocks || frames == 0 || !codec_info(codec, ci) || width == 0 || height == 0 || width % 4 || height % 4 ||
         rowBytes < 4ul * width || rowBytes % 16 || ((uintptr_t)rgba | (uintptr_t)blocks | frameStride | blocksStride) % 16)
         return HapResult_Bad_Arguments;
-    if (!runtime_ok()) return HapResult_Internal_Error;
-    cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
+    HAP_ENTER(rgba, blocks);
+    cudaStream_t st = stream ? (cudaStream_t)stream : kLegacyStream;
     uint32_t r = launch_block_encode((const uint8_t *)rgba, frames, frameStride, width, height, rowBytes, ci, (uint8_t *)blocks,
                                      blocksStride, HapB200TextureBytes(width, height, codec, 0), st);
     if (r == HapResult_No_Error && !stream && cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); r = HapResult_Internal_Error; }
@@ -829,8 +883,8 @@ unsigned int HapB200BlockDecodeBatch(const void *blocks, unsigned int frames, un
     if (!rgba || !blocks || frames == 0 || !codec_info(codec, ci) || width == 0 || height == 0 || width % 4 || height % 4 ||
         rowBytes < 4ul * width || rowBytes % 16 || ((uintptr_t)rgba | (uintptr_t)blocks | frameStride | blocksStride) % 16)
         return HapResult_Bad_Arguments;
-    if (!runtime_ok()) return HapResult_Internal_Error;
-    cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
+    HAP_ENTER(blocks, rgba);
+    cudaStream_t st = stream ? (cudaStream_t)stream : kLegacyStream;
     const uint8_t *b = (const uint8_t *)blocks;
     uint32_t r = launch_block_decode(b, b + HapB200TextureBytes(width, height, codec, 0), frames, blocksStride, blocksStride, width,
                                      height, ci, (uint8_t *)rgba, frameStride, rowBytes, st);
@@ -859,8 +913,8 @@ unsigned int HapB200EncodeBatch(unsigned int count, const void **textures, unsig
     FrameGeom G;
     uint32_t r = build_frame_geom(count, ta, G);
     if (r != HapResult_No_Error) return r;
-    if (!runtime_ok()) return HapResult_Internal_Error;
-    cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
+    HAP_ENTER(out, textures[0]);
+    cudaStream_t st = stream ? (cudaStream_t)stream : kLegacyStream;
     const uint8_t *base = (const uint8_t *)textures[0];
     for (unsigned i = 0; i < count; i++) {
         G.s[i].in_offset = (uint64_t)((const uint8_t *)textures[i] - base);  // wraps for i = 1 when below base; 64-bit add undoes it
@@ -882,8 +936,8 @@ unsigned int HapB200EncodeRGBABatch(const void *rgba, unsigned int frames, unsig
         (compressor != HapCompressorNone && compressor != HapCompressorSnappy))
         return HapResult_Bad_Arguments;
     if (outStride < HapB200MaxEncodedLengthRGBA(width, height, codec, chunkCount)) return HapResult_Buffer_Too_Small;
-    if (!runtime_ok()) return HapResult_Internal_Error;
-    cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
+    HAP_ENTER(rgba, out);
+    cudaStream_t st = stream ? (cudaStream_t)stream : kLegacyStream;
     const uint64_t t0 = HapB200TextureBytes(width, height, codec, 0), t1 = HapB200TextureBytes(width, height, codec, 1);
     const uint64_t dxt_stride = align16(t0) + align16(t1);
     DevBuf dxt(st);
@@ -915,7 +969,7 @@ unsigned int HapB200EncodeRGBA(const void *rgba, unsigned int width, unsigned in
         return HapResult_Bad_Arguments;
     const unsigned long cap = HapB200MaxEncodedLengthRGBA(width, height, codec, chunkCount);
     if (outputBufferBytes < cap) return HapResult_Buffer_Too_Small;
-    if (!runtime_ok()) return HapResult_Internal_Error;
+    HAP_ENTER(rgba, outputBuffer);
     CallStream call(!is_device_pointer(rgba) && !is_device_pointer(outputBuffer));
     cudaStream_t st = call.st;
     DevBuf img(st), frame(st), used(st);
@@ -939,8 +993,8 @@ unsigned int HapB200DecodeBatch(const void *in, unsigned int frames, unsigned lo
 {
     if (!in || !inBytes || !out || !used || !formats || !results || frames == 0 || maxChunks == 0 || index > 1)
         return HapResult_Bad_Arguments;
-    if (!runtime_ok()) return HapResult_Internal_Error;
-    cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
+    HAP_ENTER(in, out);
+    cudaStream_t st = stream ? (cudaStream_t)stream : kLegacyStream;
     uint32_t r = launch_decode_batch((const uint8_t *)in, frames, inStride, inBytes, index, maxChunks, (uint8_t *)out, outStride, outStride,
                                      used, formats, results, st);
     if (r == HapResult_No_Error && !stream && cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); r = HapResult_Internal_Error; }
@@ -955,8 +1009,8 @@ unsigned int HapB200DecodeRGBABatch(const void *in, unsigned int frames, unsigne
     if (!in || !inBytes || !rgba || !results || frames == 0 || maxChunks == 0 || !codec_info(codec, ci) || width == 0 ||
         height == 0 || width % 4 || height % 4 || rowBytes < 4ul * width || rowBytes % 16 || ((uintptr_t)rgba | frameStride) % 16)
         return HapResult_Bad_Arguments;
-    if (!runtime_ok()) return HapResult_Internal_Error;
-    cudaStream_t st = stream ? (cudaStream_t)stream : g_rt.stream;
+    HAP_ENTER(in, rgba);
+    cudaStream_t st = stream ? (cudaStream_t)stream : kLegacyStream;
     const uint64_t t0 = HapB200TextureBytes(width, height, codec, 0), t1 = HapB200TextureBytes(width, height, codec, 1);
     const uint64_t dxt_stride = align16(t0) + align16(t1);
     DevBuf dxt(st), used(st), formats(st), res1(st);
@@ -1007,15 +1061,15 @@ unsigned int HapB200DecodeRGBA(const void *inputBuffer, unsigned long inputBuffe
     }
     CodecInfo ci;
     if (!codec_info(codec, ci)) return HapResult_Bad_Frame;  // BPTC frames carry no RGBA decoder here
-    if (!runtime_ok()) return HapResult_Internal_Error;
+    HAP_ENTER(inputBuffer, rgba);
     const uint64_t t0 = HapB200TextureBytes(width, height, codec, 0), t1 = HapB200TextureBytes(width, height, codec, 1);
-    void *dxt = nullptr, *img = nullptr;
     const uint64_t tight = 4ull * width;
-    if (cudaMalloc(&dxt, align16(t0) + align16(t1) + 16) != cudaSuccess || cudaMalloc(&img, tight * height) != cudaSuccess) {
-        cudaGetLastError();
-        if (dxt) cudaFree(dxt);
-        return HapResult_Internal_Error;
-    }
+    // scratch from the device's stream-ordered pool on the legacy stream (the nested HapDecode calls below write it on
+    // that stream, or on a pooled stream they synchronise before returning): no cudaMalloc/cudaFree, no device-wide sync
+    DevBuf dxtb(kLegacyStream), imgb(kLegacyStream);
+    if (!dxtb.alloc(align16(t0) + align16(t1) + 16) || !imgb.alloc(tight * height)) { cudaGetLastError(); return HapResult_Internal_Error; }
+    void *dxt = dxtb.p, *img = imgb.p;
+    if (cudaStreamSynchronize(kLegacyStream) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }   // the allocations are real now
     auto serial = [](HapDecodeWorkFunction fn, void *p, unsigned n, void *) { for (unsigned i = 0; i < n; i++) fn(p, i); };
     unsigned long used = 0;
     unsigned fmt = 0;
@@ -1034,8 +1088,6 @@ unsigned int HapB200DecodeRGBA(const void *inputBuffer, unsigned long inputBuffe
             (cudaMemcpy2DAsync(rgba, rowBytes, img, tight, tight, height, cudaMemcpyDefault, st) != cudaSuccess ||
              cudaStreamSynchronize(st) != cudaSuccess)) { cudaGetLastError(); r = HapResult_Internal_Error; }
     }
-    cudaFree(dxt);
-    cudaFree(img);
     return r;
 }
 

@@ -45,8 +45,12 @@ struct ChunkJob {
     const uint8_t *index; // this chunk's record inside the frame's fragment index (hap_index.h), or nullptr
     uint32_t index_bytes; // bytes readable at `index`
     uint32_t mode;        // internal, see kJob*
+    uint32_t win_base;    // internal: the chunk's windows are wins[win_base .. win_base + win_count)
+    uint32_t win_count;
 };
-enum : uint32_t { kJobUndecided = 0, kJobIndexed = 1, kJobNeedsIndex = 2 };
+// kJobReady: windows listed, first execute pass takes them.  kJobNeedsIndex: waits for the index kernel.  kJobRepaired: indexed
+// again after its embedded index failed the execute kernel's checks; the second execute pass takes it.
+enum : uint32_t { kJobUndecided = 0, kJobReady = 1, kJobNeedsIndex = 2, kJobRepaired = 3, kJobFinished = 4 };
 constexpr uint32_t kStatusIndexMismatch = 0x100;  // internal: the embedded index does not describe the stream -> decode again without it
 
 enum : uint32_t { kWinSnappy = 0, kWinRaw = 1, kWinSkip = 2 };
@@ -62,9 +66,10 @@ struct DecWin {                // one unit of work of the execute kernel
 };
 struct DecodeCtl {
     uint32_t n_windows;        // windows in the list (device-side counter)
-    uint32_t ticket;           // next window to execute
     uint32_t overflow;         // a chunk did not fit the list (cannot happen with the host's sizing; checked)
-    uint32_t pad;
+    uint32_t ticket[2];        // per execute pass: next ticket.  Ticket T = window (T / njobs) of chunk (T % njobs): the
+    uint32_t max_k[2];         //   k-th windows of ALL chunks come before any (k+1)-th, so that a window rarely has to wait for
+    uint32_t pad[2];           //   its predecessor and 444 resident CTAs work on 444 different chunks.  max_k: most windows any chunk has.
 };
 
 constexpr uint32_t kSrcIn = 0u << 30, kSrcOut = 1u << 30, kSrcRun = 2u << 30, kSrcMask = 3u << 30, kPosMask = (1u << 30) - 1;
@@ -149,14 +154,17 @@ constexpr int kIdxLook = 32;                         // staged beyond the window
 constexpr int kTblStride = kIdxThreads + 4;          // row stride of the exit table: rows 65 words apart, so that the 32 lanes'
                                                      // look-ups of DIFFERENT rows spread over the banks (256 put four lanes on one)
 constexpr uint32_t kExitMaxRel = 186;                // tbl value <= this: exit = sub-block end + value
-constexpr uint32_t kExitFarBase = 187;               // kExitFarBase + o (o = 0..63): the chain leaves through a long literal whose
+constexpr uint32_t kExitFarList = 187;               // kExitFarList + i (i = 0..3): the chain leaves through a long literal; where to is
+constexpr uint32_t kFarSlots = 4;                    //   entry i of the sub-block's far list (the sweep fills it: no header to re-read)
+constexpr uint32_t kExitFarBase = 191;               // kExitFarBase + o (o = 0..63): the same, but the far list was full: the literal's
                                                      // header sits at offset o of the sub-block; its end is read from that header
-constexpr uint32_t kExitInvalid = 254;               // the chain runs into an invalid element header
+constexpr uint32_t kExitInvalid = 255;               // the chain runs into an invalid element header
 
 struct IndexSmem {
     uint8_t cin[2][kIdxWin + kIdxLook + 32];         // staged windows (double buffered), cin[b][a + i] = byte i of the window
     uint8_t tbl[kIdxSub * kTblStride];               // tbl[o][t]: where the chain entering sub-block t at offset o leaves it
     uint16_t entry[kIdxThreads];                     // true entry offset of each sub-block, 0xFFFF = no element starts there
+    uint32_t far[kFarSlots][kIdxThreads];            // window-relative positions long literals of a sub-block lead to
     uint32_t scratch[kIdxThreads / 32];
     hap_mbar_t bar[2];
     unsigned long long saddr_box;
@@ -164,9 +172,10 @@ struct IndexSmem {
     int fail;
 };
 
-// jobs with mode == want_mode are indexed: entries (one byte per 64 stream bytes) and one DecWin per 16 KiB of stream are
-// appended to the lists.  entries_pool: [win_cap][256].
-__global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *jobs, int njobs, uint32_t want_mode, DecWin *wins,
+// jobs with mode == kJobNeedsIndex are indexed: entries (one byte per 64 stream bytes) and one DecWin per 16 KiB of stream
+// are appended to the lists; the job then waits for execute pass `pass` (0: kJobReady, 1: kJobRepaired).
+// entries_pool: [win_cap][256].
+__global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *jobs, int njobs, uint32_t pass, DecWin *wins,
                                                                       uint32_t win_cap, uint8_t *entries_pool, DecodeCtl *ctl)
 {
     HAP_DYN_SMEM(smem_raw);
@@ -174,7 +183,8 @@ __global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *
     const int t = threadIdx.x;
     if ((int)blockIdx.x >= njobs) return;
     ChunkJob &job = jobs[blockIdx.x];
-    if (job.mode != want_mode || job.compressor != kHapChunkSnappy) return;
+    if (job.mode != kJobNeedsIndex || job.compressor != kHapChunkSnappy) return;
+    const uint32_t done_mode = pass == 0 ? (uint32_t)kJobReady : (uint32_t)kJobRepaired;
     const uint8_t *__restrict__ src = job.src;
     const uint32_t n = job.src_bytes;
     const uint32_t expected = job.dst_bytes;
@@ -196,10 +206,11 @@ __global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *
     }
     __syncthreads();
     if (S.fail) {
-        if (t == 0) { job.status = S.fail == 2 ? HapResult_Internal_Error : HapResult_Bad_Frame; job.mode = kJobIndexed; }
+        if (t == 0) { job.status = S.fail == 2 ? HapResult_Internal_Error : HapResult_Bad_Frame; job.mode = kJobFinished; job.win_count = 0; }
         return;
     }
     const uint32_t base = S.scratch[0];
+    if (t == 0) { job.win_base = base; job.win_count = nwin; atomicMax(&ctl->max_k[pass], nwin); }
     const uint32_t a = (uint32_t)((uintptr_t)src & 15);   // the same for every window: windows are 16 KiB apart
     __syncthreads();
 
@@ -230,6 +241,7 @@ __global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *
             const uint32_t *c32 = reinterpret_cast<const uint32_t *>(S.cin[buf]) + (bi >> 2);
             const uint32_t sh = 8 * (bi & 3);
             uint8_t *col = S.tbl + t;
+            uint32_t nfar = 0;
 #pragma unroll 1
             for (int g = kIdxSub / 16 - 1; g >= 0; g--) {
                 uint32_t raw[7], w[6];
@@ -250,7 +262,12 @@ __global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *
                     const uint32_t nxt = kind != 0u ? o + ((0x5320u >> (4 * kind)) & 0xFu) : lit;     // copy headers: 2, 3 or 5 bytes
                     const uint32_t inside = nxt < blk_len ? nxt : o;                 // a row this thread has already written
                     const uint32_t chained = col[inside * kTblStride];
-                    const uint32_t beyond = nxt - blk_len <= kExitMaxRel ? nxt - blk_len : kExitFarBase + o;
+                    const bool is_far = nxt >= blk_len && nxt - blk_len > kExitMaxRel && nxt <= limit;   // (only long literals get this far)
+                    const uint32_t beyond = !is_far ? nxt - blk_len : (nfar < kFarSlots ? kExitFarList + nfar : kExitFarBase + o);
+                    if (is_far && nfar < kFarSlots) {
+                        S.far[nfar][t] = (uint32_t)t * kIdxSub + nxt;               // window-relative position the literal ends at
+                        nfar++;
+                    }
                     uint32_t x = nxt < blk_len ? chained : beyond;
                     x = nxt > limit ? kExitInvalid : x;                              // header or payload runs past the input
                     col[o * kTblStride] = (uint8_t)x;
@@ -274,6 +291,8 @@ __global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *
                 bend = bend < wl ? bend : wl;
                 if (x <= kExitMaxRel) {
                     rel = bend + x;
+                } else if (x < kExitFarBase) {
+                    rel = S.far[x - kExitFarList][blk];
                 } else if (x == kExitInvalid) {
                     S.fail = 1;
                     break;
@@ -335,7 +354,7 @@ __global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *
         }
         if (t == 0) job.status = HapResult_Bad_Frame;
     }
-    if (t == 0) job.mode = kJobIndexed;
+    if (t == 0) job.mode = done_mode;
 }
 
 // =====================================================================================================================
@@ -354,7 +373,9 @@ __global__ void hap_build_windows_kernel(ChunkJob *jobs, uint32_t njobs, uint32_
     ChunkJob &job = jobs[j];
     if (job.compressor == 0) return;   // unused slot of a batched frame (hap_parse.cuh)
     job.status = HapResult_No_Error;
-    job.mode = kJobIndexed;
+    job.mode = kJobFinished;    // nothing to execute, unless windows are listed below
+    job.win_base = 0;
+    job.win_count = 0;
     const uint32_t n = job.src_bytes, expected = job.dst_bytes;
     if (job.compressor == kHapChunkRaw) {
         // hap.c:630-636: verbatim chunk
@@ -363,6 +384,8 @@ __global__ void hap_build_windows_kernel(ChunkJob *jobs, uint32_t njobs, uint32_
         if (cnt == 0) return;
         const uint32_t base = atomicAdd(&ctl->n_windows, cnt);
         if (base + cnt > win_cap || base + cnt < base) { job.status = HapResult_Internal_Error; atomicExch(&ctl->overflow, 1u); return; }
+        job.win_base = base; job.win_count = cnt; job.mode = kJobReady;
+        atomicMax(&ctl->max_k[0], cnt);
         for (uint32_t i = 0; i < cnt; i++) {
             DecWin w;
             w.job = j; w.kind = kWinRaw; w.in_off = i * kRawWindow; w.in_len = n - i * kRawWindow < kRawWindow ? n - i * kRawWindow : kRawWindow;
@@ -393,7 +416,9 @@ __global__ void hap_build_windows_kernel(ChunkJob *jobs, uint32_t njobs, uint32_
     }
     if (stream != n || 2ull * nf + ent_bytes > job.index_bytes) return;
     const uint32_t base = atomicAdd(&ctl->n_windows, nf);
-    if (base + nf > win_cap || base + nf < base) { job.status = HapResult_Internal_Error; job.mode = kJobIndexed; atomicExch(&ctl->overflow, 1u); return; }
+    if (base + nf > win_cap || base + nf < base) { job.status = HapResult_Internal_Error; job.mode = kJobFinished; atomicExch(&ctl->overflow, 1u); return; }
+    job.win_base = base; job.win_count = nf;
+    atomicMax(&ctl->max_k[0], nf);
     uint32_t in_off = pre;
     const uint8_t *ent = job.index + 2 * nf;
     for (uint32_t f = 0; f < nf; f++) {
@@ -407,38 +432,44 @@ __global__ void hap_build_windows_kernel(ChunkJob *jobs, uint32_t njobs, uint32_
         in_off += s;
         ent += (s + (1u << kIndexSubLog2) - 1) >> kIndexSubLog2;
     }
-    job.mode = kJobIndexed;
+    job.mode = kJobReady;
 }
 
-// After an execute pass: chunks whose embedded index did not hold up are handed to the index kernel (mode kJobNeedsIndex,
-// status cleared); *any_left counts them.
-__global__ void hap_requeue_mismatched_kernel(ChunkJob *jobs, uint32_t njobs, DecodeCtl *ctl, uint32_t *any_left)
+// After the first execute pass: chunks whose embedded index did not hold up are handed to the index kernel (mode
+// kJobNeedsIndex, status cleared); *any_left counts them.
+__global__ void hap_requeue_mismatched_kernel(ChunkJob *jobs, uint32_t njobs, uint32_t *any_left)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0) ctl->ticket = ctl->n_windows;   // every window listed so far has been executed; new ones follow
     if (j >= njobs) return;
     if (jobs[j].compressor != 0 && jobs[j].status == kStatusIndexMismatch) {
         jobs[j].status = HapResult_No_Error;
         jobs[j].mode = kJobNeedsIndex;
         atomicAdd(any_left, 1u);
-    } else if (jobs[j].mode == kJobNeedsIndex) {
-        jobs[j].mode = kJobIndexed;   // (not reached: every such chunk was indexed before the execute pass)
     }
 }
 
 // =====================================================================================================================
 //  execute kernel
 // =====================================================================================================================
+#ifndef HAPB200_EX_MAX_ELEMS
+#define HAPB200_EX_MAX_ELEMS 2048
+#endif
+#ifndef HAPB200_EX_TILE
+#define HAPB200_EX_TILE 32768
+#endif
+#ifndef HAPB200_EX_MIN_BLOCKS
+#define HAPB200_EX_MIN_BLOCKS 3
+#endif
 constexpr int kExThreads = 256;
-constexpr int kExMaxElems = 2048;                    // descriptors held in shared memory per pass
+constexpr int kExMaxElems = HAPB200_EX_MAX_ELEMS;    // descriptors held in shared memory per pass
 constexpr int kExMaxIn = 32768 + 64;                 // stream bytes of one window the staging buffer holds
 constexpr int kExLook = 16;                          // staged beyond the window: header look-ahead
-constexpr int kExTile = 32768;                       // output bytes produced per tile
+constexpr int kExTile = HAPB200_EX_TILE;             // output bytes produced per tile
 constexpr int kExGroups = kExTile / 16 + 1;          // a tile that does not start on a 16-byte address touches one group more
 constexpr int kFlattenHops = 12;
 
 struct ExecSmem {
-    uint8_t cin[kExMaxIn + kExLook + 48];            // staged window, cin[a + i] = byte i of the window
+    uint8_t cin[32 + kExMaxIn + kExLook + 48];       // staged window, cin[32 + a + i] = byte i of the window (32 spare bytes in front)
     uint32_t e_dst[kExMaxElems];                     // output position inside the chunk
     uint32_t e_len[kExMaxElems];
     uint32_t e_a[kExMaxElems];                       // packed source: kSrcIn|input position, kSrcOut|output position, kSrcRun|offset
@@ -481,45 +512,42 @@ __device__ __forceinline__ void block_min_min_max(uint32_t &a, uint32_t &b, uint
 
 __device__ __forceinline__ unsigned long long low_bytes_mask(uint32_t k) { return k >= 8 ? ~0ull : ((1ull << (8 * k)) - 1ull); }
 
-// One aligned 32-bit word at `wa`, of which only the bytes inside [need_lo, need_hi) are wanted.  The word is loaded whole
-// when it lies inside the readable region [r_lo, r_hi); otherwise its wanted bytes are fetched one by one (the first and
-// last word of a chunk or of the output buffer), so that nothing outside the region is touched.
-__device__ __forceinline__ uint32_t word_for(uintptr_t wa, uintptr_t need_lo, uintptr_t need_hi, uintptr_t r_lo, uintptr_t r_hi)
+// One aligned 32-bit word at `wa`, of which only the bytes inside [need_lo, need_hi) are wanted, fetched byte by byte:
+// the first and last word of a chunk or of the output buffer, where a whole-word load would touch bytes outside it.
+__device__ __noinline__ uint32_t edge_word(uintptr_t wa, uintptr_t need_lo, uintptr_t need_hi)
 {
-    if (wa + 4 <= need_lo || wa >= need_hi) return 0;
-    if (wa >= r_lo && wa + 4 <= r_hi) return *reinterpret_cast<const uint32_t *>(wa);
     uint32_t v = 0;
     for (uint32_t q = 0; q < 4; q++)
         if (wa + q >= need_lo && wa + q < need_hi) v |= (uint32_t) * reinterpret_cast<const uint8_t *>(wa + q) << (8 * q);
     return v;
 }
 
-// n (1..16) bytes at `ptr` -> bytes [q, q + n) of the 16-byte group held in (lo64, hi64)
-__device__ __forceinline__ void gather_into_group(const uint8_t *ptr, uint32_t n, uint32_t q, uintptr_t r_lo, uintptr_t r_hi,
-                                                  unsigned long long &lo64, unsigned long long &hi64)
+// n (1..16) bytes at `ptr` -> bytes [q, 16) of the 16-byte group held in (lo64, hi64); bytes below q are kept.  (What lands
+// behind q + n is overwritten by the pieces that follow, or lies beyond the group's last byte and is never stored.)
+// `safe`: the five aligned words around the piece may be read whole (shared memory, or well inside a global buffer).
+__device__ __forceinline__ void gather_into_group(const uint8_t *ptr, uint32_t n, uint32_t q, bool safe, unsigned long long &lo64,
+                                                  unsigned long long &hi64)
 {
     const uintptr_t p = (uintptr_t)ptr;
-    if (n == 16 && (p & 15) == 0 && p >= r_lo && p + 16 <= r_hi) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(p);
-        lo64 = v.x | ((unsigned long long)v.y << 32);
-        hi64 = v.z | ((unsigned long long)v.w << 32);
-        return;
-    }
     // the address that corresponds to byte 0 of the group, its aligned base and the shift between the two
     const uintptr_t g0 = p - q;
     const uint32_t mis = (uint32_t)(g0 & 3);
     const uintptr_t b0 = g0 - mis;
     uint32_t s[5];
+    if (safe) {
 #pragma unroll
-    for (int k = 0; k < 5; k++) s[k] = word_for(b0 + 4 * k, p, p + n, r_lo, r_hi);
-    const uint32_t c0 = __funnelshift_r(s[0], s[1], 8 * mis), c1 = __funnelshift_r(s[1], s[2], 8 * mis);
-    const uint32_t c2 = __funnelshift_r(s[2], s[3], 8 * mis), c3 = __funnelshift_r(s[3], s[4], 8 * mis);
+        for (int k = 0; k < 5; k++) s[k] = reinterpret_cast<const uint32_t *>(b0)[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 5; k++) s[k] = edge_word(b0 + 4 * k, p, p + n);
+    }
+    const uint32_t sh = 8 * mis;
+    const uint32_t c0 = __funnelshift_r(s[0], s[1], sh), c1 = __funnelshift_r(s[1], s[2], sh);
+    const uint32_t c2 = __funnelshift_r(s[2], s[3], sh), c3 = __funnelshift_r(s[3], s[4], sh);
     const unsigned long long cl = c0 | ((unsigned long long)c1 << 32), ch = c2 | ((unsigned long long)c3 << 32);
-    const uint32_t e = q + n;
-    const unsigned long long ml = low_bytes_mask(e < 8 ? e : 8) & ~low_bytes_mask(q < 8 ? q : 8);
-    const unsigned long long mh = low_bytes_mask(e > 8 ? e - 8 : 0) & ~low_bytes_mask(q > 8 ? q - 8 : 0);
-    lo64 = (lo64 & ~ml) | (cl & ml);
-    hi64 = (hi64 & ~mh) | (ch & mh);
+    const unsigned long long kl = low_bytes_mask(q), kh = q > 8 ? low_bytes_mask(q - 8) : 0ull;   // the bytes to keep
+    lo64 = (lo64 & kl) | (cl & ~kl);
+    hi64 = (hi64 & kh) | (ch & ~kh);
 }
 
 __device__ __forceinline__ uint32_t group_byte(unsigned long long lo64, unsigned long long hi64, uint32_t i)
@@ -560,10 +588,14 @@ __device__ __forceinline__ bool assemble_group(ExecSmem &S, const TileCtx &C, ui
         uint32_t n = seg_end - pos;
         const uint32_t q = (uint32_t)((int32_t)pos - gstart);
         const uint32_t a = S.e_a[e], kind = a & kSrcMask, ap = a & kPosMask;
+        const uint8_t *ptr;
+        bool safe;
         if (kind == kSrcIn) {
             const uint32_t ip = ap + (pos - d);
-            if (ip >= C.wb && ip + n <= C.wb + C.staged) gather_into_group(C.cin + (ip - C.wb), n, q, 0, ~(uintptr_t)0, lo64, hi64);
-            else gather_into_group(C.src + ip, n, q, (uintptr_t)C.src, (uintptr_t)C.src + C.src_bytes, lo64, hi64);
+            const bool staged = ip >= C.wb && ip + n <= C.wb + C.staged;
+            ptr = staged ? C.cin + (ip - C.wb) : C.src + ip;
+            // (the staging buffer has 32 spare bytes in front of and behind the window: whole words around a piece are always readable)
+            safe = staged || (ip >= 20u && ip + 20u <= C.src_bytes);
         } else {
             uint32_t sp;
             if (kind == kSrcOut) {
@@ -578,18 +610,22 @@ __device__ __forceinline__ bool assemble_group(ExecSmem &S, const TileCtx &C, ui
             if (sp >= lo) {
                 // the source bytes are earlier bytes of this very group (offsets below 16): they are in the registers
                 for (uint32_t i = 0; i < n; i++) set_group_byte(lo64, hi64, q + i, group_byte(lo64, hi64, (uint32_t)((int32_t)(sp + i) - gstart)));
-            } else {
-                if (sp + n > lo) n = lo - sp;             // the rest of the piece comes from the registers next time round
-                if (sp + n > C.T0) {
-                    // bytes this tile produces: their groups must have been written in an earlier round
-                    const int32_t rel0 = (int32_t)sp - C.gbase, rel1 = (int32_t)(sp + n - 1) - C.gbase;
-                    const uint32_t g0 = rel0 < 0 ? 0u : (uint32_t)rel0 >> 4, g1 = (uint32_t)rel1 >> 4;
-                    const uint32_t r0 = S.gdone[g0], r1 = S.gdone[g1];
-                    if (r0 == 0 || r0 >= round || r1 == 0 || r1 >= round) return false;
-                }
-                gather_into_group(C.dst + sp, n, q, (uintptr_t)C.dst, (uintptr_t)C.dst + C.dst_bytes, lo64, hi64);
+                pos += n;
+                if (pos >= d + l) e++;
+                continue;
             }
+            if (sp + n > lo) n = lo - sp;             // the rest of the piece comes from the registers next time round
+            if (sp + n > C.T0) {
+                // bytes this tile produces: their groups must have been written in an earlier round
+                const int32_t rel0 = (int32_t)sp - C.gbase, rel1 = (int32_t)(sp + n - 1) - C.gbase;
+                const uint32_t g0 = rel0 < 0 ? 0u : (uint32_t)rel0 >> 4, g1 = (uint32_t)rel1 >> 4;
+                const uint32_t r0 = S.gdone[g0], r1 = S.gdone[g1];
+                if (r0 == 0 || r0 >= round || r1 == 0 || r1 >= round) return false;
+            }
+            ptr = C.dst + sp;
+            safe = sp >= 20u && sp + 20u <= C.dst_bytes;
         }
+        gather_into_group(ptr, n, q, safe, lo64, hi64);
         pos += n;
         if (pos >= d + l) e++;
     }
@@ -625,20 +661,34 @@ __device__ __forceinline__ WalkResult walk_piece(const uint8_t *cin, uint32_t wb
     return r;
 }
 
-__global__ void __launch_bounds__(kExThreads, 3) snappy_execute_kernel(ChunkJob *jobs, const DecWin *wins, DecodeCtl *ctl, uint32_t *done)
+// pass 0 executes the chunks in mode kJobReady, pass 1 (repair) those in mode kJobRepaired.
+__global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_execute_kernel(ChunkJob *jobs, uint32_t njobs, uint32_t pass, const DecWin *wins,
+                                                                       DecodeCtl *ctl, uint32_t *done)
 {
     HAP_DYN_SMEM(smem_raw);
     ExecSmem &S = *reinterpret_cast<ExecSmem *>(smem_raw);
     const int t = threadIdx.x;
-    const uint32_t nwin = ctl->n_windows;      // final: every kernel that appends windows ran before this one
+    const uint32_t max_k = ctl->max_k[pass];   // final: every kernel that lists windows ran before this one
+    const uint32_t want_mode = pass == 0 ? (uint32_t)kJobReady : (uint32_t)kJobRepaired;
+    const unsigned long long n_tickets = (unsigned long long)max_k * njobs;
     if (t == 0) hap_mbar_init(&S.bar, 1);
     uint32_t phase = 0;
     __syncthreads();
     for (;;) {
-        if (t == 0) S.ticket = atomicAdd(&ctl->ticket, 1u);
+        if (t == 0) {
+            // the next ticket that names an existing window: window k = T / njobs of chunk T % njobs
+            uint32_t w = 0xFFFFFFFFu;
+            for (;;) {
+                const unsigned long long T = atomicAdd(&ctl->ticket[pass], 1u);
+                if (T >= n_tickets) break;
+                const uint32_t k = (uint32_t)(T / njobs), j = (uint32_t)(T % njobs);
+                if (jobs[j].compressor != 0 && jobs[j].mode == want_mode && k < jobs[j].win_count) { w = jobs[j].win_base + k; break; }
+            }
+            S.ticket = w;
+        }
         __syncthreads();
         const uint32_t w = S.ticket;
-        if (w >= nwin) break;
+        if (w == 0xFFFFFFFFu) break;
         if (t < (int)(sizeof(DecWin) / 4)) reinterpret_cast<uint32_t *>(&S.win)[t] = reinterpret_cast<const uint32_t *>(&wins[w])[t];
         if (t == 0) { S.fail = 0; S.fail_desc = 0; S.mismatch = 0; S.min_src = 0xFFFFFFFFu; }
         S.landed[t] = 0;
@@ -679,14 +729,14 @@ __global__ void __launch_bounds__(kExThreads, 3) snappy_execute_kernel(ChunkJob 
         // ---- stage the window (TMA bulk copy), read the entries meanwhile ---------------------------------------------
         uint32_t ent = kIndexNoEntry;
         const uint32_t staged = in_end - win.in_off < win.in_len + (uint32_t)kExLook ? in_end - win.in_off : win.in_len + (uint32_t)kExLook;
-        stage_bytes(S.cin, src + win.in_off, staged, &S.bar, t);
+        stage_bytes(S.cin + 32, src + win.in_off, staged, &S.bar, t);
         if ((uint32_t)t < nsub) ent = win.entries[t];
         if (embedded && (uint32_t)t + kExThreads < nsub_all && win.entries[t + kExThreads] != kIndexNoEntry) S.mismatch = 1;  // no starts beyond piece 255
         hap_mbar_wait(&S.bar, phase);
         phase ^= 1;
         __syncthreads();
         const uint32_t a_sh = (uint32_t)((uintptr_t)(src + win.in_off) & 15);
-        const uint8_t *cin = S.cin + a_sh;
+        const uint8_t *cin = S.cin + 32 + a_sh;
         const uint32_t wb = win.in_off;
 
         // ---- walk: every entered piece from its entry to its end ---------------------------------------------------------------

@@ -27,6 +27,9 @@ class HapB200(HapABI):
         vp, u, ul, ull_p, u_p = C.c_void_p, C.c_uint, C.c_ulong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint)
         L.HapB200Version.restype = C.c_char_p
         L.HapB200KernelLaunchCount.restype = C.c_ulonglong
+        L.HapB200SetDevice.restype = C.c_int
+        L.HapB200SetDevice.argtypes = [C.c_int]
+        L.HapB200GetDevice.restype = C.c_int
         L.HapB200SetOption.restype = C.c_int
         L.HapB200SetOption.argtypes = [C.c_int, C.c_int]
         L.HapB200SetStageTiming.restype = None

@@ -165,3 +165,41 @@ def gather_band_frames(band_frame: torch.Tensor, used: int, dst: int = 0):
     if rank != dst:
         return None
     return [bytes(parts[r][: int(lens[r].item())].cpu().numpy().tobytes()) for r in range(world)]
+
+
+# ---- a stream of frames delivered to one rank (first case; BASELINE.json configs[4]) ------------------------------
+# Every rank encodes its share of the frames; the consumer (a muxer, a file writer) sits on rank `dst`.  Frames have
+# different lengths, so the exchange is a GATHERV: one all-gather of the lengths (8 bytes per frame), then one group of
+# point-to-point transfers that move exactly the encoded bytes -- ncclSend/ncclRecv under NCCL, which on an NVSwitch box go
+# GPU to GPU over NVLink.  No padding travels (the padded all-gather of gather_encoded_frames moves world x worst-case
+# bytes to EVERY rank; this moves the sum of the real lengths to one).
+
+def gatherv_frames_to_root(local_frames: torch.Tensor, local_used: torch.Tensor, dst: int = 0, ring: torch.Tensor = None):
+    """local_frames: (n, stride) uint8 -- this rank's n encoded frames, frame i in its first local_used[i] bytes (every
+    rank passes the same n and stride).  On rank `dst`: returns (ring, lengths) where ring is a (world, n, stride) uint8
+    tensor holding rank r's frame i in ring[r, i, :lengths[r, i]] (pass `ring` to reuse a buffer) -- stream order for
+    round-robin sharding is (i, r).  Elsewhere: (None, lengths).  lengths is a (world, n) int64 CPU tensor on every
+    rank; total bytes moved over the interconnect = lengths.sum() - lengths[dst].sum()."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n, stride = int(local_frames.shape[0]), int(local_frames.shape[1])
+    lens_dev = torch.empty((world, n), dtype=torch.int64, device=local_used.device)
+    dist.all_gather_into_tensor(lens_dev.view(-1), local_used.contiguous().view(-1))
+    lengths = lens_dev.cpu()     # the message sizes must be known on the host: the one synchronisation of the step
+    ops = []
+    if rank == dst:
+        if ring is None:
+            ring = torch.empty((world, n, stride), dtype=torch.uint8, device=local_frames.device)
+        for i in range(n):
+            ring[dst, i, : int(lengths[dst, i])].copy_(local_frames[i, : int(lengths[dst, i])], non_blocking=True)
+        for r in range(world):
+            if r == dst:
+                continue
+            for i in range(n):
+                ops.append(dist.P2POp(dist.irecv, ring[r, i, : int(lengths[r, i])], r))
+    else:
+        for i in range(n):
+            ops.append(dist.P2POp(dist.isend, local_frames[i, : int(lengths[rank, i])], dst))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return (ring if rank == dst else None), lengths

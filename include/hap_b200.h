@@ -29,6 +29,13 @@ enum HapB200Codec {
 const char *HapB200Version(void);
 /* kernels launched by this library in this process so far (bench.py reports the delta) */
 unsigned long long HapB200KernelLaunchCount(void);
+/* Devices.  One process can drive every GPU of the box: a call with a device pointer among its buffers runs on that
+ * pointer's device; a call with host pointers only runs on the default device -- the device that was current in the
+ * thread that made the library's first call, or the one set here (-1: forget it).  The caller's current device is
+ * restored before a call returns.  HapB200SetDevice returns 0, or -1 for an ordinal out of range. */
+int HapB200SetDevice(int device);
+int HapB200GetDevice(void);
+
 /* Options.  HAPB200_OPTION_USE_INDEX: the decoder uses a frame's embedded fragment index when it finds one (default 1;
  * 0 = always derive the index from the Snappy streams, as for every frame another encoder wrote).
  * HAPB200_OPTION_WRITE_INDEX: the encoder adds a private "fragment index" section to the Decode Instructions container

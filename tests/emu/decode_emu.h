@@ -13,17 +13,18 @@ static inline void decode_jobs_emu(hapb200::ChunkJob *jobs, uint32_t njobs, uint
     std::vector<DecWin> wins(win_cap);
     std::vector<uint8_t> entries((size_t)win_cap * kIdxThreads, 0xEE);
     std::vector<uint32_t> done(win_cap, 0);
-    DecodeCtl ctl = {0, 0, 0, 0};
+    DecodeCtl ctl;
+    memset(&ctl, 0, sizeof ctl);
     uint32_t any_left = 0;
     HAP_LAUNCH(hap_build_windows_kernel, dim3((njobs + 127) / 128), dim3(128), 0, nullptr, jobs, njobs, use_index, wins.data(), win_cap, &ctl);
-    HAP_LAUNCH(snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), nullptr, jobs, (int)njobs, (uint32_t)kJobNeedsIndex, wins.data(),
+    HAP_LAUNCH(snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), nullptr, jobs, (int)njobs, 0u, wins.data(),
                win_cap, entries.data(), &ctl);
-    HAP_LAUNCH(snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), nullptr, jobs, wins.data(), &ctl, done.data());
+    HAP_LAUNCH(snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), nullptr, jobs, njobs, 0u, wins.data(), &ctl, done.data());
     if (use_index) {
-        HAP_LAUNCH(hap_requeue_mismatched_kernel, dim3((njobs + 127) / 128), dim3(128), 0, nullptr, jobs, njobs, &ctl, &any_left);
-        HAP_LAUNCH(snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), nullptr, jobs, (int)njobs, (uint32_t)kJobNeedsIndex, wins.data(),
+        HAP_LAUNCH(hap_requeue_mismatched_kernel, dim3((njobs + 127) / 128), dim3(128), 0, nullptr, jobs, njobs, &any_left);
+        HAP_LAUNCH(snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), nullptr, jobs, (int)njobs, 1u, wins.data(),
                    win_cap, entries.data(), &ctl);
-        HAP_LAUNCH(snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), nullptr, jobs, wins.data(), &ctl, done.data());
+        HAP_LAUNCH(snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), nullptr, jobs, njobs, 1u, wins.data(), &ctl, done.data());
     }
     if (ctl.overflow) g_decode_emu_overflow++;
     if (windows_out) { windows_out[0] = ctl.n_windows; windows_out[1] = any_left; }

@@ -43,6 +43,8 @@ static void check_stream(const std::string &name, const std::vector<uint8_t> &st
     job.index = nullptr;
     job.index_bytes = 0;
     job.mode = kJobUndecided;
+    job.win_base = 0;
+    job.win_count = 0;
     emu::g_order_mode() = mode;
     decode_jobs_emu(&job, 1, stream.size(), job.dst_bytes, 1);
     bool ok = true;

@@ -136,7 +136,7 @@ static void check(const std::string &name, const std::vector<Tex> &tex, int mode
                     if (cc == kHapChunkSnappy && !snappy_preamble(sec + t.data + in_run, sz, usz)) { ok = false; why = "preamble"; break; }
                     ChunkJob j;
                     j.src = sec + t.data + in_run; j.dst = back.data() + 32 + out_run; j.src_bytes = sz; j.dst_bytes = usz; j.compressor = cc;
-                    j.status = 99; j.index = nullptr; j.index_bytes = 0; j.mode = kJobUndecided;
+                    j.status = 99; j.index = nullptr; j.index_bytes = 0; j.mode = kJobUndecided; j.win_base = 0; j.win_count = 0;
                     uint32_t ioff = 0, ib = 0;
                     if (cc == kHapChunkSnappy && have_ix && fragment_index_record(fr.data(), ix, i, (uint32_t)t.count, (uint32_t)c, ioff, ib)) { j.index = fr.data() + ioff; j.index_bytes = ib; has_index = true; }
                     jobs.push_back(j);
@@ -151,7 +151,7 @@ static void check(const std::string &name, const std::vector<Tex> &tex, int mode
             } else {
                 ChunkJob j;
                 j.src = sec; j.dst = back.data() + 32; j.src_bytes = loc.len; j.dst_bytes = loc.len; j.compressor = kHapChunkRaw;
-                j.status = 99; j.index = nullptr; j.index_bytes = 0; j.mode = kJobUndecided;
+                j.status = 99; j.index = nullptr; j.index_bytes = 0; j.mode = kJobUndecided; j.win_base = 0; j.win_count = 0;
                 jobs.push_back(j);
                 in_sum = loc.len;
             }

@@ -159,3 +159,43 @@ def test_band_gather_and_assembly_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _gatherv_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, stride = 3, 96
+    frames = torch.zeros((n, stride), dtype=torch.uint8)
+    used = torch.zeros(n, dtype=torch.int64)
+    for i in range(n):
+        f = i * world + rank                     # round-robin stream position
+        ln = 9 + (f * 11) % 80
+        frames[i, :ln] = (torch.arange(ln) * 3 + f).to(torch.uint8)
+        used[i] = ln
+    ring, lengths = sharding.gatherv_frames_to_root(frames, used, dst=0)
+    ok = lengths.shape == (world, n)
+    if rank == 0:
+        for r in range(world):
+            for i in range(n):
+                f = i * world + r
+                ln = 9 + (f * 11) % 80
+                ok = ok and int(lengths[r, i]) == ln and torch.equal(ring[r, i, :ln], (torch.arange(ln) * 3 + f).to(torch.uint8))
+    else:
+        ok = ok and ring is None
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gatherv_to_root_world2_gloo():
+    """The stream case of SURVEY.md 8e: exact-length frames delivered to rank 0 by grouped point-to-point transfers."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 500
+    procs = [ctx.Process(target=_gatherv_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
