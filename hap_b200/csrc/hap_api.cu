@@ -31,6 +31,7 @@ std::atomic<unsigned long long> g_launches{0};
 // (hap_index.h).  g_write_index: the encoder writes that section into Complex texture sections.
 std::atomic<int> g_use_index{1};
 std::atomic<int> g_write_index{0};
+std::atomic<int> g_write_offsets{0};
 
 // Optional per-stage device timing (HapB200SetStageTiming): CUDA events around every kernel, on the
 // stream the kernel is launched on.  Off by default; bench.py turns it on for its roofline pass only.
@@ -125,6 +126,7 @@ struct DeviceGuard {
             // process-wide defaults of the two options (HapB200SetOption overrides them)
             if (const char *e = getenv("HAPB200_WRITE_INDEX")) g_write_index.store(atoi(e) != 0);
             if (const char *e = getenv("HAPB200_USE_INDEX")) g_use_index.store(atoi(e) != 0);
+            if (const char *e = getenv("HAPB200_WRITE_OFFSET_TABLE")) g_write_offsets.store(atoi(e) != 0);
         });
         if (cudaGetDevice(&saved) != cudaSuccess) { cudaGetLastError(); saved = -1; return; }
         int want = -1;
@@ -297,7 +299,8 @@ uint32_t launch_encode(const uint8_t *base, const FrameGeom &G, uint32_t frames,
     HAP_KLAUNCH(kStSnappyEncode, snappy_encode_fragments_kernel, dim3(k5_grid), dim3(kEncThreads), sizeof(EncodeSmem), st, base, G,
                 (uint32_t)nfrag, scratch.as<uint8_t>(), fsize.as<uint32_t>(), write_index ? fent.as<uint8_t>() : (uint8_t *)nullptr);
     HAP_KLAUNCH(kStPlan, hap_plan_frames_kernel, dim3(frames), dim3(kPlanThreads), 0, st, G, base, fsize.as<uint32_t>(),
-                fdst.as<uint32_t>(), fidx.as<uint32_t>(), write_index, out, out_stride, used);
+                fdst.as<uint32_t>(), fidx.as<uint32_t>(), (write_index ? kPlanWriteIndex : 0u) | (g_write_offsets.load() ? kPlanWriteOffsets : 0u), out,
+                out_stride, used);
     HAP_KLAUNCH(kStPlace, hap_place_fragments_kernel, dim3((unsigned)nfrag), dim3(kPlaceThreads), 0, st, G, base,
                 scratch.as<uint8_t>(), fsize.as<uint32_t>(), fdst.as<uint32_t>(), fidx.as<uint32_t>(),
                 write_index ? fent.as<uint8_t>() : (const uint8_t *)nullptr, out, out_stride);
@@ -482,6 +485,7 @@ int HapB200SetOption(int option, int value)
 {
     if (option == 1) { g_use_index.store(value != 0); return 0; }
     if (option == 2) { g_write_index.store(value != 0); return 0; }
+    if (option == 3) { g_write_offsets.store(value != 0); return 0; }
     return -1;
 }
 

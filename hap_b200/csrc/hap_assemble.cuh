@@ -17,6 +17,7 @@
 namespace hapb200 {
 
 constexpr int kPlanThreads = 256;
+constexpr uint32_t kPlanWriteIndex = 1, kPlanWriteOffsets = 2;
 constexpr uint32_t kPlaceRawFlag = 0x80000000u;
 
 __device__ __forceinline__ void put_section_header(uint8_t *p, uint32_t hdr, uint32_t len, uint32_t type)
@@ -68,14 +69,18 @@ __device__ __forceinline__ uint32_t plan_excl_sum(uint32_t v, uint64_t *total, u
 }
 
 // out: [frames][out_stride]; frag_size / frag_dst / frag_idx_dst: [frames][G.frags_per_frame]; out_used: [frames].
-// write_index != 0: a frame with at least one compressed chunk gets the trailing fragment index section (hap_index.h);
-// frag_idx_dst[f] then says where fragment f's entries go (0: nowhere).
+// flags & kPlanWriteIndex: a frame with at least one compressed chunk gets the trailing fragment index section
+// (hap_index.h); frag_idx_dst[f] then says where fragment f's entries go (0: nowhere).
+// flags & kPlanWriteOffsets: Complex sections carry the optional Chunk Offset Table (HapVideoDRAFT.md:126-128, honoured by
+// hap.c:697-700 and :800-803) and every chunk starts on a 16-byte boundary of the frame; the up to 15 bytes between two
+// chunks are zero.  The reference's own encoder never writes this table (hap.c:430-442), hence an option.
 __global__ void __launch_bounds__(kPlanThreads) hap_plan_frames_kernel(
     FrameGeom G, const uint8_t *__restrict__ dxt, const uint32_t *__restrict__ frag_size,
-    uint32_t *__restrict__ frag_dst, uint32_t *__restrict__ frag_idx_dst, uint32_t write_index, uint8_t *__restrict__ out,
+    uint32_t *__restrict__ frag_dst, uint32_t *__restrict__ frag_idx_dst, uint32_t flags, uint8_t *__restrict__ out,
     uint64_t out_stride, unsigned long long *__restrict__ out_used)
 {
     __shared__ uint32_t scratch[kPlanThreads / 32];
+    const uint32_t write_index = flags & kPlanWriteIndex, write_offsets = flags & kPlanWriteOffsets;
     const int t = threadIdx.x;
     const uint32_t frame = blockIdx.x;
     uint8_t *fo = out + (uint64_t)frame * out_stride;
@@ -100,14 +105,17 @@ __global__ void __launch_bounds__(kPlanThreads) hap_plan_frames_kernel(
                 uint32_t c = c0 + t, sz = 0, rec = 0;
                 if (c < k && chunk_packed_size(fs + (uint64_t)c * fpc, fpc, sec.chunk_bytes, sz) && indexed)
                     rec = chunk_index_record_bytes(fs + (uint64_t)c * fpc, fpc);
+                if (write_offsets && c + 1 < k) sz = (sz + 15u) & ~15u;   // every chunk but the last is padded to the next chunk's aligned start
                 uint64_t ts, tr;
-                plan_excl_sum(sz, &ts, scratch);
+                plan_excl_sum(c < k ? sz : 0u, &ts, scratch);
                 plan_excl_sum(rec, &tr, scratch);
                 body[si] += ts;
                 rec_total[si] += tr;
             }
-            body[si] += 4u + 5ull * k + 8ull;   // hap.c:265-275: the Decode Instructions container
-            complex_storage[si] = body[si] < (uint64_t)sec.bytes + sec.top_hdr;  // hap.c:478
+            const uint32_t di1 = 5u * k + 8u + (write_offsets ? 4u * k + 4u : 0u);   // hap.c:265-275 (+ the offset table)
+            body[si] += 4u + di1;
+            if (write_offsets) body[si] += (16u - ((running_off + sec.top_hdr + 4u + di1) & 15u)) & 15u;   // chunk 0 starts aligned too
+            complex_storage[si] = body[si] < (uint64_t)sec.bytes + sec.top_hdr && body[si] < (1ull << 31);  // hap.c:478
         }
         if (!complex_storage[si]) rec_total[si] = 0;
         sec_off[si] = running_off;
@@ -134,7 +142,7 @@ __global__ void __launch_bounds__(kPlanThreads) hap_plan_frames_kernel(
     for (uint32_t si = 0; si < G.sections; si++) {
         const SectionGeom &sec = G.s[si];
         const uint32_t k = sec.chunks, fpc = sec.frags_per_chunk, hdr = sec.top_hdr;
-        const uint32_t di = 5u * k + 8u;  // hap.c:265-275
+        const uint32_t di = 5u * k + 8u + (write_offsets ? 4u * k + 4u : 0u);  // hap.c:265-275 (+ the offset table)
         const uint32_t *fs = fs_frame + sec.frag_base;
         uint32_t *fd = fd_frame + sec.frag_base;
         uint32_t *fi = fi_frame + sec.frag_base;
@@ -142,25 +150,33 @@ __global__ void __launch_bounds__(kPlanThreads) hap_plan_frames_kernel(
         uint8_t *slots = ibody + kIndexHeaderBytes + 4u * (si ? k0 : 0u);   // this texture's record offsets
         if (complex_storage[si]) {
             uint8_t *p = so + hdr;
-            uint8_t *ctab = p + 8, *stab = p + 8 + k + 4;
+            uint8_t *ctab = p + 8, *stab = p + 8 + k + 4, *otab = stab + 4u * k + 4;
             if (t == 0) {
                 put_section_header(so, hdr, sec_len[si], (kHapComplex << 4) | sec.fmt_nibble);
                 put_section_header(p, 4, di, kSecDecodeInstructions);        // hap.c:436
                 put_section_header(p + 4, 4, k, kSecCompressorTable);        // hap.c:438
                 put_section_header(ctab + k, 4, 4u * k, kSecSizeTable);      // hap.c:440
+                if (write_offsets) put_section_header(stab + 4u * k, 4, 4u * k, kSecOffsetTable);   // HapVideoDRAFT.md:126-128
             }
-            uint32_t running = sec_off[si] + hdr + 4u + di;  // offset of chunk 0 inside the frame
+            const uint32_t data0 = sec_off[si] + hdr + 4u + di;   // "frame data": what the offset table counts from (hap.c:672)
+            uint32_t running = write_offsets ? (data0 + 15u) & ~15u : data0;  // offset of chunk 0 inside the frame
+            if (write_offsets && (uint32_t)t < running - data0) fo[data0 + t] = 0;
             for (uint32_t c0 = 0; c0 < k; c0 += kPlanThreads) {
                 uint32_t c = c0 + t, sz = 0, rec = 0;
                 bool snappy = false;
                 if (c < k) snappy = chunk_packed_size(fs + (uint64_t)c * fpc, fpc, sec.chunk_bytes, sz);
                 if (snappy && rec_total[si]) rec = chunk_index_record_bytes(fs + (uint64_t)c * fpc, fpc);
                 uint64_t ts, tr;
-                const uint32_t start = running + plan_excl_sum(sz, &ts, scratch);
+                const uint32_t szp = c >= k ? 0u : (write_offsets && c + 1 < k ? (sz + 15u) & ~15u : sz);   // with its padding
+                const uint32_t start = running + plan_excl_sum(szp, &ts, scratch);
                 const uint32_t rec_off = rec_running + plan_excl_sum(rec, &tr, scratch);
                 if (c < k) {
                     ctab[c] = snappy ? kHapChunkSnappy : kHapChunkRaw;
                     put_le32(stab + 4 * c, sz);
+                    if (write_offsets) {
+                        put_le32(otab + 4 * c, start - data0);
+                        for (uint32_t z = sz; z < szp; z++) fo[start + z] = 0;   // the gap in front of the next chunk
+                    }
                     if (index_len) put_le32(slots + 4 * c, rec ? rec_off : 0u);
                     if (snappy) {
                         uint32_t v = sec.chunk_bytes, o = start;

@@ -27,7 +27,6 @@ inline uint32_t build_frame_geom(uint32_t count, const TextureArgs *tex, FrameGe
 {
     G.sections = count;
     G.outer_hdr = 0;
-    G.pad = 0;
     uint32_t frag_base = 0;
     for (uint32_t i = 0; i < count; i++) {
         const TextureArgs &a = tex[i];
@@ -48,6 +47,7 @@ inline uint32_t build_frame_geom(uint32_t count, const TextureArgs *tex, FrameGe
             s.chunk_bytes = (uint32_t)a.bytes;
         }
         s.frags_per_chunk = (s.chunk_bytes + kFragBytes - 1) / kFragBytes;
+        s.inv_frags_per_chunk = s.frags_per_chunk <= 1 ? 0xFFFFFFFFu : (uint32_t)(0x100000000ull / s.frags_per_chunk);
         s.period_words = (a.format == HapFmt_RGB_DXT1 || a.format == HapFmt_A_RGTC1) ? 2 : 4;
         s.compress = s.want_snappy && (s.chunk_bytes % 8 == 0);
         s.frag_base = frag_base;
@@ -58,6 +58,7 @@ inline uint32_t build_frame_geom(uint32_t count, const TextureArgs *tex, FrameGe
         frag_base += (uint32_t)frags;
     }
     G.frags_per_frame = frag_base;
+    G.inv_frags_per_frame = frag_base <= 1 ? 0xFFFFFFFFu : (uint32_t)(0x100000000ull / frag_base);
     if (count == 2) {
         // hap.c:563-576 (uses the REQUESTED chunk counts)
         uint64_t worst = 0;

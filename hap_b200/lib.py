@@ -63,7 +63,7 @@ class HapB200(HapABI):
     def launches(self) -> int:
         return int(self.lib.HapB200KernelLaunchCount())
 
-    OPTION_USE_INDEX, OPTION_WRITE_INDEX = 1, 2
+    OPTION_USE_INDEX, OPTION_WRITE_INDEX, OPTION_WRITE_OFFSET_TABLE = 1, 2, 3
 
     def set_option(self, option: int, value: int) -> int:
         """OPTION_USE_INDEX: the decoder uses a frame's embedded fragment index (default on).  OPTION_WRITE_INDEX: the

@@ -45,6 +45,11 @@ int HapB200GetDevice(void);
  * Returns 0, or -1 for an unknown option. */
 #define HAPB200_OPTION_USE_INDEX 1
 #define HAPB200_OPTION_WRITE_INDEX 2
+/* HAPB200_OPTION_WRITE_OFFSET_TABLE: Complex texture sections carry the optional Chunk Offset Table (reference
+ * documentation/HapVideoDRAFT.md:126-128; honoured by the reference decoder, hap.c:697-700 and :800-803, and by FFmpeg) and
+ * every chunk starts on a 16-byte boundary of the frame, the few bytes between chunks being zero.  Default 0: the
+ * reference's encoder never writes this table and packs chunks back to back (hap.c:473). */
+#define HAPB200_OPTION_WRITE_OFFSET_TABLE 3
 int HapB200SetOption(int option, int value);
 
 /* Per-stage device timing for profiling runs: when enabled every kernel launch is bracketed by CUDA

@@ -50,11 +50,12 @@ static std::vector<uint8_t> gpu_encode(const std::vector<Tex> &tex, int mode, ui
     // a grid smaller than the fragment count, as on the device: CTAs stride over the fragments (modes alternate 1, 2, 3 CTAs)
     const unsigned k5_grid = G.frags_per_frame < (unsigned)(1 + mode % 3) ? G.frags_per_frame : (unsigned)(1 + mode % 3);
     HAP_LAUNCH(snappy_encode_fragments_kernel, dim3(k5_grid), dim3(kEncThreads), sizeof(EncodeSmem), nullptr,
-               in.data(), G, (uint32_t)G.frags_per_frame, scratch.data(), fsize.data(), write_index ? fent.data() : (uint8_t *)nullptr);
+               in.data(), G, (uint32_t)G.frags_per_frame, scratch.data(), fsize.data(), (write_index & 1) ? fent.data() : (uint8_t *)nullptr);
+    // write_index: bit 0 = fragment index, bit 1 = chunk offset table with aligned chunk starts
     HAP_LAUNCH(hap_plan_frames_kernel, dim3(1), dim3(kPlanThreads), 0, nullptr, G, in.data(), fsize.data(), fdst.data(), fidx.data(),
                write_index, out.data(), (uint64_t)cap, &used);
     HAP_LAUNCH(hap_place_fragments_kernel, dim3(G.frags_per_frame), dim3(kPlaceThreads), 0, nullptr, G, in.data(),
-               scratch.data(), fsize.data(), fdst.data(), fidx.data(), write_index ? fent.data() : (const uint8_t *)nullptr, out.data(),
+               scratch.data(), fsize.data(), fdst.data(), fidx.data(), (write_index & 1) ? fent.data() : (const uint8_t *)nullptr, out.data(),
                (uint64_t)cap);
     if (used > cap) { fprintf(stderr, "used %llu > cap %lu\n", used, cap); abort(); }
     out.resize(used);
@@ -133,21 +134,30 @@ static void check(const std::string &name, const std::vector<Tex> &tex, int mode
                 uint64_t in_run = 0, out_run = 0;
                 for (int c = 0; c < t.count; c++) {
                     uint32_t cc = sec[t.compressors + c], sz = rd_le32(sec + t.sizes + 4 * c), usz = sz;
-                    if (cc == kHapChunkSnappy && !snappy_preamble(sec + t.data + in_run, sz, usz)) { ok = false; why = "preamble"; break; }
                     ChunkJob j;
-                    j.src = sec + t.data + in_run; j.dst = back.data() + 32 + out_run; j.src_bytes = sz; j.dst_bytes = usz; j.compressor = cc;
+                    const uint64_t at = t.offsets != 0xFFFFFFFFu ? rd_le32(sec + t.offsets + 4 * c) : in_run;
+                    if (cc == kHapChunkSnappy && !snappy_preamble(sec + t.data + at, sz, usz)) { ok = false; why = "preamble"; break; }
+                    j.src = sec + t.data + at; j.dst = back.data() + 32 + out_run; j.src_bytes = sz; j.dst_bytes = usz; j.compressor = cc;
                     j.status = 99; j.index = nullptr; j.index_bytes = 0; j.mode = kJobUndecided; j.win_base = 0; j.win_count = 0;
                     uint32_t ioff = 0, ib = 0;
                     if (cc == kHapChunkSnappy && have_ix && fragment_index_record(fr.data(), ix, i, (uint32_t)t.count, (uint32_t)c, ioff, ib)) { j.index = fr.data() + ioff; j.index_bytes = ib; has_index = true; }
                     jobs.push_back(j);
                     in_run += sz; out_run += usz; in_sum += sz;
                 }
-                if (write_index && !has_index) {
+                if ((write_index & 2) && t.offsets == 0xFFFFFFFFu) { ok = false; why = "offset table missing"; break; }
+                if ((write_index & 2)) {
+                    // every chunk starts on a 16-byte boundary of the frame, gaps are zero
+                    for (int c = 0; c < t.count && ok; c++) {
+                        const uint32_t o = rd_le32(sec + t.offsets + 4 * c);
+                        if (((loc.offset + t.data + o) & 15) != 0) { ok = false; why = "chunk start not aligned"; }
+                    }
+                }
+                if ((write_index & 1) && !has_index) {
                     bool any_snappy = false;
                     for (auto &j : jobs) any_snappy = any_snappy || j.compressor == kHapChunkSnappy;
                     if (any_snappy) { ok = false; why = "index section missing"; break; }
                 }
-                if (!write_index && have_ix) { ok = false; why = "unexpected index section"; break; }
+                if (!(write_index & 1) && have_ix) { ok = false; why = "unexpected index section"; break; }
             } else {
                 ChunkJob j;
                 j.src = sec; j.dst = back.data() + 32; j.src_bytes = loc.len; j.dst_bytes = loc.len; j.compressor = kHapChunkRaw;
@@ -256,6 +266,11 @@ int main(int argc, char **argv)
             double ratio = 0, ratio_i = 0;
             check(c.name, c.tex, mode, 0, &ratio);
             check(c.name + "+index", c.tex, mode, 1, &ratio_i);
+            if (mode == 0) {   // (the chunk offset table changes host-side arithmetic only: one thread order is enough)
+                double ratio_o = 0;
+                check(c.name + "+offsets", c.tex, mode, 2, &ratio_o);
+                check(c.name + "+index+offsets", c.tex, mode, 3, &ratio_o);
+            }
             if (mode == 0) printf("  %-26s size vs oracle-encoded frame: %.3f   with fragment index: %.3f\n", c.name.c_str(), ratio, ratio_i);
         }
     g_fail += g_decode_emu_overflow;

@@ -434,3 +434,40 @@ def test_frames_with_fragment_index(index_on, w, h, codec_name, k):
         want = torch.frombuffer(bytearray(ref.decode(with_ix, i, n)[1]), dtype=torch.uint8).cuda()
         for f in range(F):
             assert torch.equal(tex[f * stride: f * stride + n], want), (i, f)
+
+
+@pytest.mark.parametrize("with_index", [0, 1])
+def test_chunk_offset_table_option(lib, with_index):
+    """HAPB200_OPTION_WRITE_OFFSET_TABLE: the optional table of HapVideoDRAFT.md:126-128 is written, chunks
+    start on 16-byte boundaries of the frame, gaps are zero; the reference (hap.c:800-803 honours the table) and this
+    decoder give the same texture as for the packed layout."""
+    import hap_b200.lib as L
+    w, h, k = 1024, 512, 6
+    codec = L.HapB200Codec_HapY
+    img = synth.frame(w, h, 9).numpy()
+    lib.set_option(lib.OPTION_WRITE_INDEX, with_index)
+    try:
+        r, plain = lib.encode_rgba(img, w, h, codec, 1, k)
+        lib.set_option(lib.OPTION_WRITE_OFFSET_TABLE, 1)
+        r2, cot = lib.encode_rgba(img, w, h, codec, 1, k)
+    finally:
+        lib.set_option(lib.OPTION_WRITE_OFFSET_TABLE, 0)
+        lib.set_option(lib.OPTION_WRITE_INDEX, 0)
+    assert r == 0 and r2 == 0 and cot != plain
+    n = lib.texture_bytes(w, h, codec)
+    ref = oracles.ref_abi() or oracles.oracle_abi()
+    want = ref.decode(plain, 0, n)
+    assert want[0] == 0
+    assert ref.decode(cot, 0, n)[:3] == want[:3]
+    assert lib.decode(cot, 0, n)[:3] == want[:3] and lib.chunk_count(cot, 0) == (0, k)
+    # layout: DI container = compressor table, size table, offset table (9k + 12 bytes); aligned chunk starts
+    di_len = int.from_bytes(cot[4:7], "little")
+    assert cot[7] == 0x01 and di_len == 9 * k + 12 and cot[8 + k + 4 + 4 * k + 4 + 3] == 0x04
+    data0 = 8 + di_len
+    otab = 8 + 4 + k + 4 + 4 * k + 4
+    sizes = [int.from_bytes(cot[8 + 4 + k + 4 + 4 * c: 8 + 4 + k + 8 + 4 * c], "little") for c in range(k)]
+    offs = [int.from_bytes(cot[otab + 4 * c: otab + 4 * c + 4], "little") for c in range(k)]
+    for c in range(k):
+        assert (data0 + offs[c]) % 16 == 0
+        if c + 1 < k:
+            assert offs[c + 1] >= offs[c] + sizes[c] and set(cot[data0 + offs[c] + sizes[c]: data0 + offs[c + 1]]) <= {0}
