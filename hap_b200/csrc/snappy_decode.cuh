@@ -452,14 +452,16 @@ __global__ void hap_requeue_mismatched_kernel(ChunkJob *jobs, uint32_t njobs, ui
 //  execute kernel
 // =====================================================================================================================
 #ifndef HAPB200_EX_MAX_ELEMS
-#define HAPB200_EX_MAX_ELEMS 2048
+#define HAPB200_EX_MAX_ELEMS 1024
 #endif
 #ifndef HAPB200_EX_TILE
-#define HAPB200_EX_TILE 32768
+#define HAPB200_EX_TILE 16384
 #endif
 #ifndef HAPB200_EX_MIN_BLOCKS
-#define HAPB200_EX_MIN_BLOCKS 3
+#define HAPB200_EX_MIN_BLOCKS 4
 #endif
+// Measured (r02c, 444 4K Hap Q frames with index): 2048 descriptors / 32 KiB tiles / 3 CTAs per SM (74 KB, 80 registers):
+// 6.40 ms; 1024 / 16 KiB / 3 CTAs: 6.26 ms; 1024 / 16 KiB / 4 CTAs per SM (54 KB, 64 registers, no spills): 5.56 ms.
 constexpr int kExThreads = 256;
 constexpr int kExMaxElems = HAPB200_EX_MAX_ELEMS;    // descriptors held in shared memory per pass
 constexpr int kExMaxIn = 32768 + 64;                 // stream bytes of one window the staging buffer holds
@@ -479,13 +481,21 @@ struct ExecSmem {
     uint8_t landed[kExThreads];                      // a chain exit lands in this sub-block
     uint32_t scratch[kExThreads / 32];
     uint32_t red[3][kExThreads / 32];
-    DecWin win;
+    // the window being worked on, two slots used alternately: thread 0 fills the slot of the next iteration while slower
+    // threads may still be reading this iteration's (some paths reach the top of the loop without passing a barrier)
+    struct Slot {
+        DecWin win;
+        uint32_t ticket;
+    } slot[2];
     hap_mbar_t bar;
-    uint32_t ticket;
-    uint32_t min_src;
-    int fail;         // walk stage
-    int fail_desc;    // descriptor stage
-    int mismatch;     // embedded index does not describe the chain
+    // per-window flags, two sets used alternately: the set of the NEXT window is cleared while this one is being worked on
+    // (clearing the current set at the top of the loop would race with threads that still test it on their way there)
+    struct Flags {
+        uint32_t min_src;
+        int fail;         // walk stage
+        int fail_desc;    // descriptor stage
+        int mismatch;     // embedded index does not describe the chain
+    } flags[2];
 };
 
 // three block reductions at once: minimum of a, minimum of b, maximum of c (two barriers)
@@ -671,10 +681,14 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
     const uint32_t max_k = ctl->max_k[pass];   // final: every kernel that lists windows ran before this one
     const uint32_t want_mode = pass == 0 ? (uint32_t)kJobReady : (uint32_t)kJobRepaired;
     const unsigned long long n_tickets = (unsigned long long)max_k * njobs;
-    if (t == 0) hap_mbar_init(&S.bar, 1);
+    if (t == 0) {
+        hap_mbar_init(&S.bar, 1);
+        for (int q = 0; q < 2; q++) { S.flags[q].min_src = 0xFFFFFFFFu; S.flags[q].fail = 0; S.flags[q].fail_desc = 0; S.flags[q].mismatch = 0; }
+    }
     uint32_t phase = 0;
     __syncthreads();
-    for (;;) {
+    for (uint32_t it = 0;; it++) {
+        ExecSmem::Flags &F = S.flags[it & 1];
         if (t == 0) {
             // the next ticket that names an existing window: window k = T / njobs of chunk T % njobs
             uint32_t w = 0xFFFFFFFFu;
@@ -684,16 +698,15 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
                 const uint32_t k = (uint32_t)(T / njobs), j = (uint32_t)(T % njobs);
                 if (jobs[j].compressor != 0 && jobs[j].mode == want_mode && k < jobs[j].win_count) { w = jobs[j].win_base + k; break; }
             }
-            S.ticket = w;
+            S.slot[it & 1].ticket = w;
+            if (w != 0xFFFFFFFFu) S.slot[it & 1].win = wins[w];   // one thread fetches the record: the CTA meets it behind the same barrier as the ticket
         }
         __syncthreads();
-        const uint32_t w = S.ticket;
+        const uint32_t w = S.slot[it & 1].ticket;
         if (w == 0xFFFFFFFFu) break;
-        if (t < (int)(sizeof(DecWin) / 4)) reinterpret_cast<uint32_t *>(&S.win)[t] = reinterpret_cast<const uint32_t *>(&wins[w])[t];
-        if (t == 0) { S.fail = 0; S.fail_desc = 0; S.mismatch = 0; S.min_src = 0xFFFFFFFFu; }
-        S.landed[t] = 0;
-        __syncthreads();
-        const DecWin win = S.win;
+        if (t == 0) { ExecSmem::Flags &N = S.flags[(it + 1) & 1]; N.min_src = 0xFFFFFFFFu; N.fail = 0; N.fail_desc = 0; N.mismatch = 0; }
+        S.landed[t] = 0;    // (written by the walk behind the staging barrier below; last read before the previous window's scans ended)
+        const DecWin win = S.slot[it & 1].win;
         if (win.kind == kWinSkip) {
             if (t == 0) hap_st_release(&done[w], 1u);
             continue;
@@ -731,7 +744,7 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
         const uint32_t staged = in_end - win.in_off < win.in_len + (uint32_t)kExLook ? in_end - win.in_off : win.in_len + (uint32_t)kExLook;
         stage_bytes(S.cin + 32, src + win.in_off, staged, &S.bar, t);
         if ((uint32_t)t < nsub) ent = win.entries[t];
-        if (embedded && (uint32_t)t + kExThreads < nsub_all && win.entries[t + kExThreads] != kIndexNoEntry) S.mismatch = 1;  // no starts beyond piece 255
+        if (embedded && (uint32_t)t + kExThreads < nsub_all && win.entries[t + kExThreads] != kIndexNoEntry) F.mismatch = 1;  // no starts beyond piece 255
         hap_mbar_wait(&S.bar, phase);
         phase ^= 1;
         __syncthreads();
@@ -760,7 +773,7 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
                 if (embedded && wr.exit > win.in_len) wr.invalid = 1;
             }
         }
-        if (wr.invalid) S.fail = 1;
+        if (wr.invalid) F.fail = 1;
         uint32_t total_e, total_o;
         const uint32_t ebase = block_excl_sum<kExThreads>(wr.count, &total_e, S.scratch);
         const uint32_t obase = block_excl_sum<kExThreads>(wr.out_bytes > 0x40000000u ? 0x40000000u : wr.out_bytes, &total_o, S.scratch);
@@ -768,17 +781,17 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
             // the entries must describe exactly the chain that starts at byte 0 of the fragment: a piece is entered if and
             // only if an exit lands in it (piece 0: the fragment's first element), at the entry's very offset
             const bool should = (uint32_t)t < nsub && (t == 0 || S.landed[t]);
-            if (should != entered) S.mismatch = 1;
-            if (t == 0 && (!entered || ent != 0)) S.mismatch = 1;
+            if (should != entered) F.mismatch = 1;
+            if (t == 0 && (!entered || ent != 0)) F.mismatch = 1;
             if (entered && !wr.invalid && wr.exit < win.in_len) {
                 uint32_t b = wr.exit >> win.sub_log2;
                 b = b < (uint32_t)kExThreads ? b : (uint32_t)kExThreads - 1;
-                if (b * sub + win.entries[b] != wr.exit) S.mismatch = 1;
+                if (b * sub + win.entries[b] != wr.exit) F.mismatch = 1;
             }
         }
-        if (t == 0 && total_o != win.out_len) S.fail = 1;
+        if (t == 0 && total_o != win.out_len) F.fail = 1;
         __syncthreads();
-        if (S.fail || S.mismatch) {
+        if (F.fail || F.mismatch) {
             if (t == 0) { job.status = embedded ? kStatusIndexMismatch : (uint32_t)HapResult_Bad_Frame; __threadfence(); hap_st_release(&done[w], 1u); }
             continue;
         }
@@ -824,7 +837,7 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
                         S.e_b[e] = 0;  // literals break same-offset runs (a copy's offset is never 0)
                         pos += hdr + len;
                     } else {
-                        if (aux == 0 || aux > o) S.fail_desc = 1;  // offset 0 or before the start of the output
+                        if (aux == 0 || aux > o) F.fail_desc = 1;  // offset 0 or before the start of the output
                         else if (o - aux < msrc) msrc = o - aux;
                         S.e_a[e] = aux >= len ? (kSrcOut | (o - aux)) : (kSrcRun | aux);
                         S.e_b[e] = aux;  // the offset, for run detection below; becomes the run base afterwards
@@ -833,10 +846,10 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
                     o += len;
                     e++;
                 }
-                if (!waited && msrc < win.out_off) atomicMin(&S.min_src, msrc);
+                if (!waited && msrc < win.out_off) atomicMin(&F.min_src, msrc);
             }
             __syncthreads();
-            if (S.fail_desc) { bad = true; break; }
+            if (F.fail_desc) { bad = true; break; }
 
             // ---- same-offset runs: a copy with the offset of the copy right before it continues that copy's
             //      match, so it is a periodic fill of the run head's base period, independent of its neighbours --
@@ -904,8 +917,8 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
             // ---- earlier windows of the chunk this window's copies read (on-the-fly index only): wait for them once ----
             if (!waited) {
                 waited = true;
-                if (t == 0 && S.min_src < win.out_off) {
-                    const uint32_t need = S.min_src;
+                if (t == 0 && F.min_src < win.out_off) {
+                    const uint32_t need = F.min_src;
                     for (uint32_t j = w; j > win.first;) {
                         j--;
                         const uint32_t jo = wins[j].out_off, jl = wins[j].out_len;
@@ -959,7 +972,7 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
                     int pending = 0;
                     for (uint32_t g = t; g < ngroups; g += kExThreads)
                         if (S.gdone[g] == 0 && !assemble_group(S, C, g, round)) pending = 1;
-                    if (round >= 65000u) { S.fail_desc = 1; pending = 0; }   // (a dependency chain deeper than any window has groups)
+                    if (round >= 65000u) { F.fail_desc = 1; pending = 0; }   // (a dependency chain deeper than any window has groups)
                     if (!__syncthreads_or(pending)) break;
                 }
             }
@@ -968,7 +981,7 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
         }
         __syncthreads();
         if (t == 0) {
-            if (bad || S.fail_desc) job.status = embedded ? kStatusIndexMismatch : (uint32_t)HapResult_Bad_Frame;
+            if (bad || F.fail_desc) job.status = embedded ? kStatusIndexMismatch : (uint32_t)HapResult_Bad_Frame;
             __threadfence();
             hap_st_release(&done[w], 1u);
         }

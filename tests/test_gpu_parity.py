@@ -442,7 +442,7 @@ def test_chunk_offset_table_option(lib, with_index):
     start on 16-byte boundaries of the frame, gaps are zero; the reference (hap.c:800-803 honours the table) and this
     decoder give the same texture as for the packed layout."""
     import hap_b200.lib as L
-    w, h, k = 1024, 512, 6
+    w, h, k = 1024, 512, 8
     codec = L.HapB200Codec_HapY
     img = synth.frame(w, h, 9).numpy()
     lib.set_option(lib.OPTION_WRITE_INDEX, with_index)
