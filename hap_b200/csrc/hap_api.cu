@@ -358,13 +358,16 @@ uint32_t launch_block_decode(const uint8_t *blocks, const uint8_t *alpha, uint32
 // Everything after the jobs exist (device array): windows, on-the-fly index, execute, repair of chunks whose embedded
 // index did not hold up.  in_bound / out_bound: upper bounds of the jobs' total compressed / decoded bytes (they size the
 // window list; a list that turns out too short makes the affected chunks report Internal_Error, never overruns).
-uint32_t launch_decode_jobs(ChunkJob *jobs, uint32_t njobs, uint64_t in_bound, uint64_t out_bound, cudaStream_t st)
+uint32_t launch_decode_jobs(ChunkJob *jobs, uint32_t njobs, uint64_t in_bound, uint64_t out_bound, cudaStream_t st, bool may_have_index = true)
 {
-    const uint64_t cap64 = in_bound / kIdxWin + out_bound / kIndexFragBytes + 3ull * njobs + 16;
+    // windows: up to kIdxParts per 16 KiB of stream from the index kernel (twice: a chunk may be indexed again by the repair
+    // pass), one per fragment of an indexed chunk, one per 64 KiB of a verbatim chunk
+    const uint64_t slots64 = 2 * (in_bound / kIdxWin + njobs) + 16;
+    const uint64_t cap64 = kIdxParts * slots64 + out_bound / kIndexFragBytes + 2ull * njobs + 16;
     if (cap64 >= (1ull << 31)) return HapResult_Bad_Arguments;
-    const uint32_t win_cap = (uint32_t)cap64;
+    const uint32_t win_cap = (uint32_t)cap64, entry_slots = (uint32_t)slots64;
     DevBuf wins(st), entries(st), done(st), ctl(st);
-    if (!wins.alloc((size_t)win_cap * sizeof(DecWin)) || !entries.alloc((size_t)win_cap * kIdxThreads) || !done.alloc((size_t)win_cap * 4) ||
+    if (!wins.alloc((size_t)win_cap * sizeof(DecWin)) || !entries.alloc((size_t)entry_slots * kIdxThreads) || !done.alloc((size_t)win_cap * 4) ||
         !ctl.alloc(sizeof(DecodeCtl) + 16)) {
         cudaGetLastError();
         return HapResult_Internal_Error;
@@ -379,14 +382,14 @@ uint32_t launch_decode_jobs(ChunkJob *jobs, uint32_t njobs, uint64_t in_bound, u
     HAP_KLAUNCH(kStWindows, hap_build_windows_kernel, dim3((njobs + 127) / 128), dim3(128), 0, st, jobs, njobs, (uint32_t)g_use_index.load(),
                 wins.as<DecWin>(), win_cap, c);
     HAP_KLAUNCH(kStSnappyIndex, snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), st, jobs, (int)njobs, 0u,
-                wins.as<DecWin>(), win_cap, entries.as<uint8_t>(), c);
+                wins.as<DecWin>(), win_cap, entries.as<uint8_t>(), entry_slots, c);
     HAP_KLAUNCH(kStSnappyDecode, snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), st, jobs, njobs, 0u, wins.as<DecWin>(), c,
                 done.as<uint32_t>());
-    if (g_use_index.load()) {
+    if (g_use_index.load() && may_have_index) {
         // chunks whose embedded index did not describe their stream: decode them again as if they had none
         HAP_KLAUNCH(kStWindows, hap_requeue_mismatched_kernel, dim3((njobs + 127) / 128), dim3(128), 0, st, jobs, njobs, any_left);
         HAP_KLAUNCH(kStSnappyIndex, snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), st, jobs, (int)njobs, 1u,
-                    wins.as<DecWin>(), win_cap, entries.as<uint8_t>(), c);
+                    wins.as<DecWin>(), win_cap, entries.as<uint8_t>(), entry_slots, c);
         HAP_KLAUNCH(kStSnappyDecode, snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), st, jobs, njobs, 1u, wins.as<DecWin>(),
                     c, done.as<uint32_t>());
     }
@@ -825,7 +828,7 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
         }
         if (!djobs.alloc(jobs.size() * sizeof(ChunkJob)) ||
             cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(ChunkJob), cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
-        r = launch_decode_jobs(djobs.as<ChunkJob>(), (uint32_t)jobs.size(), in_sum, produced, st);
+        r = launch_decode_jobs(djobs.as<ChunkJob>(), (uint32_t)jobs.size(), in_sum, produced, st, any_index);   // no index in the frame: no repair pass to launch
         if (r != HapResult_No_Error) return r;
         if (compressor == kHapComplex && jobs.size() > 1) {
             WorkState ws;

@@ -66,10 +66,11 @@ struct DecWin {                // one unit of work of the execute kernel
 };
 struct DecodeCtl {
     uint32_t n_windows;        // windows in the list (device-side counter)
+    uint32_t n_entry_slots;    // 256-entry slots of the on-the-fly index handed out so far
     uint32_t overflow;         // a chunk did not fit the list (cannot happen with the host's sizing; checked)
     uint32_t ticket[2];        // per execute pass: next ticket.  Ticket T = window (T / njobs) of chunk (T % njobs): the
     uint32_t max_k[2];         //   k-th windows of ALL chunks come before any (k+1)-th, so that a window rarely has to wait for
-    uint32_t pad[2];           //   its predecessor and 444 resident CTAs work on 444 different chunks.  max_k: most windows any chunk has.
+    uint32_t pad[1];           //   its predecessor and 444 resident CTAs work on 444 different chunks.  max_k: most windows any chunk has.
 };
 
 constexpr uint32_t kSrcIn = 0u << 30, kSrcOut = 1u << 30, kSrcRun = 2u << 30, kSrcMask = 3u << 30, kPosMask = (1u << 30) - 1;
@@ -159,12 +160,15 @@ constexpr uint32_t kFarSlots = 4;                    //   entry i of the sub-blo
 constexpr uint32_t kExitFarBase = 191;               // kExitFarBase + o (o = 0..63): the same, but the far list was full: the literal's
                                                      // header sits at offset o of the sub-block; its end is read from that header
 constexpr uint32_t kExitInvalid = 255;               // the chain runs into an invalid element header
+constexpr uint32_t kIdxParts = 4;                    // a 16 KiB window with many elements is listed as up to 4 execute windows ...
+constexpr uint32_t kIdxPartElems = 800;              // ... of about this many elements each (the execute kernel holds 1024 per pass)
 
 struct IndexSmem {
     uint8_t cin[2][kIdxWin + kIdxLook + 32];         // staged windows (double buffered), cin[b][a + i] = byte i of the window
     uint8_t tbl[kIdxSub * kTblStride];               // tbl[o][t]: where the chain entering sub-block t at offset o leaves it
     uint16_t entry[kIdxThreads];                     // true entry offset of each sub-block, 0xFFFF = no element starts there
     uint32_t far[kFarSlots][kIdxThreads];            // window-relative positions long literals of a sub-block lead to
+    uint32_t split_sub[kIdxParts + 1], split_out[kIdxParts + 1];   // sub-block / output offset where part q of the window starts
     uint32_t scratch[kIdxThreads / 32];
     hap_mbar_t bar[2];
     unsigned long long saddr_box;
@@ -172,11 +176,12 @@ struct IndexSmem {
     int fail;
 };
 
-// jobs with mode == kJobNeedsIndex are indexed: entries (one byte per 64 stream bytes) and one DecWin per 16 KiB of stream
-// are appended to the lists; the job then waits for execute pass `pass` (0: kJobReady, 1: kJobRepaired).
-// entries_pool: [win_cap][256].
+// jobs with mode == kJobNeedsIndex are indexed: entries (one byte per 64 stream bytes) and one to kIdxParts DecWin per 16 KiB
+// of stream are appended to the lists; the job then waits for execute pass `pass` (0: kJobReady, 1: kJobRepaired).
+// entries_pool: [entry_slots][256], one slot per 16 KiB of stream.
 __global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *jobs, int njobs, uint32_t pass, DecWin *wins,
-                                                                      uint32_t win_cap, uint8_t *entries_pool, DecodeCtl *ctl)
+                                                                      uint32_t win_cap, uint8_t *entries_pool, uint32_t entry_slots,
+                                                                      DecodeCtl *ctl)
 {
     HAP_DYN_SMEM(smem_raw);
     IndexSmem &S = *reinterpret_cast<IndexSmem *>(smem_raw);
@@ -195,12 +200,14 @@ __global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *
         const uint32_t pre = read_preamble(src, n, v);
         S.fail = (pre == 0 || v != (uint64_t)expected) ? 1 : 0;
         S.next_rel = pre;
-        uint32_t base = 0;
+        uint32_t base = 0, base_e = 0;
         if (!S.fail) {
-            base = atomicAdd(&ctl->n_windows, nwin);
-            if (base + nwin > win_cap || base + nwin < base) { S.fail = 2; atomicExch(&ctl->overflow, 1u); }
+            base = atomicAdd(&ctl->n_windows, kIdxParts * nwin);
+            base_e = atomicAdd(&ctl->n_entry_slots, nwin);
+            if (base + kIdxParts * nwin > win_cap || base + kIdxParts * nwin < base || base_e + nwin > entry_slots) { S.fail = 2; atomicExch(&ctl->overflow, 1u); }
         }
         S.scratch[0] = base;
+        S.scratch[1] = base_e;
         hap_mbar_init(&S.bar[0], 1);
         hap_mbar_init(&S.bar[1], 1);
     }
@@ -209,8 +216,8 @@ __global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *
         if (t == 0) { job.status = S.fail == 2 ? HapResult_Internal_Error : HapResult_Bad_Frame; job.mode = kJobFinished; job.win_count = 0; }
         return;
     }
-    const uint32_t base = S.scratch[0];
-    if (t == 0) { job.win_base = base; job.win_count = nwin; atomicMax(&ctl->max_k[pass], nwin); }
+    const uint32_t base = S.scratch[0], base_e = S.scratch[1];
+    uint32_t emitted = 0;     // execute windows listed so far (thread 0 keeps the count)
     const uint32_t a = (uint32_t)((uintptr_t)src & 15);   // the same for every window: windows are 16 KiB apart
     __syncthreads();
 
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *
         }
         __syncthreads();
         // ---- (c) every entered sub-block adds up the output of the elements that start in it ----------------------------
-        uint32_t out_bytes = 0;
+        uint32_t out_bytes = 0, count = 0;
         int invalid = 0;
         const uint32_t ent = S.entry[t];
         if (ent != 0xFFFFu) {
@@ -319,42 +326,55 @@ __global__ void __launch_bounds__(kIdxThreads, 4) snappy_index_kernel(ChunkJob *
                 uint32_t len, aux, hdr, kind;
                 if (!read_element_header(cin + pos, wpos + pos, n, len, aux, hdr, kind)) { invalid = 1; break; }
                 out_bytes += len;                      // (cannot wrap: <= 64 elements of <= 2^30 + ... checked against `expected` below)
+                count++;
                 pos += hdr + (kind == 0 ? len : 0);
             }
         }
-        uint32_t total_o;
-        block_excl_sum<kIdxThreads>(out_bytes > 0x40000000u ? 0x40000000u : out_bytes, &total_o, S.scratch);
+        uint32_t total_o, total_e;
+        const uint32_t obase = block_excl_sum<kIdxThreads>(out_bytes > 0x40000000u ? 0x40000000u : out_bytes, &total_o, S.scratch);
+        const uint32_t ebase = block_excl_sum<kIdxThreads>(count, &total_e, S.scratch);
         if (invalid) S.fail = 1;
         if (t == 0 && d0 + total_o > (uint64_t)expected) S.fail = 1;
+        // A window with many elements is listed as several execute windows over consecutive sub-block ranges, so that each
+        // fits the execute kernel's descriptor arrays in one pass and more CTAs share the work: part q starts behind the
+        // sub-block in which the (q * total_e / parts)-th element starts.
+        const uint32_t parts = total_e <= kIdxPartElems ? 1u : ((total_e + kIdxPartElems - 1) / kIdxPartElems < kIdxParts ? (total_e + kIdxPartElems - 1) / kIdxPartElems : kIdxParts);
+        for (uint32_t q = 1; q < parts; q++) {
+            const uint32_t thr = (uint32_t)(((unsigned long long)total_e * q) / parts);    // 0 < thr < total_e
+            if (ebase < thr && thr <= ebase + count) { S.split_sub[q] = (uint32_t)t + 1; S.split_out[q] = obase + out_bytes; }
+        }
         __syncthreads();
         if (S.fail) break;
-        entries_pool[(size_t)(base + k) * kIdxThreads + t] = ent == 0xFFFFu ? (uint8_t)kIndexNoEntry : (uint8_t)ent;
+        entries_pool[(size_t)(base_e + k) * kIdxThreads + t] = ent == 0xFFFFu ? (uint8_t)kIndexNoEntry : (uint8_t)ent;
         if (t == 0) {
-            DecWin w;
-            w.job = blockIdx.x;
-            w.kind = kWinSnappy;
-            w.in_off = wpos;
-            w.in_len = wl;
-            w.out_off = (uint32_t)d0;
-            w.out_len = total_o;
-            w.entries = entries_pool + (size_t)(base + k) * kIdxThreads;
-            w.sub_log2 = 6;
-            w.first = base;
-            wins[base + k] = w;
+            const uint32_t nsub = (wl + kIdxSub - 1) / kIdxSub;
+            S.split_sub[0] = 0; S.split_out[0] = 0;
+            S.split_sub[parts] = nsub; S.split_out[parts] = total_o;
+            for (uint32_t q = 0; q < parts; q++) {
+                DecWin w;
+                w.job = blockIdx.x;
+                w.kind = kWinSnappy;
+                w.in_off = wpos + S.split_sub[q] * kIdxSub;
+                w.in_len = (q + 1 == parts ? wl : S.split_sub[q + 1] * kIdxSub) - S.split_sub[q] * kIdxSub;
+                w.out_off = (uint32_t)d0 + S.split_out[q];
+                w.out_len = S.split_out[q + 1] - S.split_out[q];
+                w.entries = entries_pool + (size_t)(base_e + k) * kIdxThreads + S.split_sub[q];
+                w.sub_log2 = 6;
+                w.first = base;
+                wins[base + emitted + q] = w;
+            }
+            emitted += parts;
         }
         d0 += total_o;
     }
-    if (k < nwin || d0 != (uint64_t)expected) {
-        // invalid stream: the windows written so far stay (they decode what was valid), the rest of the range is skipped
-        for (uint32_t r = k + t; r < nwin; r += kIdxThreads) {
-            DecWin w;
-            w.job = blockIdx.x; w.kind = kWinSkip; w.in_off = 0; w.in_len = 0; w.out_off = 0; w.out_len = 0;
-            w.entries = nullptr; w.sub_log2 = 6; w.first = base;
-            wins[base + r] = w;
-        }
-        if (t == 0) job.status = HapResult_Bad_Frame;
+    if (t == 0) {
+        // an invalid stream keeps the windows listed so far (they decode what was valid) and reports Bad_Frame
+        if (k < nwin || d0 != (uint64_t)expected) job.status = HapResult_Bad_Frame;
+        job.win_base = base;
+        job.win_count = emitted;
+        atomicMax(&ctl->max_k[pass], emitted);
+        job.mode = done_mode;
     }
-    if (t == 0) job.mode = done_mode;
 }
 
 // =====================================================================================================================

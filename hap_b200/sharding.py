@@ -174,12 +174,15 @@ def gather_band_frames(band_frame: torch.Tensor, used: int, dst: int = 0):
 # GPU to GPU over NVLink.  No padding travels (the padded all-gather of gather_encoded_frames moves world x worst-case
 # bytes to EVERY rank; this moves the sum of the real lengths to one).
 
-def gatherv_frames_to_root(local_frames: torch.Tensor, local_used: torch.Tensor, dst: int = 0, ring: torch.Tensor = None):
+def gatherv_frames_to_root(local_frames: torch.Tensor, local_used: torch.Tensor, dst: int = 0, ring: torch.Tensor = None,
+                           wait: bool = True):
     """local_frames: (n, stride) uint8 -- this rank's n encoded frames, frame i in its first local_used[i] bytes (every
     rank passes the same n and stride).  On rank `dst`: returns (ring, lengths) where ring is a (world, n, stride) uint8
     tensor holding rank r's frame i in ring[r, i, :lengths[r, i]] (pass `ring` to reuse a buffer) -- stream order for
     round-robin sharding is (i, r).  Elsewhere: (None, lengths).  lengths is a (world, n) int64 CPU tensor on every
-    rank; total bytes moved over the interconnect = lengths.sum() - lengths[dst].sum()."""
+    rank; total bytes moved over the interconnect = lengths.sum() - lengths[dst].sum().
+    wait=False returns (ring, lengths, works) without waiting for the transfers: the caller overlaps them with the next
+    batch's encode and calls w.wait() on every work before it reuses `local_frames` / reads `ring`."""
     world, rank = dist.get_world_size(), dist.get_rank()
     n, stride = int(local_frames.shape[0]), int(local_frames.shape[1])
     lens_dev = torch.empty((world, n), dtype=torch.int64, device=local_used.device)
@@ -199,7 +202,9 @@ def gatherv_frames_to_root(local_frames: torch.Tensor, local_used: torch.Tensor,
     else:
         for i in range(n):
             ops.append(dist.P2POp(dist.isend, local_frames[i, : int(lengths[rank, i])], dst))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
+    works = dist.batch_isend_irecv(ops) if ops else []
+    if not wait:
+        return (ring if rank == dst else None), lengths, works
+    for w in works:
+        w.wait()
     return (ring if rank == dst else None), lengths

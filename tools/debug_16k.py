@@ -6,6 +6,9 @@ from hap_b200 import synth
 from hap_b200.lib import HapB200Codec_HapY
 lib = hap_b200.load()
 W = H = 16384
+INDEX = int(os.environ.get("DEBUG_INDEX", "1"))
+lib.set_option(lib.OPTION_WRITE_INDEX, INDEX)
+print("write index", INDEX, flush=True)
 for F in (1, 3):
     dev = torch.device("cuda")
     rgba = torch.empty((F, H, W, 4), dtype=torch.uint8, device=dev)
@@ -25,9 +28,14 @@ for F in (1, 3):
     tu = torch.zeros(F, dtype=torch.int64, device=dev)
     tf = torch.zeros(F, dtype=torch.int32, device=dev)
     res = torch.full((F,), 9, dtype=torch.int32, device=dev)
-    r = lib.decode_batch(frames.data_ptr(), F, cap, used.data_ptr(), 0, 64, tex.data_ptr(), n, tu.data_ptr(), tf.data_ptr(), res.data_ptr())
-    torch.cuda.synchronize()
-    print(" decode r", r, "res", res.tolist(), "used", tu.tolist(), "fmt", tf.tolist(), flush=True)
+    st = torch.cuda.Stream()
+    for rep in range(3):
+        tu.zero_(); res.fill_(9)
+        torch.cuda.synchronize()
+        r = lib.decode_batch(frames.data_ptr(), F, cap, used.data_ptr(), 0, 64, tex.data_ptr(), n, tu.data_ptr(), tf.data_ptr(), res.data_ptr(),
+                             stream=st.cuda_stream if rep else None)
+        torch.cuda.synchronize()
+        print(" decode rep", rep, "r", r, "res", res.tolist(), "used", tu.tolist(), "fmt", tf.tolist(), flush=True)
     blocks = torch.zeros(n, dtype=torch.uint8, device=dev)
     for f in range(F):
         lib.block_encode_batch(rgba[f].data_ptr(), 1, 4 * W * H, W, H, HapB200Codec_HapY, blocks.data_ptr(), n)
