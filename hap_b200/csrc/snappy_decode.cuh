@@ -691,6 +691,23 @@ __device__ __forceinline__ WalkResult walk_piece(const uint8_t *cin, uint32_t wb
     return r;
 }
 
+// The next ticket that names an existing window (window k = T / njobs of chunk T % njobs) and that window's record, fetched
+// by thread 0 one window AHEAD, right after the current window's bulk copy has been issued: the atomic and the global
+// loads then overlap the copy instead of standing alone in front of a barrier.  (Not inlined: one thread's cold path.)
+__device__ __noinline__ void fetch_next_window(const ChunkJob *jobs, uint32_t njobs, uint32_t pass, uint32_t want_mode, unsigned long long n_tickets,
+                                               const DecWin *wins, DecodeCtl *ctl, DecWin *win_out, uint32_t *ticket_out)
+{
+    uint32_t w = 0xFFFFFFFFu;
+    for (;;) {
+        const unsigned long long T = atomicAdd(&ctl->ticket[pass], 1u);
+        if (T >= n_tickets) break;
+        const uint32_t k = (uint32_t)(T / njobs), j = (uint32_t)(T % njobs);
+        if (jobs[j].compressor != 0 && jobs[j].mode == want_mode && k < jobs[j].win_count) { w = jobs[j].win_base + k; break; }
+    }
+    *ticket_out = w;
+    if (w != 0xFFFFFFFFu) *win_out = wins[w];
+}
+
 // pass 0 executes the chunks in mode kJobReady, pass 1 (repair) those in mode kJobRepaired.
 __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_execute_kernel(ChunkJob *jobs, uint32_t njobs, uint32_t pass, const DecWin *wins,
                                                                        DecodeCtl *ctl, uint32_t *done)
@@ -707,20 +724,10 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
     }
     uint32_t phase = 0;
     __syncthreads();
+    auto fetch_window = [&](uint32_t slot) { fetch_next_window(jobs, njobs, pass, want_mode, n_tickets, wins, ctl, &S.slot[slot & 1].win, &S.slot[slot & 1].ticket); };
+    if (t == 0) fetch_window(0);
     for (uint32_t it = 0;; it++) {
         ExecSmem::Flags &F = S.flags[it & 1];
-        if (t == 0) {
-            // the next ticket that names an existing window: window k = T / njobs of chunk T % njobs
-            uint32_t w = 0xFFFFFFFFu;
-            for (;;) {
-                const unsigned long long T = atomicAdd(&ctl->ticket[pass], 1u);
-                if (T >= n_tickets) break;
-                const uint32_t k = (uint32_t)(T / njobs), j = (uint32_t)(T % njobs);
-                if (jobs[j].compressor != 0 && jobs[j].mode == want_mode && k < jobs[j].win_count) { w = jobs[j].win_base + k; break; }
-            }
-            S.slot[it & 1].ticket = w;
-            if (w != 0xFFFFFFFFu) S.slot[it & 1].win = wins[w];   // one thread fetches the record: the CTA meets it behind the same barrier as the ticket
-        }
         __syncthreads();
         const uint32_t w = S.slot[it & 1].ticket;
         if (w == 0xFFFFFFFFu) break;
@@ -728,7 +735,7 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
         S.landed[t] = 0;    // (written by the walk behind the staging barrier below; last read before the previous window's scans ended)
         const DecWin win = S.slot[it & 1].win;
         if (win.kind == kWinSkip) {
-            if (t == 0) hap_st_release(&done[w], 1u);
+            if (t == 0) { hap_st_release(&done[w], 1u); fetch_window(it + 1); }
             continue;
         }
         ChunkJob &job = jobs[win.job];
@@ -747,6 +754,7 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
             } else {
                 for (uint32_t i = t; i < win.in_len; i += kExThreads) d[i] = s[i];
             }
+            if (t == 0) fetch_window(it + 1);
             continue;   // nobody waits for a verbatim window
         }
         const bool embedded = win.first == kNoDeps;     // entries come from the frame: nothing in them is trusted
@@ -756,13 +764,14 @@ __global__ void __launch_bounds__(kExThreads, HAPB200_EX_MIN_BLOCKS) snappy_exec
         const bool fits = win.in_len <= (uint32_t)kExMaxIn && win.in_off <= in_end && win.in_len <= in_end - win.in_off &&
                           win.out_off <= expected && win.out_len <= expected - win.out_off;
         if (!fits) {   // (uniform: every thread computed it from the same window and chunk records)
-            if (t == 0) { job.status = embedded ? kStatusIndexMismatch : (uint32_t)HapResult_Bad_Frame; __threadfence(); hap_st_release(&done[w], 1u); }
+            if (t == 0) { job.status = embedded ? kStatusIndexMismatch : (uint32_t)HapResult_Bad_Frame; __threadfence(); hap_st_release(&done[w], 1u); fetch_window(it + 1); }
             continue;
         }
         // ---- stage the window (TMA bulk copy), read the entries meanwhile ---------------------------------------------
         uint32_t ent = kIndexNoEntry;
         const uint32_t staged = in_end - win.in_off < win.in_len + (uint32_t)kExLook ? in_end - win.in_off : win.in_len + (uint32_t)kExLook;
         stage_bytes(S.cin + 32, src + win.in_off, staged, &S.bar, t);
+        if (t == 0) fetch_window(it + 1);
         if ((uint32_t)t < nsub) ent = win.entries[t];
         if (embedded && (uint32_t)t + kExThreads < nsub_all && win.entries[t + kExThreads] != kIndexNoEntry) F.mismatch = 1;  // no starts beyond piece 255
         hap_mbar_wait(&S.bar, phase);
