@@ -250,6 +250,9 @@ class Roundtrip:
         self.tex_used = torch.zeros(frames, dtype=torch.int64, device=dev)
         self.fmts = torch.zeros(frames, dtype=torch.int32, device=dev)
         self.res = torch.zeros(frames, dtype=torch.int32, device=dev)
+        # the tensors above were filled on torch's current stream; the library calls run on side streams that do not wait
+        # for it (a 16K batch was encoded before its own zero-fills had landed: lengths read back as 0)
+        torch.cuda.synchronize(dev)
 
     def encode(self, st):
         r = self.lib.encode_rgba_batch(self.rgba.data_ptr(), self.F, self.rgba_bytes, self.w, self.h, self.codec, 1, self.chunks,

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """TEST INFRASTRUCTURE (it lives under tests/ because it drives the reference build, which only tests may touch).
-How fast does K7 decode frames made by the REFERENCE encoder (unmodified hap.c + Google Snappy)?
+How fast do the decode kernels take frames made by the REFERENCE encoder (unmodified hap.c + Google Snappy)?
 bench.py times streams from our own encoder; players mostly meet files written by others.  Run on the GPU box:
 
     python tests/measure_ref_decode.py [--frames 16] > gpurun_out/ref_decode.json
@@ -77,13 +77,17 @@ def main():
         e1.record(st)
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    ph = lib.decode_phase_cycles(reset=True)
-    tot = max(sum(ph.values()), 1)
-    phase_share = {k: round(v / tot, 4) for k, v in ph.items()}
-    counts = getattr(lib, 'last_decode_counts', None)
-    print(json.dumps({"what": "K7 on reference-encoded 4K Hap Q frames (Google Snappy), device-resident batch",
+    lib.set_stage_timing(True)
+    lib.stage_times()
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            run()
+    stages = {k: v[0] / 3 for k, v in lib.stage_times().items() if v[0] > 0}
+    lib.set_stage_timing(False)
+    print(json.dumps({"what": "decode of reference-encoded 4K Hap Q frames (Google Snappy), device-resident batch",
                       "frames": F, "chunks": K, "ms_per_batch": ms, "ratio": float(used.double().mean()) / n,
-                      "texture_GBps": F * n / ms / 1e6, "rgba_equiv_GBps": F * 4 * W * H / ms / 1e6, "phase_share": phase_share, "counts_over_8_batches": counts}))
+                      "texture_GBps": F * n / ms / 1e6, "rgba_equiv_GBps": F * 4 * W * H / ms / 1e6, "stage_ms_per_batch": stages,
+                      "stream_elements_of_one_chunk": stats}))
 
 
 if __name__ == "__main__":
