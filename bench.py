@@ -509,6 +509,36 @@ def run_gpu_arm(args, rank, local_rank, world):
         del host_rgba, host_frame, host_tex, host_dxt
         pool.shutdown()
 
+    # ---- N > 1 only, outside the timed region: the one step of a multi-GPU deployment that does cross GPUs -- delivering the
+    #      encoded frames to the rank where the consumer sits (sharding.gatherv_frames_to_root: all-gather of the lengths +
+    #      grouped ncclSend/ncclRecv of exactly the encoded bytes, NVLink).  64 frames of the batch per rank. ------------------
+    delivery = None
+    if world > 1 and not args.profile:
+        from hap_b200 import sharding
+        FD = min(F, 64)
+        fview = frames_buf[0].view(F, A.cap)[:FD]
+        uview = used[0][:FD]
+        ring = torch.empty((world, FD, A.cap), dtype=torch.uint8, device=dev) if rank == 0 else None
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                _, lengths = sharding.gatherv_frames_to_root(fview, uview, 0, ring)
+            barrier()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record(stream)
+            for _ in range(3):
+                _, lengths = sharding.gatherv_frames_to_root(fview, uview, 0, ring)
+            d1.record(stream)
+            barrier()
+            dms = torch.tensor([d0.elapsed_time(d1) / 3], dtype=torch.float64, device=dev)
+            dist.all_reduce(dms, op=dist.ReduceOp.MAX)
+        moved = int(lengths.sum() - lengths[0].sum())
+        if rank == 0:
+            ok = all(torch.equal(ring[r, i, : int(lengths[r, i])][:64], ring[r, i, :64]) for r in range(world) for i in (0, FD - 1))
+            delivery = {"what": f"{FD} encoded frames per rank delivered to rank 0: all-gather of lengths + grouped ncclSend/ncclRecv (gatherv), device to device",
+                        "ms": float(dms.item()), "nvlink_bytes": moved, "nvlink_GBps_into_rank0": moved / (float(dms.item()) * 1e-3) / 1e9,
+                        "frames_per_s": world * FD / (float(dms.item()) * 1e-3), "ok": bool(ok)}
+        del ring
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -560,6 +590,8 @@ def run_gpu_arm(args, rank, local_rank, world):
                         "roofline_frac_frame_plus_texture": F * (mean_frame + DXT_BYTES) / dec_ms / 1e6 / peak, "target": 0.80}}
 
     extra = {}
+    if delivery is not None:
+        extra["delivery_to_rank0"] = delivery
     if not args.no_index:
         lib.set_option(lib.OPTION_USE_INDEX, 0)
         ms_noix = time_on_stream(torch, stream, lambda: decode_from(0, sp), 3)
