@@ -180,6 +180,34 @@ HAP_HD void snap_pair(float a, float b, float off, float A2, float B2, float AB,
     gb_out = (uint32_t)(int)gb;
 }
 
+// ---- endpoint refinement where the grid is coarse against the data ---------------------------------------------
+// snap_pair scores grid candidates with the clusters of the unquantised fit held fixed.  That is right while the
+// grid step is small against the block's extent; when the Co' endpoints lie less than one 5-bit cell (8.2 storage
+// units) apart, putting them on the grid stretches or collapses the segment so much that texels change cluster, and the
+// fixed-partition score picks the wrong candidate about half the time (-0.47 dB on slow colour ramps against the
+// oracle's search over all partitions).  There, the four floor/ceil candidates of the Co' pair are scored by their TRUE
+// error instead: every texel re-assigned to the nearest of the candidate's four palette points.
+//   sum |x - p0 - r e|^2 = sum |x - p0|^2 + |e|^2 sum r (r - 2u),  u = (x - p0).e / |e|^2,  r = round(3 sat(u)) / 3:
+// the first sum follows from the block moments, the second costs 7 instructions per texel.
+// It doubles the cost of the blocks it touches (half of the blocks of a smooth 4K picture), so it is an encoder OPTION
+// (HAPB200_OPTION_CHROMA_REFINE, include/hap_b200.h) and a template parameter here: off costs nothing.
+HAP_HD float chroma_true_error(const float x[16], const float y[16], float Sx, float Sy, float Sxx, float Syy, float p0x, float p0y, float p1x, float p1y)
+{
+    const float ex = p1x - p0x, ey = p1y - p0y;
+    const float ee = hap_fma(ex, ex, ey * ey);
+    const float iee = ee > 1e-9f ? 1.0f / ee : 0.0f;      // both endpoints on one grid point: every texel decodes to p0
+    const float wx = ex * iee, wy = ey * iee, w0 = -hap_fma(p0x, wx, p0y * wy);
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        const float u = hap_fma(x[t], wx, hap_fma(y[t], wy, w0));
+        const float r3 = hap_fma(hap_sat(u), 3.0f, kRoundMagic) - kRoundMagic;     // 3 r = 0, 1, 2, 3
+        acc = hap_fma(r3, hap_fma(u, -6.0f, r3), acc);                            // 9 r (r - 2u)
+    }
+    const float P = hap_fma(16.0f, hap_fma(p0x, p0x, p0y * p0y), hap_fma(-2.0f * p0x, Sx, hap_fma(-2.0f * p0y, Sy, Sxx + Syy)));
+    return hap_fma(ee * (1.0f / 9.0f), acc, P);
+}
+
 // The chroma half of a scaled-YCoCg block: 16 (Co, Cg) pairs -> BC1 colour block (R' = Co', G' = Cg', B' = scale
 // code).  co2 = R - B (half units), cg4 = -R + 2G - B (quarter units), with their max / min over the block.
 //
@@ -192,6 +220,7 @@ HAP_HD void snap_pair(float a, float b, float off, float A2, float B2, float AB,
 //   projection onto the decoder's palette segment.
 // Cluster sums are kept in terms of q = 0..3 (the cluster number): with beta = q/3, alpha = 1 - beta all nine
 // sums of the normal equations follow from sum(q), sum(q^2), sum(q x), sum(q y) and the plain moments.
+template <bool REFINE>
 HAP_HD Block8 encode_ycocg_chroma(const int co2[16], const int cg4[16], int co_hi, int co_lo, int cg_hi, int cg_lo)
 {
     const int m2 = co_hi > -co_lo ? co_hi : -co_lo, m4 = cg_hi > -cg_lo ? cg_hi : -cg_lo;
@@ -261,8 +290,22 @@ HAP_HD Block8 encode_ycocg_chroma(const int co2[16], const int cg4[16], int co_h
             const float ar = fminf(fmaxf(hap_fma(eax, imx, offx), 0.f), 255.f), br = fminf(fmaxf(hap_fma(ebx, imx, offx), 0.f), 255.f);
             const float ag = fminf(fmaxf(hap_fma(eay, imy, offy), 0.f), 255.f), bg = fminf(fmaxf(hap_fma(eby, imy, offy), 0.f), 255.f);
             if (det >= 1e-4f) {
-                snap_pair(ar, br, offx, A2, B2, AB, AXx * imx, BXx * imx, 31.0f, a5r, b5r);
                 a6g = (uint32_t)(int)floorf(hap_fma(ag, 63.0f / 255.0f, 0.5f)); b6g = (uint32_t)(int)floorf(hap_fma(bg, 63.0f / 255.0f, 0.5f));
+                if (REFINE && fabsf(ar - br) < 255.0f / 31.0f) {
+                    const float p0y = ((float)expand6(a6g) - offy) * kYCoCgMetricCg, p1y = ((float)expand6(b6g) - offy) * kYCoCgMetricCg;
+                    const uint32_t fa = (uint32_t)(int)floorf(ar * (31.0f / 255.0f)), fb = (uint32_t)(int)floorf(br * (31.0f / 255.0f));
+                    float best = 3.0e38f;
+                    a5r = fa; b5r = fb;
+#pragma unroll 1
+                    for (uint32_t c = 0; c < 4; c++) {
+                        const uint32_t ca = fa + (c & 1u) < 31u ? fa + (c & 1u) : 31u, cb = fb + (c >> 1) < 31u ? fb + (c >> 1) : 31u;
+                        const float e = chroma_true_error(x, y, Sx, Sy, Sxx, Syy, ((float)expand5(ca) - offx) * kYCoCgMetricCo, p0y,
+                                                          ((float)expand5(cb) - offx) * kYCoCgMetricCo, p1y);
+                        if (e < best) { best = e; a5r = ca; b5r = cb; }
+                    }
+                } else {
+                    snap_pair(ar, br, offx, A2, B2, AB, AXx * imx, BXx * imx, 31.0f, a5r, b5r);
+                }
             } else {
                 a5r = (uint32_t)(int)floorf(hap_fma(ar, 31.0f / 255.0f, 0.5f)); b5r = (uint32_t)(int)floorf(hap_fma(br, 31.0f / 255.0f, 0.5f));
                 a6g = (uint32_t)(int)floorf(hap_fma(ag, 63.0f / 255.0f, 0.5f)); b6g = (uint32_t)(int)floorf(hap_fma(bg, 63.0f / 255.0f, 0.5f));
@@ -618,6 +661,7 @@ HAP_HD void encode_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colour)
     colour = encode_dxt1(px);
 }
 
+template <bool REFINE = false>
 HAP_HD void encode_ycocg_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colour)
 {
     if (block_is_flat_rgb(px)) {
@@ -651,7 +695,7 @@ HAP_HD void encode_ycocg_dxt5(const uint32_t px[16], Block8 &alpha, Block8 &colo
     cg_hi = hap_max3(cg_hi, cg4[15], cg4[15]); cg_lo = hap_min3(cg_lo, cg4[15], cg4[15]);
     y_hi = hap_max3(y_hi, y28[15], y28[15]); y_lo = hap_min3(y_lo, y28[15], y28[15]);
     alpha = encode_bc4_scaled<28>(y28, y_hi, y_lo);
-    colour = encode_ycocg_chroma(co2, cg4, co_hi, co_lo, cg_hi, cg_lo);
+    colour = encode_ycocg_chroma<REFINE>(co2, cg4, co_hi, co_lo, cg_hi, cg_lo);
 }
 
 }  // namespace hapb200

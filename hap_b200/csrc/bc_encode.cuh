@@ -24,8 +24,8 @@ struct BcGeom {
     uint64_t second_offset;        // kBcYCoCgPlusAlpha: offset of the RGTC1 plane inside a frame's output
 };
 
-// grid = (ceil(blocks/kBcThreads), frames)
-template <int KIND>
+// grid = (ceil(blocks/kBcThreads), frames).  REFINE: the chroma endpoint refinement of the YCoCg kinds (bc_block.cuh).
+template <int KIND, bool REFINE = false>
 __global__ void __launch_bounds__(kBcThreads) bc_encode_kernel(const uint8_t *__restrict__ rgba, BcGeom G,
                                                                 uint8_t *__restrict__ out)
 {
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kBcThreads) bc_encode_kernel(const uint8_t *__
         reinterpret_cast<uint4 *>(o)[bi] = make_uint4(a.lo, a.hi, c.lo, c.hi);
     } else {
         Block8 a, c;
-        encode_ycocg_dxt5(px, a, c);
+        encode_ycocg_dxt5<REFINE>(px, a, c);
         reinterpret_cast<uint4 *>(o)[bi] = make_uint4(a.lo, a.hi, c.lo, c.hi);
         if (KIND == kBcYCoCgPlusAlpha) {
             Block8 al = encode_rgtc1_alpha(px);

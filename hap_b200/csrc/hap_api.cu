@@ -32,6 +32,7 @@ std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_use_index{1};
 std::atomic<int> g_write_index{0};
 std::atomic<int> g_write_offsets{0};
+std::atomic<int> g_chroma_refine{0};   // HAPB200_OPTION_CHROMA_REFINE
 
 // Optional per-stage device timing (HapB200SetStageTiming): CUDA events around every kernel, on the
 // stream the kernel is launched on.  Off by default; bench.py turns it on for its roofline pass only.
@@ -127,6 +128,7 @@ struct DeviceGuard {
             if (const char *e = getenv("HAPB200_WRITE_INDEX")) g_write_index.store(atoi(e) != 0);
             if (const char *e = getenv("HAPB200_USE_INDEX")) g_use_index.store(atoi(e) != 0);
             if (const char *e = getenv("HAPB200_WRITE_OFFSET_TABLE")) g_write_offsets.store(atoi(e) != 0);
+            if (const char *e = getenv("HAPB200_CHROMA_REFINE")) g_chroma_refine.store(atoi(e) != 0);
         });
         if (cudaGetDevice(&saved) != cudaSuccess) { cudaGetLastError(); saved = -1; return; }
         int want = -1;
@@ -321,12 +323,19 @@ uint32_t launch_block_encode(const uint8_t *rgba, uint32_t frames, uint64_t fram
     g.out_stride = blocks_stride;
     g.second_offset = second_offset;
     dim3 grid((g.blocks_x * g.blocks_y + kBcThreads - 1) / kBcThreads, frames);
+    const bool refine = g_chroma_refine.load() != 0;
     switch (ci.bc_kind) {
     case kBcDxt1: HAP_KLAUNCH(kStBcEncode, bc_encode_kernel<kBcDxt1>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
     case kBcDxt5: HAP_KLAUNCH(kStBcEncode, bc_encode_kernel<kBcDxt5>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
-    case kBcYCoCg: HAP_KLAUNCH(kStBcEncode, bc_encode_kernel<kBcYCoCg>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
+    case kBcYCoCg:
+        if (refine) HAP_KLAUNCH(kStBcEncode, (bc_encode_kernel<kBcYCoCg, true>), grid, dim3(kBcThreads), 0, st, rgba, g, blocks);
+        else HAP_KLAUNCH(kStBcEncode, bc_encode_kernel<kBcYCoCg>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks);
+        break;
     case kBcRgtc1: HAP_KLAUNCH(kStBcEncode, bc_encode_kernel<kBcRgtc1>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
-    default: HAP_KLAUNCH(kStBcEncode, bc_encode_kernel<kBcYCoCgPlusAlpha>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks); break;
+    default:
+        if (refine) HAP_KLAUNCH(kStBcEncode, (bc_encode_kernel<kBcYCoCgPlusAlpha, true>), grid, dim3(kBcThreads), 0, st, rgba, g, blocks);
+        else HAP_KLAUNCH(kStBcEncode, bc_encode_kernel<kBcYCoCgPlusAlpha>, grid, dim3(kBcThreads), 0, st, rgba, g, blocks);
+        break;
     }
     return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
 }
@@ -414,21 +423,84 @@ uint32_t launch_decode_batch(const uint8_t *in, uint32_t frames, uint64_t in_str
     return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
 }
 
-// host-side view of a frame whose bytes may live on the device: fetches what header walks need
+// host-side view of a frame whose bytes may live on the device.  Header walks read a few hundred bytes at data-dependent
+// places (section headers, the Decode Instructions tables, five bytes at the head of every chunk, the trailing index header), so
+// a device frame is mirrored LAZILY: `p` points at a zero-page-backed image of the whole frame and need(off, len) fetches the
+// 4 KiB pages under [off, off+len) that are not there yet.  A 4K Hap Q frame costs ~10 small copies instead of 5 MB.
 struct HeaderView {
-    std::vector<uint8_t> copy;
+    static constexpr uint64_t kPage = 4096;
+    uint8_t *mirror = nullptr;
+    const uint8_t *dev = nullptr;
     const uint8_t *p = nullptr;
+    uint64_t bytes = 0;
+    std::vector<bool> have;
     bool ok = true;
-    HeaderView(const void *frame, unsigned long bytes)
+    HeaderView(const void *frame, unsigned long n) : bytes(n)
     {
         if (!is_device_pointer(frame)) { p = (const uint8_t *)frame; return; }
-        // headers + tables sit at the front of each section, but an inner section of a two-texture
-        // frame starts after the first texture's data: fetch the whole frame (queries on device
-        // frames are rare and not on the hot path; the batch decode parses on the device instead)
-        copy.resize(bytes ? bytes : 1);
-        ok = cudaMemcpy(copy.data(), frame, bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
-        if (!ok) cudaGetLastError();
-        p = copy.data();
+        dev = (const uint8_t *)frame;
+        mirror = (uint8_t *)calloc(n ? n : 1, 1);     // untouched pages stay uncommitted
+        if (!mirror) { ok = false; return; }
+        p = mirror;
+        have.assign((size_t)((n + kPage - 1) / kPage), false);
+        need(0, kPage);
+    }
+    ~HeaderView() { free(mirror); }
+    HeaderView(const HeaderView &) = delete;
+    HeaderView &operator=(const HeaderView &) = delete;
+    // make [off, off+len) of the frame readable through p (clamped to the frame); false after a failed copy
+    bool need(uint64_t off, uint64_t len)
+    {
+        if (!dev || !ok || off >= bytes || len == 0) return ok;
+        if (len > bytes - off) len = bytes - off;
+        uint64_t a = off / kPage;
+        const uint64_t b = (off + len - 1) / kPage;
+        while (a <= b) {
+            if (have[(size_t)a]) { a++; continue; }
+            uint64_t e = a;
+            while (e <= b && !have[(size_t)e]) have[(size_t)e++] = true;
+            const uint64_t lo = a * kPage, hi = e * kPage < bytes ? e * kPage : bytes;
+            if (cudaMemcpy(mirror + lo, dev + lo, hi - lo, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); ok = false; return false; }
+            a = e;
+        }
+        return true;
+    }
+    // the texture section `index` (hap.c:932-991), fetching the inner section headers a two-texture frame needs
+    uint32_t locate(uint32_t index, Located &loc)
+    {
+        Section top;
+        if (dev && read_section_header(p, (uint32_t)bytes, top) == HapResult_No_Error && top.type == kSecMultipleImages) {
+            uint64_t off = top.hdr;
+            for (uint32_t i = 0; i < index; i++) {
+                Section s;
+                need(off, 8);
+                if (off >= bytes || read_section_header(p + off, (uint32_t)(bytes - off), s) != HapResult_No_Error) break;
+                off += (uint64_t)s.hdr + s.len;
+            }
+            need(off, 8);
+        }
+        if (!ok) return HapResult_Internal_Error;
+        return locate_texture(p, (uint32_t)bytes, index, loc);
+    }
+    // the Decode Instructions container at the head of texture section `loc` (hap.c:644-730)
+    void need_tables(const Located &loc)
+    {
+        if (!dev) return;
+        need(loc.offset, 8);
+        Section di;
+        if (loc.offset < bytes && read_section_header(p + loc.offset, loc.len, di) == HapResult_No_Error)
+            need(loc.offset, (uint64_t)di.hdr + di.len);
+    }
+    // the trailing fragment index section's header and record-offset table (hap_index.h)
+    void need_index_header()
+    {
+        if (!dev) return;
+        Section top;
+        if (read_section_header(p, (uint32_t)bytes, top) != HapResult_No_Error) return;
+        const uint64_t end = (uint64_t)top.hdr + top.len;
+        need(end, 8 + kIndexHeaderBytes);
+        FragmentIndex ix;
+        if (locate_fragment_index(p, (uint32_t)bytes, ix)) need(ix.body, (uint64_t)kIndexHeaderBytes + 4ull * ((uint64_t)ix.chunks[0] + ix.chunks[1]));
     }
 };
 
@@ -443,6 +515,48 @@ void work_function(void *p, unsigned int)
 }
 
 }  // namespace
+
+// ---- delivery rings: helpers ----
+namespace {
+struct OnDevice {      // the calling thread's device for the duration of one ring call
+    int saved = -1;
+    bool ok = false;
+    explicit OnDevice(int device)
+    {
+        if (device < 0 || device >= kMaxDevices || cudaGetDevice(&saved) != cudaSuccess) { cudaGetLastError(); return; }
+        ok = device == saved || cudaSetDevice(device) == cudaSuccess;
+        if (ok) { std::call_once(g_dev[device].once, device_init, device); ok = g_dev[device].ready; }
+        if (!ok) cudaGetLastError();
+    }
+    ~OnDevice()
+    {
+        int cur = -1;
+        if (saved >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != saved) cudaSetDevice(saved);
+        cudaGetLastError();
+    }
+};
+__global__ void ring_publish_kernel(unsigned int *flag, unsigned int value)
+{
+    // the kernels queued before this one have completed, their stores to the peer are performed; the fence orders this
+    // thread's view, the release store makes the flag the last thing the consumer can see
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__global__ void ring_wait_kernel(const unsigned int *flag, unsigned int value, unsigned long long timeout_ns)
+{
+    unsigned int v;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - value) >= 0) break;
+        hap_nanosleep(500);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (timeout_ns && t1 - t0 > timeout_ns) break;     // a producer that died must not hang the consumer's GPU for ever
+    }
+}
+}  // namespace
+
 
 // =====================================================================================================
 extern "C" {
@@ -482,6 +596,99 @@ int HapB200SetDevice(int device)
 }
 int HapB200GetDevice(void) { return g_default_device.load(); }
 
+// ---- delivery rings (include/hap_b200.h) ---------------------------------------------------------------------------
+unsigned int HapB200RingCreate(int device, unsigned long bytes, void **ring, void *handle)
+{
+    if (!ring || bytes == 0) return HapResult_Bad_Arguments;
+    OnDevice on(device);
+    if (!on.ok) return HapResult_Internal_Error;
+    void *p = nullptr;
+    // plain cudaMalloc: memory of a stream-ordered pool cannot be exported
+    if (cudaMalloc(&p, bytes) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        cudaGetLastError();
+        if (p) cudaFree(p);
+        return HapResult_Internal_Error;
+    }
+    if (handle) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == HAPB200_RING_HANDLE_BYTES, "handle size");
+        cudaIpcMemHandle_t h;
+        if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return HapResult_Internal_Error; }
+        memcpy(handle, &h, sizeof h);
+    }
+    *ring = p;
+    return HapResult_No_Error;
+}
+
+unsigned int HapB200RingDestroy(int device, void *ring)
+{
+    if (!ring) return HapResult_Bad_Arguments;
+    OnDevice on(device);
+    if (!on.ok) return HapResult_Internal_Error;
+    cudaDeviceSynchronize();
+    const bool ok = cudaFree(ring) == cudaSuccess;
+    cudaGetLastError();
+    return ok ? HapResult_No_Error : HapResult_Internal_Error;
+}
+
+unsigned int HapB200RingOpen(int device, const void *handle, void **ring)
+{
+    if (!handle || !ring) return HapResult_Bad_Arguments;
+    OnDevice on(device);
+    if (!on.ok) return HapResult_Internal_Error;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+    *ring = p;
+    return HapResult_No_Error;
+}
+
+unsigned int HapB200RingClose(int device, void *ring)
+{
+    if (!ring) return HapResult_Bad_Arguments;
+    OnDevice on(device);
+    if (!on.ok) return HapResult_Internal_Error;
+    cudaDeviceSynchronize();
+    const bool ok = cudaIpcCloseMemHandle(ring) == cudaSuccess;
+    cudaGetLastError();
+    return ok ? HapResult_No_Error : HapResult_Internal_Error;
+}
+
+unsigned int HapB200RingAttach(int device, int ringDevice)
+{
+    if (ringDevice < 0 || ringDevice >= kMaxDevices) return HapResult_Bad_Arguments;
+    if (device == ringDevice) return HapResult_No_Error;
+    OnDevice on(device);
+    if (!on.ok) return HapResult_Internal_Error;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, device, ringDevice) != cudaSuccess || !can) { cudaGetLastError(); return HapResult_Internal_Error; }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(ringDevice, 0);
+    cudaGetLastError();
+    return (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) ? HapResult_No_Error : HapResult_Internal_Error;
+}
+
+unsigned int HapB200RingPublish(int device, void *flag, unsigned int value, void *stream)
+{
+    if (!flag || ((uintptr_t)flag & 3)) return HapResult_Bad_Arguments;
+    OnDevice on(device);
+    if (!on.ok) return HapResult_Internal_Error;
+    cudaStream_t st = stream ? (cudaStream_t)stream : kLegacyStream;
+    ring_publish_kernel<<<1, 1, 0, st>>>((unsigned int *)flag, value);
+    g_launches.fetch_add(1);
+    return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
+}
+
+unsigned int HapB200RingWait(int device, const void *flag, unsigned int value, unsigned int timeoutMs, void *stream)
+{
+    if (!flag || ((uintptr_t)flag & 3)) return HapResult_Bad_Arguments;
+    OnDevice on(device);
+    if (!on.ok) return HapResult_Internal_Error;
+    cudaStream_t st = stream ? (cudaStream_t)stream : kLegacyStream;
+    ring_wait_kernel<<<1, 1, 0, st>>>((const unsigned int *)flag, value, 1000000ull * timeoutMs);
+    g_launches.fetch_add(1);
+    return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
+}
+
 // Options.  HAPB200_OPTION_USE_INDEX (1): decoder uses a frame's embedded fragment index (default 1).
 // HAPB200_OPTION_WRITE_INDEX (2): encoder writes the fragment index section (default: see g_write_index).
 int HapB200SetOption(int option, int value)
@@ -489,6 +696,7 @@ int HapB200SetOption(int option, int value)
     if (option == 1) { g_use_index.store(value != 0); return 0; }
     if (option == 2) { g_write_index.store(value != 0); return 0; }
     if (option == 3) { g_write_offsets.store(value != 0); return 0; }
+    if (option == 4) { g_chroma_refine.store(value != 0); return 0; }
     return -1;
 }
 
@@ -545,6 +753,7 @@ unsigned int HapGetFrameTextureCount(const void *inputBuffer, unsigned long inpu
     *outputTextureCount = 0;
     while (off < top.len) {  // hap.c:1064 compares against the body length, as here
         Section s;
+        if (!hv.need(off, 8)) return HapResult_Internal_Error;
         r = read_section_header(in + off, (uint32_t)(inputBufferBytes - off), s);
         if (r != HapResult_No_Error) return r;
         off += s.hdr + s.len;
@@ -561,7 +770,7 @@ unsigned int HapGetFrameTextureFormat(const void *inputBuffer, unsigned long inp
     HeaderView hv(inputBuffer, inputBufferBytes);
     if (!hv.ok) return HapResult_Internal_Error;
     Located loc;
-    uint32_t r = locate_texture(hv.p, (uint32_t)inputBufferBytes, index, loc);
+    uint32_t r = hv.locate(index, loc);
     if (r != HapResult_No_Error) return r;
     *outputBufferTextureFormat = format_from_nibble(loc.type & 0xF);
     return *outputBufferTextureFormat ? HapResult_No_Error : HapResult_Bad_Frame;
@@ -576,12 +785,14 @@ unsigned int HapGetFrameTextureChunkCount(const void *inputBuffer, unsigned long
     HeaderView hv(inputBuffer, inputBufferBytes);
     if (!hv.ok) return HapResult_Internal_Error;
     Located loc;
-    uint32_t r = locate_texture(hv.p, (uint32_t)inputBufferBytes, index, loc);
+    uint32_t r = hv.locate(index, loc);
     if (r != HapResult_No_Error) return r;
     const uint32_t compressor = (loc.type >> 4) & 0xF;
     if (compressor == kHapComplex) {
         ChunkTables t;
         t.count = 0;
+        hv.need_tables(loc);
+        if (!hv.ok) return HapResult_Internal_Error;
         r = parse_decode_instructions(hv.p + loc.offset, loc.len, t);
         *chunk_count = t.count;
         return r;
@@ -718,7 +929,7 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
     if (!hv.ok) return HapResult_Internal_Error;
     const uint8_t *frame = hv.p;
     Located loc;
-    uint32_t r = locate_texture(frame, (uint32_t)inputBufferBytes, index, loc);
+    uint32_t r = hv.locate(index, loc);
     if (r != HapResult_No_Error) return r;
     const uint8_t *sec = frame + loc.offset;
     const uint32_t compressor = (loc.type >> 4) & 0xF;
@@ -733,8 +944,11 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
     if (compressor == kHapComplex) {
         ChunkTables t;
         t.count = 0;
+        hv.need_tables(loc);
+        if (!hv.ok) return HapResult_Internal_Error;
         r = parse_decode_instructions(sec, loc.len, t);
         if (r != HapResult_No_Error) return r;
+        hv.need_index_header();
         FragmentIndex ix;
         const bool have_ix = locate_fragment_index(frame, (uint32_t)inputBufferBytes, ix);
         if (have_ix) { hv_index_body = ix.body; hv_index_len = ix.len; }
@@ -747,6 +961,7 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
                 const uint64_t start = t.data + (t.offsets != 0xFFFFFFFFu ? (uint64_t)rd_le32(sec + t.offsets + 4 * i) : in_run);
                 in_run += sz;
                 if (start + sz > loc.len) return HapResult_Bad_Frame;  // the reference reads out of bounds here
+                if (cc == kHapChunkSnappy && !hv.need(loc.offset + start, 5)) return HapResult_Internal_Error;
                 uint32_t usz = sz;
                 if (cc == kHapChunkSnappy && !snappy_preamble(sec + start, sz, usz)) return HapResult_Bad_Frame;  // hap.c:817-829
                 hj[i] = HostJob{(uint32_t)start, sz, 0, usz, (cc == kHapChunkSnappy || cc == kHapChunkRaw) ? cc : 0xFFu, 0, 0};
@@ -760,6 +975,7 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
         }
     } else if (compressor == kHapChunkSnappy) {
         uint32_t usz = 0;
+        if (!hv.need(loc.offset, 5)) return HapResult_Internal_Error;
         if (!snappy_preamble(sec, loc.len, usz)) return HapResult_Internal_Error;  // hap.c:890-894
         if (usz > outputBufferBytes) return HapResult_Buffer_Too_Small;
         hj.push_back(HostJob{0, loc.len, 0, usz, kHapChunkSnappy, 0, 0});

@@ -56,6 +56,12 @@ class HapB200(HapABI):
         L.HapB200BlockEncodeBatch.argtypes = [vp, u, ul, u, u, ul, u, vp, ul, vp]
         L.HapB200BlockDecodeBatch.restype = u
         L.HapB200BlockDecodeBatch.argtypes = [vp, u, ul, u, u, u, vp, ul, ul, vp]
+        for name, args in (("RingCreate", [C.c_int, ul, C.POINTER(vp), vp]), ("RingDestroy", [C.c_int, vp]),
+                           ("RingOpen", [C.c_int, vp, C.POINTER(vp)]), ("RingClose", [C.c_int, vp]),
+                           ("RingAttach", [C.c_int, C.c_int]), ("RingPublish", [C.c_int, vp, u, vp]), ("RingWait", [C.c_int, vp, u, u, vp])):
+            f = getattr(L, "HapB200" + name)
+            f.restype = u
+            f.argtypes = args
 
     def version(self) -> str:
         return self.lib.HapB200Version().decode()
@@ -63,7 +69,7 @@ class HapB200(HapABI):
     def launches(self) -> int:
         return int(self.lib.HapB200KernelLaunchCount())
 
-    OPTION_USE_INDEX, OPTION_WRITE_INDEX, OPTION_WRITE_OFFSET_TABLE = 1, 2, 3
+    OPTION_USE_INDEX, OPTION_WRITE_INDEX, OPTION_WRITE_OFFSET_TABLE, OPTION_CHROMA_REFINE = 1, 2, 3, 4
 
     def set_option(self, option: int, value: int) -> int:
         """OPTION_USE_INDEX: the decoder uses a frame's embedded fragment index (default on).  OPTION_WRITE_INDEX: the
@@ -172,6 +178,38 @@ class HapB200(HapABI):
     def block_decode_batch(self, blocks, frames, blocks_stride, w, h, codec, rgba, frame_stride, row_bytes=None, stream=None):
         return int(self.lib.HapB200BlockDecodeBatch(blocks, frames, blocks_stride, w, h, codec, rgba, frame_stride,
                                                     row_bytes or 4 * w, stream))
+
+
+    # -- delivery rings (include/hap_b200.h): frames written straight into another GPU's memory -----------------
+    RING_HANDLE_BYTES = 64
+
+    def ring_create(self, device: int, nbytes: int):
+        """(result, ring address, 64-byte handle for the producers)"""
+        ring = C.c_void_p(0)
+        handle = (C.c_ubyte * self.RING_HANDLE_BYTES)()
+        r = self.lib.HapB200RingCreate(device, nbytes, C.byref(ring), handle)
+        return int(r), int(ring.value or 0), bytes(handle)
+
+    def ring_destroy(self, device: int, ring: int) -> int:
+        return int(self.lib.HapB200RingDestroy(device, ring))
+
+    def ring_open(self, device: int, handle: bytes):
+        ring = C.c_void_p(0)
+        buf = (C.c_ubyte * self.RING_HANDLE_BYTES).from_buffer_copy(handle)
+        r = self.lib.HapB200RingOpen(device, buf, C.byref(ring))
+        return int(r), int(ring.value or 0)
+
+    def ring_close(self, device: int, ring: int) -> int:
+        return int(self.lib.HapB200RingClose(device, ring))
+
+    def ring_attach(self, device: int, ring_device: int) -> int:
+        return int(self.lib.HapB200RingAttach(device, ring_device))
+
+    def ring_publish(self, device: int, flag: int, value: int, stream=None) -> int:
+        return int(self.lib.HapB200RingPublish(device, flag, value, stream))
+
+    def ring_wait(self, device: int, flag: int, value: int, timeout_ms: int = 0, stream=None) -> int:
+        return int(self.lib.HapB200RingWait(device, flag, value, timeout_ms, stream))
 
 
 @functools.lru_cache(None)

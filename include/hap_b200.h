@@ -36,6 +36,30 @@ unsigned long long HapB200KernelLaunchCount(void);
 int HapB200SetDevice(int device);
 int HapB200GetDevice(void);
 
+/* Delivery rings: frames encoded on one GPU written STRAIGHT into memory of another GPU of the box.
+ * Frames of a stream are independent (HapVideoDRAFT.md:29-34), so N GPUs encode N frames at once; the consumer (a muxer, a
+ * file writer) sits next to ONE of them.  A ring is device memory on the consumer's GPU.  Producers -- other processes
+ * (CUDA IPC) or other threads of this process -- pass an address inside it as the `out` (and `used`) argument of
+ * HapB200EncodeRGBABatch / HapB200EncodeBatch: the kernel that lays the frame out stores it over NVLink / NVSwitch into the
+ * consumer's memory, so there is no second pass over the encoded bytes (no staging copy, no collective).
+ *   consumer:  HapB200RingCreate(device, bytes, &ring, handle)        -- handle: 64 bytes to hand to the producers
+ *   producer:  HapB200RingOpen(device, handle, &ring)                 -- other process; maps the ring, enables peer access
+ *              HapB200RingAttach(device, ringDevice)                  -- same process: enables peer access, use `ring` as is
+ *              ... HapB200EncodeRGBABatch(..., out = ring + slot, ..., stream) ...
+ *              HapB200RingPublish(device, ring + flagOffset, value, stream)  -- after everything queued on `stream` so far
+ *   consumer:  HapB200RingWait(device, ring + flagOffset, value, timeoutMs, stream)  -- work queued on `stream` afterwards sees
+ *              the frames; timeoutMs > 0: stop waiting after that long (a dead producer must not hold the GPU), 0: wait for ever
+ * Layout inside the ring (slots, flags, lengths) is the caller's; flags are 4-byte words, 4-byte aligned, that only grow.
+ * Results: HapResult values (hap.h).  Close / Destroy synchronise the device. */
+#define HAPB200_RING_HANDLE_BYTES 64
+unsigned int HapB200RingCreate(int device, unsigned long bytes, void **ring, void *handle);
+unsigned int HapB200RingDestroy(int device, void *ring);
+unsigned int HapB200RingOpen(int device, const void *handle, void **ring);
+unsigned int HapB200RingClose(int device, void *ring);
+unsigned int HapB200RingAttach(int device, int ringDevice);
+unsigned int HapB200RingPublish(int device, void *flag, unsigned int value, void *stream);
+unsigned int HapB200RingWait(int device, const void *flag, unsigned int value, unsigned int timeoutMs, void *stream);
+
 /* Options.  HAPB200_OPTION_USE_INDEX: the decoder uses a frame's embedded fragment index when it finds one (default 1;
  * 0 = always derive the index from the Snappy streams, as for every frame another encoder wrote).
  * HAPB200_OPTION_WRITE_INDEX: the encoder adds a private "fragment index" section to the Decode Instructions container
@@ -50,6 +74,12 @@ int HapB200GetDevice(void);
  * every chunk starts on a 16-byte boundary of the frame, the few bytes between chunks being zero.  Default 0: the
  * reference's encoder never writes this table and packs chunks back to back (hap.c:473). */
 #define HAPB200_OPTION_WRITE_OFFSET_TABLE 3
+/* HAPB200_OPTION_CHROMA_REFINE: the scaled-YCoCg block encoders (Hap Q, Hap Q Alpha) score the 5-bit Co' endpoint
+ * candidates of blocks with less than one grid cell of Co' extent by their true error (every texel re-assigned) instead of
+ * with the clusters of the unquantised fit held fixed.  Closes the encoder's one deficit against the cluster-fit oracle
+ * beyond the 0.1 dB bar (slow colour ramps, 1080p: -0.47 dB -> -0.06 dB; video content +0.61 -> +0.65 dB) for +58 % block-encode
+ * time on 4K footage (half of its blocks qualify).  Default 0.  Environment: HAPB200_CHROMA_REFINE. */
+#define HAPB200_OPTION_CHROMA_REFINE 4
 int HapB200SetOption(int option, int value);
 
 /* Per-stage device timing for profiling runs: when enabled every kernel launch is bracketed by CUDA

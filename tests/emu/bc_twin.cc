@@ -15,7 +15,7 @@ static void gather(const uint8_t *rgba, int w, int bx, int by, uint32_t px[16])
 
 extern "C" void twin_encode(const uint8_t *rgba, int w, int h, int kind, uint8_t *out)
 {
-    // kind: 0 dxt1, 1 dxt5, 2 ycocg-dxt5, 3 rgtc1 (alpha channel)
+    // kind: 0 dxt1, 1 dxt5, 2 ycocg-dxt5, 3 rgtc1 (alpha channel), 4 ycocg-dxt5 with the chroma refinement option
     for (int by = 0; by < h / 4; by++)
         for (int bx = 0; bx < w / 4; bx++) {
             uint32_t px[16];
@@ -25,7 +25,7 @@ extern "C" void twin_encode(const uint8_t *rgba, int w, int h, int kind, uint8_t
             else if (kind == 3) { Block8 a = encode_rgtc1_alpha(px); memcpy(out + 8 * bi, &a, 8); }
             else {
                 Block8 a, c;
-                if (kind == 1) encode_dxt5(px, a, c); else encode_ycocg_dxt5(px, a, c);
+                if (kind == 1) encode_dxt5(px, a, c); else if (kind == 4) encode_ycocg_dxt5<true>(px, a, c); else encode_ycocg_dxt5<false>(px, a, c);
                 memcpy(out + 16 * bi, &a, 8);
                 memcpy(out + 16 * bi + 8, &c, 8);
             }

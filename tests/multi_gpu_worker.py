@@ -95,6 +95,85 @@ def main():
         used_l = torch.zeros(1, dtype=torch.int64, device=dev)
         assert lib.encode_rgba_batch(img_l.data_ptr(), 1, img_l.numel(), 256, 128, codec, 1, 2, out_l.data_ptr(), cap_o, used_l.data_ptr()) == 0
         assert fr == out_l[: int(used_l[0])].cpu().numpy().tobytes()
+    # 5. delivery ring: every rank's encoder writes its frames STRAIGHT into rank 0's memory (CUDA IPC peer mapping), lengths
+    #    into the slot header, a release store publishes the slot; rank 0 waits on the flags and decodes every frame (reference
+    #    build on the host) to the texture of the picture its stream position names
+    HEADER = 4096
+    slot_bytes = HEADER + n * cap
+    handle = torch.zeros(lib.RING_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+    ring_ptr = 0
+    if rank == 0:
+        rr, ring_ptr, hb = lib.ring_create(local, world * slot_bytes)
+        assert rr == 0
+        handle.copy_(torch.frombuffer(bytearray(hb), dtype=torch.uint8))
+    dist.broadcast(handle, 0)
+    if rank != 0:
+        rr, ring_ptr = lib.ring_open(local, handle.cpu().numpy().tobytes())
+        assert rr == 0 and ring_ptr != 0
+    mine_slot = ring_ptr + rank * slot_bytes
+    st = torch.cuda.Stream(device=dev)
+    assert lib.encode_rgba_batch(imgs.data_ptr(), n, w * h * 4, w, h, codec, 1, k, mine_slot + HEADER, cap, mine_slot + 64, stream=st.cuda_stream) == 0
+    assert lib.ring_publish(local, mine_slot, 1, stream=st.cuda_stream) == 0
+    assert torch.cuda.current_device() == local
+    if rank == 0:
+        cs = torch.cuda.Stream(device=dev)
+        for r in range(world):
+            assert lib.ring_wait(local, ring_ptr + r * slot_bytes, 1, 30000, stream=cs.cuda_stream) == 0
+        cs.synchronize()
+
+        class _Ext:
+            def __init__(self, ptr, nb):
+                self.__cuda_array_interface__ = {"shape": (nb,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        ring_t = torch.as_tensor(_Ext(ring_ptr, world * slot_bytes), device=dev)
+        host = ring_t.cpu().numpy()
+        ref = oracles.ref_abi() or oracles.oracle_abi()
+        for r in range(world):
+            o = r * slot_bytes
+            assert int(np.frombuffer(host[o: o + 4].tobytes(), np.uint32)[0]) == 1
+            lens = np.frombuffer(host[o + 64: o + 64 + 8 * n].tobytes(), np.uint64)
+            assert [int(x) for x in lens] == [int(x) for x in lengths[r]], (r, lens, lengths[r])     # the same frames the gatherv moved
+            for i in range(n):
+                fr = host[o + HEADER + i * cap: o + HEADER + i * cap + int(lens[i])].tobytes()
+                img = synth.frame(w, h, i * world + r, device=dev)
+                tex = torch.zeros(tex_n, dtype=torch.uint8, device=dev)
+                assert lib.block_encode_batch(img.data_ptr(), 1, img.numel(), w, h, codec, tex.data_ptr(), tex_n) == 0
+                rr, data, fmt, _ = ref.decode(fr, 0, tex_n)
+                assert rr == 0 and data == tex.cpu().numpy().tobytes(), ("ring", r, i)
+        del ring_t
+        # a flag nobody publishes: the wait gives up after its timeout instead of holding the GPU
+        assert lib.ring_wait(local, ring_ptr + 8, 7, 50, stream=cs.cuda_stream) == 0
+        cs.synchronize()
+    st.synchronize()
+    dist.barrier()
+    if rank != 0:
+        assert lib.ring_close(local, ring_ptr) == 0
+    dist.barrier()
+    if rank == 0:
+        assert lib.ring_destroy(local, ring_ptr) == 0
+        # same process, two devices: attach instead of open
+        if torch.cuda.device_count() >= 2:
+            od = (local + 1) % torch.cuda.device_count()
+            other = torch.device("cuda", od)
+            rr, rp, _ = lib.ring_create(local, slot_bytes)
+            assert rr == 0 and lib.ring_attach(od, local) == 0
+            img_o = imgs.to(other)
+            so = torch.cuda.Stream(device=other)
+            assert lib.encode_rgba_batch(img_o.data_ptr(), n, w * h * 4, w, h, codec, 1, k, rp + HEADER, cap, rp + 64, stream=so.cuda_stream) == 0
+            assert lib.ring_publish(od, rp, 5, stream=so.cuda_stream) == 0
+            assert lib.ring_wait(local, rp, 5, 30000) == 0          # legacy stream: returns when the flag is there
+            torch.cuda.synchronize(dev)
+
+            class _Ext2:
+                def __init__(self, ptr, nb):
+                    self.__cuda_array_interface__ = {"shape": (nb,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+            rt = torch.as_tensor(_Ext2(rp, slot_bytes), device=dev)
+            lens = rt[64: 64 + 8 * n].view(torch.int64).cpu()
+            assert [int(x) for x in lens] == [int(x) for x in lengths[0]]
+            for i in range(n):
+                assert torch.equal(rt[HEADER + i * cap: HEADER + i * cap + int(lens[i])], frames[i, : int(lens[i])])
+            del rt
+            so.synchronize()
+            assert lib.ring_destroy(local, rp) == 0
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

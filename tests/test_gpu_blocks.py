@@ -35,6 +35,26 @@ def test_device_blocks_equal_host_build_of_same_source(lib, name, codec, kind):
     assert gpu_blocks(lib, img, codec) == twin.encode(name, img)
 
 
+@pytest.mark.parametrize("kind", ["video", "gradient", "edges"])
+def test_chroma_refine_option_device_equals_host_build(lib, kind):
+    """HAPB200_OPTION_CHROMA_REFINE selects the <.., true> kernels: bytes equal the host build with the refinement, differ from the
+    default path where it matters, and the option goes back off."""
+    img = synth.frame(512, 256, 1, kind=kind, alpha="ramp").numpy()
+    plain = gpu_blocks(lib, img, L.HapB200Codec_HapY)
+    assert lib.set_option(lib.OPTION_CHROMA_REFINE, 1) == 0
+    try:
+        fine = gpu_blocks(lib, img, L.HapB200Codec_HapY)
+        both = gpu_blocks(lib, img, L.HapB200Codec_HapM)
+    finally:
+        lib.set_option(lib.OPTION_CHROMA_REFINE, 0)
+    assert fine == twin.encode("ycocg_refine", img) and plain == twin.encode("ycocg", img)
+    n0 = lib.texture_bytes(512, 256, L.HapB200Codec_HapM, 0)
+    assert both[:n0] == fine and both[n0:] == twin.encode("bc4", img)
+    if kind == "gradient":
+        assert fine != plain
+    assert gpu_blocks(lib, img, L.HapB200Codec_HapY) == plain
+
+
 def test_hapm_writes_both_planes(lib):
     img = synth.frame(128, 64, 0, alpha="ramp").numpy()
     b = gpu_blocks(lib, img, L.HapB200Codec_HapM)

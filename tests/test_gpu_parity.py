@@ -146,6 +146,79 @@ def test_device_pointers_and_callback_contract(lib):
     assert r == 0 and dev_f[:used].cpu().numpy().tobytes() == f
 
 
+def test_device_frame_header_walks_fetch_pages_only(lib):
+    """Queries and HapDecode on a DEVICE frame read headers through a lazily fetched mirror (hap_api.cu HeaderView): a
+    two-texture frame whose second section header, tables and chunk heads lie megabytes apart must give exactly what the
+    same calls give on the host copy of the frame, for both textures, with and without the trailing index."""
+    rng = np.random.default_rng(21)
+    t0 = dxt_like(rng, 65536, 16)          # 1 MiB colour plane
+    t1 = dxt_like(rng, 65536, 8)           # 512 KiB alpha plane
+    for write_index in (1, 0):
+        lib.set_option(lib.OPTION_WRITE_INDEX, write_index)
+        try:
+            r, f = lib.encode([t0, t1], [YCOCG, RGTC1], [1, 1], [16, 8])
+        finally:
+            lib.set_option(lib.OPTION_WRITE_INDEX, 1)
+        assert r == 0
+        dev = torch.frombuffer(bytearray(f), dtype=torch.uint8).cuda()
+        dp = (dev.data_ptr(), len(f))
+        assert lib.texture_count(dp) == lib.texture_count(f) == (0, 2)
+        for i, (t, fmt, k) in enumerate(((t0, YCOCG, 16), (t1, RGTC1, 8))):
+            assert lib.texture_format(dp, i) == lib.texture_format(f, i) == (0, fmt)
+            assert lib.chunk_count(dp, i) == lib.chunk_count(f, i) == (0, k)
+            out = torch.zeros(len(t), dtype=torch.uint8, device="cuda")
+            r, used, gf, calls = lib.decode(dp, i, len(t), out=(out.data_ptr(), len(t)))
+            assert (r, used, gf, calls) == (0, len(t), fmt, [k])
+            assert out.cpu().numpy().tobytes() == t
+            assert lib.decode(dp, i, len(t))[:3] == (0, t, fmt)          # device frame, host texture
+        # a truncated device frame fails like its host copy does
+        for cut in (3, 9, 4099, len(f) // 2):
+            assert lib.decode((dev.data_ptr(), cut), 1, len(t1))[0] == lib.decode(f[:cut], 1, len(t1))[0] != 0
+
+
+def test_delivery_ring_on_one_device(lib):
+    """HapB200Ring* with producer and consumer on the same GPU: frames encoded straight into the ring are the frames a
+    plain batch encode writes; flags order the consumer behind the producer; bad arguments are refused."""
+    from hap_b200.lib import HapB200Codec_HapM
+    w, h, k, n = 256, 128, 4, 3
+    dev = torch.device("cuda", torch.cuda.current_device())
+    imgs = torch.stack([synth.frame(w, h, i, alpha="ramp", device="cuda") for i in range(n)])
+    cap = (lib.max_encoded_length_rgba(w, h, HapB200Codec_HapM, k) + 255) // 256 * 256
+    plain = torch.zeros((n, cap), dtype=torch.uint8, device="cuda")
+    used = torch.zeros(n, dtype=torch.int64, device="cuda")
+    assert lib.encode_rgba_batch(imgs.data_ptr(), n, w * h * 4, w, h, HapB200Codec_HapM, 1, k, plain.data_ptr(), cap, used.data_ptr()) == 0
+    header = 4096
+    r, ring, handle = lib.ring_create(dev.index, header + n * cap)
+    assert r == 0 and ring != 0 and len(handle) == lib.RING_HANDLE_BYTES
+    try:
+        producer, consumer = torch.cuda.Stream(), torch.cuda.Stream()
+        assert lib.ring_wait(dev.index, ring, 1, 30000, stream=consumer.cuda_stream) == 0      # queued BEFORE the producer runs
+        got = torch.zeros((n, cap), dtype=torch.uint8, device="cuda")
+        glen = torch.zeros(n, dtype=torch.int64, device="cuda")
+
+        class _Ext:
+            def __init__(self, ptr, nb):
+                self.__cuda_array_interface__ = {"shape": (nb,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        ring_t = torch.as_tensor(_Ext(ring, header + n * cap), device="cuda")
+        with torch.cuda.stream(consumer):
+            got.copy_(ring_t[header:].view(n, cap))
+            glen.copy_(ring_t[64: 64 + 8 * n].view(torch.int64))
+        assert lib.encode_rgba_batch(imgs.data_ptr(), n, w * h * 4, w, h, HapB200Codec_HapM, 1, k, ring + header, cap, ring + 64,
+                                     stream=producer.cuda_stream) == 0
+        assert lib.ring_publish(dev.index, ring, 1, stream=producer.cuda_stream) == 0
+        consumer.synchronize()
+        assert torch.equal(glen, used)
+        for i in range(n):
+            assert torch.equal(got[i, : int(used[i])], plain[i, : int(used[i])])
+        del ring_t
+        # refused: misaligned flag, no flag, device out of range; a handle that is not one
+        assert lib.ring_publish(dev.index, ring + 2, 1) != 0 and lib.ring_wait(dev.index, 0, 1, 10) != 0
+        assert lib.ring_create(99, 4096)[0] != 0 and lib.ring_attach(dev.index, 99) != 0 and lib.ring_attach(dev.index, dev.index) == 0
+        assert lib.ring_open(dev.index, bytes(64))[0] != 0
+    finally:
+        assert lib.ring_destroy(dev.index, ring) == 0
+
+
 def test_batch_encode_decode_roundtrip(lib):
     from hap_b200.lib import HapB200Codec_HapY
     frames, n = 6, 16 * 4096

@@ -145,3 +145,13 @@ def test_psnr_bar_full_1080p_per_content_class(lib, kind, cls):
         theirs = b"".join(pool.map(lambda r: oracles.bc_encode_clusterfit(kind, np.ascontiguousarray(img[r[0]:r[1]]), 8), rows))
     pa, pb = _psnr(kind, img, ours, w, h), _psnr(kind, img, theirs, w, h)
     assert pa >= pb - BAR[(kind, cls)], (kind, cls, pa, pb)
+    if kind == "ycocg":
+        # with HAPB200_OPTION_CHROMA_REFINE every class is inside the north-star bar except `edges` (-0.13 dB: three-valued
+        # luma blocks where BC4's 6-value mode happens to fit better, which the oracle tries and this encoder does not)
+        assert lib.set_option(lib.OPTION_CHROMA_REFINE, 1) == 0
+        try:
+            assert lib.block_encode_batch(d.data_ptr(), 1, d.numel(), w, h, codec, out.data_ptr(), out.numel()) == 0
+        finally:
+            lib.set_option(lib.OPTION_CHROMA_REFINE, 0)
+        pr = _psnr(kind, img, out[:n].cpu().numpy().tobytes(), w, h)
+        assert pr >= pb - (0.20 if cls == "edges" else 0.10) and pr >= pa - 0.005, (kind, cls, pr, pa, pb)

@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KIND = {"bc1": 0, "bc3": 1, "ycocg": 2, "bc4": 3}
+KIND = {"bc1": 0, "bc3": 1, "ycocg": 2, "bc4": 3, "ycocg_refine": 4}
 
 
 @functools.lru_cache(None)
@@ -24,7 +24,7 @@ def _lib():
 def encode(kind: str, rgba: np.ndarray) -> bytes:
     rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
     h, w = rgba.shape[:2]
-    n = (w // 4) * (h // 4) * (8 if kind in ("bc1", "bc4") else 16)
+    n = (w // 4) * (h // 4) * (8 if kind in ("bc1", "bc4") else 16)   # "ycocg_refine": HAPB200_OPTION_CHROMA_REFINE on
     out = np.empty(n, np.uint8)
     _lib().twin_encode(C.c_void_p(rgba.ctypes.data), w, h, KIND[kind], C.c_void_p(out.ctypes.data))
     return out.tobytes()

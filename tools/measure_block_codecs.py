@@ -24,7 +24,8 @@ def main():
         rgba[i] = synth.frame(W, H, i, device=dev, alpha="ramp")
     out = {}
     for name, codec in (("Hap1", L.HapB200Codec_Hap1), ("Hap5", L.HapB200Codec_Hap5), ("HapY", L.HapB200Codec_HapY),
-                        ("HapM", L.HapB200Codec_HapM), ("HapA", L.HapB200Codec_HapA)):
+                        ("HapM", L.HapB200Codec_HapM), ("HapA", L.HapB200Codec_HapA), ("HapY+chroma_refine", L.HapB200Codec_HapY)):
+        lib.set_option(lib.OPTION_CHROMA_REFINE, 1 if name.endswith("refine") else 0)
         nb = lib.texture_bytes(W, H, codec, 0) + lib.texture_bytes(W, H, codec, 1)
         stride = (nb + 15) // 16 * 16
         blocks = torch.empty(F * stride, dtype=torch.uint8, device=dev)
@@ -44,6 +45,7 @@ def main():
         traffic = 4 * W * H + nb
         out[name] = {"encode_us_per_frame": round(enc * 1e3, 2), "encode_GBps": round(traffic / (enc * 1e-3) / 1e9, 1),
                      "decode_us_per_frame": round(dec * 1e3, 2), "decode_GBps": round(traffic / (dec * 1e-3) / 1e9, 1)}
+    lib.set_option(lib.OPTION_CHROMA_REFINE, 0)
     print(json.dumps({"what": "block codec kernels on 3840x2160 frames, %d frames per launch" % F, "per_flavour": out}))
 
 

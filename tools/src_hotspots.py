@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Per-SOURCE-LINE hot spots of one kernel in an .ncu-rep (needs -lineinfo and --import-source on):
-    python tools/src_hotspots.py <report.ncu-rep> <kernel-regex> [top_n]
+    python tools/src_hotspots.py <report.ncu-rep> <kernel-regex> [top_n [inst]]
 Prints, per source line: stall samples, share, warp instructions executed, top stall reasons."""
 import csv
 import subprocess
@@ -10,6 +10,7 @@ import sys
 def main():
     rep, pat = sys.argv[1], sys.argv[2]
     top_n = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    by_inst = len(sys.argv) > 4 and sys.argv[4] == "inst"     # rank the lines by warp instructions instead of stall samples
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda", "--kernel-name",
                           f"regex:{pat}"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -34,7 +35,7 @@ def main():
     inst = sum(l[4] for l in lines) or 1
     print(f"samples {tot}, warp instructions {inst}")
     print(f"{'file:line':<28}{'samples':>8}{'%':>6}{'inst%':>7}  top stalls / source")
-    for f, ln, src, smp, ins, st in sorted(lines, key=lambda l: -l[3])[:top_n]:
+    for f, ln, src, smp, ins, st in sorted(lines, key=lambda l: -(l[4] if by_inst else l[3]))[:top_n]:
         top = ", ".join(f"{k} {v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:2] if v)
         print(f"{f + ':' + str(ln):<28}{smp:>8}{100 * smp / tot:>6.1f}{100 * ins / inst:>7.1f}  [{top}] {src[:90]}")
 
