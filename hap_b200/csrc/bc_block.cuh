@@ -58,6 +58,30 @@ __device__ __forceinline__ int hap_dp4a_us(uint32_t a, uint32_t b, int c)
 }
 #endif
 
+// unsigned x unsigned bytes, and the byte permute (selector nibble n picks byte n of the result from the 8 bytes {a, b})
+#if defined(HAPB200_EMU) || !defined(__CUDA_ARCH__)
+HAP_HD uint32_t hap_dp4a_uu(uint32_t a, uint32_t b, uint32_t c)
+{
+    for (int k = 0; k < 4; k++) c += ((a >> (8 * k)) & 0xFF) * ((b >> (8 * k)) & 0xFF);
+    return c;
+}
+HAP_HD uint32_t hap_prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    const uint64_t v = (uint64_t)a | ((uint64_t)b << 32);
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * k)) & 7))) & 0xFF) << (8 * k);
+    return r;
+}
+#else
+__device__ __forceinline__ uint32_t hap_dp4a_uu(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t hap_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+#endif
+
 HAP_HD int hap_clampi(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
 
 // Three-input min/max, clamp(a+b, 0, c) and saturate: single instructions on sm_100a (VIMNMX3, FMNMX3,
@@ -448,23 +472,43 @@ HAP_HD float snap_pair_centred(float a, float b, float mean, float A2, float B2,
     return best;
 }
 
-// clusters along the segment [lo, hi] of the axis projection d[] -> normal-equation sums; false when degenerate
-HAP_HD bool rgb_cluster_sums(const float d[16], const float x[16], const float y[16], const float z[16], float lo, float hi, RgbFit &F)
+// Texel data never leaves the integer domain: the sixteen texels are kept as RGBA words (px) and as three PLANES of
+// packed bytes (four texels per word), so that every sum over texels is a handful of DP4A instructions --
+//   moments:        sum R, sum R^2, sum R G ...      = DP4A(plane, 0x01010101), DP4A(plane, plane')          (36 for all nine)
+//   projections:    d_t = texel . axis                = DP4A(px[t], axis as four signed bytes)                 (1 per texel)
+//   cluster sums:   sum q, sum q^2, sum q R ...       = DP4A(q bytes, ...) with the cluster numbers q packed 4 to a word (20)
+//   palette search: texel . (P_k - 128)               = DP4A(px[t], palette point as signed bytes)              (4 per texel)
+// -- where the float formulation spends 3 to 6 instructions per texel and channel.  All sums are exact integers below 2^24,
+// so the conversion to float for the 2x2 solve loses nothing.
+struct RgbPlanes { uint32_t r[4], g[4], b[4]; };
+
+// cluster numbers (0..3, one byte each, texel t in byte t%4 of word t/4) along [lo, hi] of the projections d[] -> sums
+HAP_HD bool rgb_cluster_sums(const float d[16], const RgbPlanes &P, float mr, float mg, float mb, float lo, float hi, RgbFit &F)
 {
     const float ext = hi - lo;
     if (!(ext > 1e-6f)) return false;
-    const float sc = 3.0f * (1.0f / ext), c0 = -lo * sc;
-    float Sq = 0.f, Sqq = 0.f, Sqx = 0.f, Sqy = 0.f, Sqz = 0.f;
+    const float sc = 1.0f / ext, c0 = -lo * sc;
+    uint32_t sq = 0, sqq = 0, sqr = 0, sqg = 0, sqb = 0;
 #pragma unroll
-    for (int t = 0; t < 16; t++) {
-        const float q = fminf(fmaxf(rintf(hap_fma(d[t], sc, c0)), 0.0f), 3.0f);
-        Sq += q; Sqq = hap_fma(q, q, Sqq);
-        Sqx = hap_fma(q, x[t], Sqx); Sqy = hap_fma(q, y[t], Sqy); Sqz = hap_fma(q, z[t], Sqz);
+    for (int i = 0; i < 4; i++) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            // q = round(3 sat((d - lo) / ext)) sits in the low mantissa bits of (3 w + magic); four of them share a word
+            // (the magic's own bits add up to a constant that is taken off once)
+            const float q = hap_fma(hap_sat(hap_fma(d[4 * i + j], sc, c0)), 3.0f, kRoundMagic);
+            w += hap_float_bits(q) << (8 * j);
+        }
+        w -= kRoundMagicBits * 0x01010101u;
+        sq = hap_dp4a_uu(w, 0x01010101u, sq); sqq = hap_dp4a_uu(w, w, sqq);
+        sqr = hap_dp4a_uu(w, P.r[i], sqr); sqg = hap_dp4a_uu(w, P.g[i], sqg); sqb = hap_dp4a_uu(w, P.b[i], sqb);
     }
+    const float Sq = (float)sq, Sqq = (float)sqq;
     F.B2 = Sqq * (1.0f / 9.0f);
     F.AB = hap_fma(Sq, 1.0f / 3.0f, -F.B2);
     F.A2 = 16.0f - hap_fma(Sq, 2.0f / 3.0f, -F.B2);
-    F.BXr = Sqx * (1.0f / 3.0f); F.BXg = Sqy * (1.0f / 3.0f); F.BXb = Sqz * (1.0f / 3.0f);
+    // sums about the mean: sum q (R - mr) = sum q R - mr sum q
+    F.BXr = hap_fma(-mr, Sq, (float)sqr) * (1.0f / 3.0f); F.BXg = hap_fma(-mg, Sq, (float)sqg) * (1.0f / 3.0f); F.BXb = hap_fma(-mb, Sq, (float)sqb) * (1.0f / 3.0f);
     return hap_fma(F.A2, F.B2, -(F.AB * F.AB)) >= 1e-4f;
 }
 
@@ -475,23 +519,41 @@ HAP_HD void rgb_solve(const RgbFit &F, float idet, float BX, float &a, float &b)
     b = BX * (F.A2 + F.AB) * idet;
 }
 
+// endpoints of fit F in storage units, put on the 5:6:5 grid (4 candidates per channel); returns the error there
+HAP_HD float rgb_solve_and_snap(const RgbFit &F, float mr, float mg, float mb, float &gar, float &gag, float &gab, float &gbr, float &gbg, float &gbb)
+{
+    const float idet = 1.0f / hap_fma(F.A2, F.B2, -(F.AB * F.AB));
+    float ar, br, ag, bg, ab, bb;
+    rgb_solve(F, idet, F.BXr, ar, br); rgb_solve(F, idet, F.BXg, ag, bg); rgb_solve(F, idet, F.BXb, ab, bb);
+    ar = fminf(fmaxf(ar + mr, 0.f), 255.f); br = fminf(fmaxf(br + mr, 0.f), 255.f);
+    ag = fminf(fmaxf(ag + mg, 0.f), 255.f); bg = fminf(fmaxf(bg + mg, 0.f), 255.f);
+    ab = fminf(fmaxf(ab + mb, 0.f), 255.f); bb = fminf(fmaxf(bb + mb, 0.f), 255.f);
+    return snap_pair_centred(ar, br, mr, F.A2, F.B2, F.AB, F.BXr, 31.f, gar, gbr) +
+           snap_pair_centred(ag, bg, mg, F.A2, F.B2, F.AB, F.BXg, 63.f, gag, gbg) +
+           snap_pair_centred(ab, bb, mb, F.A2, F.B2, F.AB, F.BXb, 31.f, gab, gbb);
+}
+
+// (r, g, b) small signed integers -> the DP4A operand that multiplies a texel word's R, G, B bytes by them (A by 0)
+HAP_HD uint32_t pack_s8x3(int r, int g, int b) { return ((uint32_t)r & 0xFFu) | (((uint32_t)g & 0xFFu) << 8) | (((uint32_t)b & 0xFFu) << 16); }
+
 HAP_HD Block8 encode_rgb_block(const uint32_t px[16])
 {
-    float x[16], y[16], z[16];
-    float mr = 0.f, mg = 0.f, mb = 0.f;
+    RgbPlanes P;
+    uint32_t sr = 0, sg = 0, sb = 0, rr = 0, rg = 0, rb = 0, gg = 0, gb = 0, bb2 = 0;
 #pragma unroll
-    for (int t = 0; t < 16; t++) {
-        x[t] = (float)(px[t] & 0xFF); y[t] = (float)((px[t] >> 8) & 0xFF); z[t] = (float)((px[t] >> 16) & 0xFF);
-        mr += x[t]; mg += y[t]; mb += z[t];
+    for (int i = 0; i < 4; i++) {
+        const uint32_t t0 = hap_prmt(px[4 * i], px[4 * i + 1], 0x5140u), t1 = hap_prmt(px[4 * i + 2], px[4 * i + 3], 0x5140u);
+        const uint32_t t2 = hap_prmt(px[4 * i], px[4 * i + 1], 0x6262u), t3 = hap_prmt(px[4 * i + 2], px[4 * i + 3], 0x6262u);
+        P.r[i] = hap_prmt(t0, t1, 0x5410u); P.g[i] = hap_prmt(t0, t1, 0x7632u); P.b[i] = hap_prmt(t2, t3, 0x5410u);
+        sr = hap_dp4a_uu(P.r[i], 0x01010101u, sr); sg = hap_dp4a_uu(P.g[i], 0x01010101u, sg); sb = hap_dp4a_uu(P.b[i], 0x01010101u, sb);
+        rr = hap_dp4a_uu(P.r[i], P.r[i], rr); rg = hap_dp4a_uu(P.r[i], P.g[i], rg); rb = hap_dp4a_uu(P.r[i], P.b[i], rb);
+        gg = hap_dp4a_uu(P.g[i], P.g[i], gg); gb = hap_dp4a_uu(P.g[i], P.b[i], gb); bb2 = hap_dp4a_uu(P.b[i], P.b[i], bb2);
     }
-    mr *= 0.0625f; mg *= 0.0625f; mb *= 0.0625f;
-    float crr = 0.f, crg = 0.f, crb = 0.f, cgg = 0.f, cgb = 0.f, cbb = 0.f;
-#pragma unroll
-    for (int t = 0; t < 16; t++) {
-        x[t] -= mr; y[t] -= mg; z[t] -= mb;
-        crr = hap_fma(x[t], x[t], crr); crg = hap_fma(x[t], y[t], crg); crb = hap_fma(x[t], z[t], crb);
-        cgg = hap_fma(y[t], y[t], cgg); cgb = hap_fma(y[t], z[t], cgb); cbb = hap_fma(z[t], z[t], cbb);
-    }
+    const float fsr = (float)sr, fsg = (float)sg, fsb = (float)sb;
+    const float mr = fsr * 0.0625f, mg = fsg * 0.0625f, mb = fsb * 0.0625f;
+    // covariance * 16 (exact: every term is an integer below 2^24, the products with 1/16 are exact too)
+    const float crr = hap_fma(-mr, fsr, (float)rr), crg = hap_fma(-mr, fsg, (float)rg), crb = hap_fma(-mr, fsb, (float)rb);
+    const float cgg = hap_fma(-mg, fsg, (float)gg), cgb = hap_fma(-mg, fsb, (float)gb), cbb = hap_fma(-mb, fsb, (float)bb2);
     float gar, gag, gab, gbr, gbg, gbb;   // endpoints on the 5:6:5 grid
     if (crr + cgg + cbb < 0.5f) {
         // flat block: bracket the colour with its grid neighbours so the 4 palette entries straddle it
@@ -512,16 +574,19 @@ HAP_HD Block8 encode_rgb_block(const uint32_t px[16])
             const float inv = 1.0f / fmaxf(fabsf(nr), fmaxf(fabsf(ng), fabsf(nb)));
             vr = nr * inv; vg = ng * inv; vb = nb * inv;
         }
-        // projection on the axis (in units where the endpoints are mean + v * t), once
-        const float ivv = 1.0f / hap_fma(vr, vr, hap_fma(vg, vg, vb * vb));
+        // the axis in 7 bits + sign (its largest component is +-127): a texel's projection is one DP4A.  Only the ORDER and
+        // spacing of the projections matter (they choose the clusters; the endpoints come from the least-squares solve).
+        const int ar8 = (int)rintf(vr * 127.0f), ag8 = (int)rintf(vg * 127.0f), ab8 = (int)rintf(vb * 127.0f);
+        const uint32_t axis = pack_s8x3(ar8, ag8, ab8);
         float d[16];
-        float tmin = 1e30f, tmax = -1e30f;
+        int dmin = 0x7FFFFFFF, dmax = -0x7FFFFFFF;
 #pragma unroll
-        for (int t = 0; t < 16; t++) {
-            d[t] = hap_fma(x[t], vr, hap_fma(y[t], vg, z[t] * vb)) * ivv;
-            tmin = fminf(tmin, d[t]);
-            tmax = fmaxf(tmax, d[t]);
+        for (int t = 0; t < 16; t += 2) {
+            const int d0 = hap_dp4a_us(px[t], axis, 0), d1 = hap_dp4a_us(px[t + 1], axis, 0);
+            d[t] = (float)d0; d[t + 1] = (float)d1;
+            dmin = hap_min3(dmin, d0, d1); dmax = hap_max3(dmax, d0, d1);
         }
+        const float tmin = (float)dmin, tmax = (float)dmax;
         // starts: both ends of the extent moved independently outwards or inwards by 1/5 of its length (2 x 2).
         // (A 3 x 3 grid that also tried 3/5 inwards was measured: its five extra starts win almost never,
         // +0.005 dB for more than twice the work.)
@@ -533,56 +598,43 @@ HAP_HD Block8 encode_rgb_block(const uint32_t px[16])
             const float lo = HAP_RGB_STARTS == 1 ? tmin : tmin + ((float)(st & 1) * 2.0f - 1.0f) * step;
             const float hi = HAP_RGB_STARTS == 1 ? tmax : tmax - ((float)(st >> 1) * 2.0f - 1.0f) * step;
             RgbFit F;
-            if (!rgb_cluster_sums(d, x, y, z, lo, hi, F)) continue;
-            const float idet = 1.0f / hap_fma(F.A2, F.B2, -(F.AB * F.AB));
-            float ar, br, ag, bg, ab, bb;
-            rgb_solve(F, idet, F.BXr, ar, br); rgb_solve(F, idet, F.BXg, ag, bg); rgb_solve(F, idet, F.BXb, ab, bb);
-            // storage units, clamped; scored with plain rounding to the grid
-            ar = fminf(fmaxf(ar + mr, 0.f), 255.f); br = fminf(fmaxf(br + mr, 0.f), 255.f);
-            ag = fminf(fmaxf(ag + mg, 0.f), 255.f); bg = fminf(fmaxf(bg + mg, 0.f), 255.f);
-            ab = fminf(fmaxf(ab + mb, 0.f), 255.f); bb = fminf(fmaxf(bb + mb, 0.f), 255.f);
+            if (!rgb_cluster_sums(d, P, mr, mg, mb, lo, hi, F)) continue;
             // scored AFTER the endpoints are put on the grid (4 candidates per channel): scoring the unquantised or the
             // plainly rounded endpoints picks the wrong start often enough to cost 0.01 ... 0.06 dB
             float s_ar, s_br, s_ag, s_bg, s_ab, s_bb;
-            const float e = snap_pair_centred(ar, br, mr, F.A2, F.B2, F.AB, F.BXr, 31.f, s_ar, s_br) +
-                            snap_pair_centred(ag, bg, mg, F.A2, F.B2, F.AB, F.BXg, 63.f, s_ag, s_bg) +
-                            snap_pair_centred(ab, bb, mb, F.A2, F.B2, F.AB, F.BXb, 31.f, s_ab, s_bb);
+            const float e = rgb_solve_and_snap(F, mr, mg, mb, s_ar, s_ag, s_ab, s_br, s_bg, s_bb);
             if (e < best_e) {
                 best_e = e; have = true;
                 gar = s_ar; gag = s_ag; gab = s_ab; gbr = s_br; gbg = s_bg; gbb = s_bb;
             }
         }
         if (!have) {
-            // no start had two usable clusters: the ends of the extent, rounded
-            gar = grid_round(fminf(fmaxf(hap_fma(vr, tmin, mr), 0.f), 255.f), 31.f); gbr = grid_round(fminf(fmaxf(hap_fma(vr, tmax, mr), 0.f), 255.f), 31.f);
-            gag = grid_round(fminf(fmaxf(hap_fma(vg, tmin, mg), 0.f), 255.f), 63.f); gbg = grid_round(fminf(fmaxf(hap_fma(vg, tmax, mg), 0.f), 255.f), 63.f);
-            gab = grid_round(fminf(fmaxf(hap_fma(vb, tmin, mb), 0.f), 255.f), 31.f); gbb = grid_round(fminf(fmaxf(hap_fma(vb, tmax, mb), 0.f), 255.f), 31.f);
+            // no start had two usable clusters: the ends of the extent, rounded (t = projection / |axis|^2 along the axis)
+            const float fr8 = (float)ar8, fg8 = (float)ag8, fb8 = (float)ab8;
+            const float ivv = 1.0f / fmaxf(hap_fma(fr8, fr8, hap_fma(fg8, fg8, fb8 * fb8)), 1.0f);
+            const float m_ax = hap_fma(mr, fr8, hap_fma(mg, fg8, mb * fb8));
+            const float t0 = (tmin - m_ax) * ivv, t1 = (tmax - m_ax) * ivv;
+            gar = grid_round(fminf(fmaxf(hap_fma(fr8, t0, mr), 0.f), 255.f), 31.f); gbr = grid_round(fminf(fmaxf(hap_fma(fr8, t1, mr), 0.f), 255.f), 31.f);
+            gag = grid_round(fminf(fmaxf(hap_fma(fg8, t0, mg), 0.f), 255.f), 63.f); gbg = grid_round(fminf(fmaxf(hap_fma(fg8, t1, mg), 0.f), 255.f), 63.f);
+            gab = grid_round(fminf(fmaxf(hap_fma(fb8, t0, mb), 0.f), 255.f), 31.f); gbb = grid_round(fminf(fmaxf(hap_fma(fb8, t1, mb), 0.f), 255.f), 31.f);
         } else {
             // Lloyd rounds on the quantised problem: re-cluster against the snapped segment, re-solve, re-snap
 #pragma unroll 1
             for (int rs = 0; rs < HAP_RGB_RESNAP; rs++) {
-                const float ear = grid_expand(gar, 31.f) - mr, eag = grid_expand(gag, 63.f) - mg, eab = grid_expand(gab, 31.f) - mb;
-                const float ebr = grid_expand(gbr, 31.f) - mr, ebg = grid_expand(gbg, 63.f) - mg, ebb = grid_expand(gbb, 31.f) - mb;
-                const float sr_ = ebr - ear, sg_ = ebg - eag, sb_ = ebb - eab;
-                const float ss = hap_fma(sr_, sr_, hap_fma(sg_, sg_, sb_ * sb_));
-                if (ss > 1e-6f) {
-                    // projection of the texels on the snapped segment: p = ((x - ea) . s) / (s . s), in 0..1
-                    const float iss = 1.0f / ss;
+                const int ear = (int)expand5((uint32_t)(int)gar), eag = (int)expand6((uint32_t)(int)gag), eab = (int)expand5((uint32_t)(int)gab);
+                const int sr_ = (int)expand5((uint32_t)(int)gbr) - ear, sg_ = (int)expand6((uint32_t)(int)gbg) - eag, sb_ = (int)expand5((uint32_t)(int)gbb) - eab;
+                // projection of the texels on the snapped segment, p = ((x - ea) . s') / (s . s') with s' = s / 2 as signed
+                // bytes (p is 0 at ea and 1 at eb exactly; the direction is off by half a unit per channel at most)
+                const int hr = sr_ / 2, hg = sg_ / 2, hb = sb_ / 2;
+                const int ss = sr_ * hr + sg_ * hg + sb_ * hb;
+                if (ss > 0) {
+                    const uint32_t seg = pack_s8x3(hr, hg, hb);
+                    const int base = -(ear * hr + eag * hg + eab * hb);
                     float p[16];
 #pragma unroll
-                    for (int t = 0; t < 16; t++) p[t] = hap_fma(x[t] - ear, sr_, hap_fma(y[t] - eag, sg_, (z[t] - eab) * sb_)) * iss;
+                    for (int t = 0; t < 16; t++) p[t] = (float)hap_dp4a_us(px[t], seg, base);
                     RgbFit N;
-                    if (rgb_cluster_sums(p, x, y, z, 0.0f, 1.0f, N)) {
-                        const float idet = 1.0f / hap_fma(N.A2, N.B2, -(N.AB * N.AB));
-                        float ar, br, ag, bg, ab, bb;
-                        rgb_solve(N, idet, N.BXr, ar, br); rgb_solve(N, idet, N.BXg, ag, bg); rgb_solve(N, idet, N.BXb, ab, bb);
-                        ar = fminf(fmaxf(ar + mr, 0.f), 255.f); br = fminf(fmaxf(br + mr, 0.f), 255.f);
-                        ag = fminf(fmaxf(ag + mg, 0.f), 255.f); bg = fminf(fmaxf(bg + mg, 0.f), 255.f);
-                        ab = fminf(fmaxf(ab + mb, 0.f), 255.f); bb = fminf(fmaxf(bb + mb, 0.f), 255.f);
-                        snap_pair_centred(ar, br, mr, N.A2, N.B2, N.AB, N.BXr, 31.f, gar, gbr);
-                        snap_pair_centred(ag, bg, mg, N.A2, N.B2, N.AB, N.BXg, 63.f, gag, gbg);
-                        snap_pair_centred(ab, bb, mb, N.A2, N.B2, N.AB, N.BXb, 31.f, gab, gbb);
-                    }
+                    if (rgb_cluster_sums(p, P, mr, mg, mb, 0.0f, (float)ss, N)) rgb_solve_and_snap(N, mr, mg, mb, gar, gag, gab, gbr, gbg, gbb);
                 }
             }
         }
@@ -602,26 +654,25 @@ HAP_HD Block8 encode_rgb_block(const uint32_t px[16])
         tmp = a5b; a5b = b5b; b5b = tmp;
         out.lo = c0 | (c1 << 16);
     }
-    // exact indices: nearest of the decoder's four palette colours (truncating thirds), DXT numbering 0 = c0, 1 = c1, 2, 3
-    const float e0r = (float)expand5(a5r), e0g = (float)expand6(a6g), e0b = (float)expand5(a5b);
-    const float e1r = (float)expand5(b5r), e1g = (float)expand6(b6g), e1b = (float)expand5(b5b);
-    const float p0r = e0r - mr, p0g = e0g - mg, p0b = e0b - mb, p1r = e1r - mr, p1g = e1g - mg, p1b = e1b - mb;
-    const float q2r = floorf((2.0f * e0r + e1r) * (1.0f / 3.0f) + 0.01f) - mr, q3r = floorf((e0r + 2.0f * e1r) * (1.0f / 3.0f) + 0.01f) - mr;
-    const float q2g = floorf((2.0f * e0g + e1g) * (1.0f / 3.0f) + 0.01f) - mg, q3g = floorf((e0g + 2.0f * e1g) * (1.0f / 3.0f) + 0.01f) - mg;
-    const float q2b = floorf((2.0f * e0b + e1b) * (1.0f / 3.0f) + 0.01f) - mb, q3b = floorf((e0b + 2.0f * e1b) * (1.0f / 3.0f) + 0.01f) - mb;
-    // |x - p|^2 = |x|^2 - 2 x.p + |p|^2: the |x|^2 term is common, so compare  |p|^2 - 2 x.p
-    const float n0 = hap_fma(p0r, p0r, hap_fma(p0g, p0g, p0b * p0b)), n1 = hap_fma(p1r, p1r, hap_fma(p1g, p1g, p1b * p1b));
-    const float n2 = hap_fma(q2r, q2r, hap_fma(q2g, q2g, q2b * q2b)), n3 = hap_fma(q3r, q3r, hap_fma(q3g, q3g, q3b * q3b));
+    // exact indices: nearest of the decoder's four palette colours (truncating thirds), DXT numbering 0 = c0, 1 = c1, 2, 3.
+    // |x - P|^2 = |x|^2 - 2 x.P + |P|^2 and x.P = x.(P - 128) + 128 (R + G + B): the first and the last term are the same for
+    // all four colours, so compare  |P|^2 - 2 x.(P - 128), the dot product being one DP4A with P - 128 as signed bytes
+    const int e0r = (int)expand5(a5r), e0g = (int)expand6(a6g), e0b = (int)expand5(a5b);
+    const int e1r = (int)expand5(b5r), e1g = (int)expand6(b6g), e1b = (int)expand5(b5b);
+    const int q2r = (int)((uint32_t)(2 * e0r + e1r) / 3u), q2g = (int)((uint32_t)(2 * e0g + e1g) / 3u), q2b = (int)((uint32_t)(2 * e0b + e1b) / 3u);
+    const int q3r = (int)((uint32_t)(e0r + 2 * e1r) / 3u), q3g = (int)((uint32_t)(e0g + 2 * e1g) / 3u), q3b = (int)((uint32_t)(e0b + 2 * e1b) / 3u);
+    const uint32_t w0 = pack_s8x3(e0r - 128, e0g - 128, e0b - 128), w1 = pack_s8x3(e1r - 128, e1g - 128, e1b - 128);
+    const uint32_t w2 = pack_s8x3(q2r - 128, q2g - 128, q2b - 128), w3 = pack_s8x3(q3r - 128, q3g - 128, q3b - 128);
+    const int n0 = e0r * e0r + e0g * e0g + e0b * e0b, n1 = e1r * e1r + e1g * e1g + e1b * e1b;
+    const int n2 = q2r * q2r + q2g * q2g + q2b * q2b, n3 = q3r * q3r + q3g * q3g + q3b * q3b;
     uint32_t bits = 0;
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        const float d0 = hap_fma(-2.0f * x[t], p0r, hap_fma(-2.0f * y[t], p0g, hap_fma(-2.0f * z[t], p0b, n0)));
-        const float d1 = hap_fma(-2.0f * x[t], p1r, hap_fma(-2.0f * y[t], p1g, hap_fma(-2.0f * z[t], p1b, n1)));
-        const float d2 = hap_fma(-2.0f * x[t], q2r, hap_fma(-2.0f * y[t], q2g, hap_fma(-2.0f * z[t], q2b, n2)));
-        const float d3 = hap_fma(-2.0f * x[t], q3r, hap_fma(-2.0f * y[t], q3g, hap_fma(-2.0f * z[t], q3b, n3)));
+        const int d0 = n0 - 2 * hap_dp4a_us(px[t], w0, 0), d1 = n1 - 2 * hap_dp4a_us(px[t], w1, 0);
+        const int d2 = n2 - 2 * hap_dp4a_us(px[t], w2, 0), d3 = n3 - 2 * hap_dp4a_us(px[t], w3, 0);
         const uint32_t i01 = d1 < d0 ? 1u : 0u, i23 = d3 < d2 ? 3u : 2u;
-        const uint32_t idx = fminf(d2, d3) < fminf(d0, d1) ? i23 : i01;
-        bits |= idx << (2 * t);
+        const int m01 = d1 < d0 ? d1 : d0, m23 = d3 < d2 ? d3 : d2;
+        bits |= (m23 < m01 ? i23 : i01) << (2 * t);
     }
     out.hi = bits;
     return out;

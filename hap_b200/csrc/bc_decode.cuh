@@ -16,17 +16,10 @@ namespace hapb200 {
 // A block's palette has 4 (colour) or 8 (BC4) byte-sized entries per channel: they fit one or two registers, and
 // PRMT picks four of them at once when its selector holds the four texel indices of a block row, one per nibble.
 // The indices arrive 2 or 3 bits apart; two mask-shift-or steps spread them to nibbles.
+// (hap_prmt: bc_block.cuh)
 #if defined(HAPB200_EMU) || !defined(__CUDA_ARCH__)
-HAP_HD uint32_t hap_prmt(uint32_t a, uint32_t b, uint32_t sel)
-{
-    const uint64_t src = ((uint64_t)b << 32) | a;
-    uint32_t r = 0;
-    for (int k = 0; k < 4; k++) r |= (uint32_t)((src >> (8 * ((sel >> (4 * k)) & 7))) & 0xFF) << (8 * k);
-    return r;
-}
 HAP_HD int hap_min_relu(int a, int b) { int m = a < b ? a : b; return m < 0 ? 0 : m; }
 #else
-__device__ __forceinline__ uint32_t hap_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 __device__ __forceinline__ int hap_min_relu(int a, int b) { return __vimin_s32_relu(a, b); }   // clamp(a, 0, b) for b >= 0
 #endif
 HAP_HD uint32_t spread3_to_nibbles(uint32_t x)   // i0 | i1<<3 | i2<<6 | i3<<9  ->  i0 | i1<<4 | i2<<8 | i3<<12

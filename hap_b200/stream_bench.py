@@ -103,7 +103,7 @@ def run(args, rank, local_rank, world, emit, ClockSampler, measured_peak_hbm):
         assert lib.ring_publish(local_rank, s, state["n"], stream=sp) == 0
         if rank == 0:
             for q in range(world):
-                assert lib.ring_wait(local_rank, slot(k, q), state["n"], 20000, stream=consumer.cuda_stream) == 0
+                assert lib.ring_wait(local_rank, slot(k, q), state["n"], 0, stream=consumer.cuda_stream) == 0
 
     # ---- the NCCL baseline: two sets of local buffers, the delivery of batch i overlaps the encode of batch i+1 ---------
     frames2 = [torch.empty((B, cap), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None

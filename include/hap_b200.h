@@ -48,7 +48,8 @@ int HapB200GetDevice(void);
  *              ... HapB200EncodeRGBABatch(..., out = ring + slot, ..., stream) ...
  *              HapB200RingPublish(device, ring + flagOffset, value, stream)  -- after everything queued on `stream` so far
  *   consumer:  HapB200RingWait(device, ring + flagOffset, value, timeoutMs, stream)  -- work queued on `stream` afterwards sees
- *              the frames; timeoutMs > 0: stop waiting after that long (a dead producer must not hold the GPU), 0: wait for ever
+ *              the frames.  timeoutMs 0: wait for ever, as a stream memory operation (cuStreamWaitValue32: no SM is occupied);
+ *              timeoutMs > 0: a one-thread polling kernel that gives up after that long (a dead producer cannot hold the GPU)
  * Layout inside the ring (slots, flags, lengths) is the caller's; flags are 4-byte words, 4-byte aligned, that only grow.
  * Results: HapResult values (hap.h).  Close / Destroy synchronise the device. */
 #define HAPB200_RING_HANDLE_BYTES 64

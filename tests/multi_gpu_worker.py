@@ -118,7 +118,7 @@ def main():
     if rank == 0:
         cs = torch.cuda.Stream(device=dev)
         for r in range(world):
-            assert lib.ring_wait(local, ring_ptr + r * slot_bytes, 1, 30000, stream=cs.cuda_stream) == 0
+            assert lib.ring_wait(local, ring_ptr + r * slot_bytes, 1, 30000 if r & 1 else 0, stream=cs.cuda_stream) == 0   # both kinds of wait
         cs.synchronize()
 
         class _Ext:

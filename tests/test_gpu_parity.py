@@ -192,7 +192,7 @@ def test_delivery_ring_on_one_device(lib):
     assert r == 0 and ring != 0 and len(handle) == lib.RING_HANDLE_BYTES
     try:
         producer, consumer = torch.cuda.Stream(), torch.cuda.Stream()
-        assert lib.ring_wait(dev.index, ring, 1, 30000, stream=consumer.cuda_stream) == 0      # queued BEFORE the producer runs
+        assert lib.ring_wait(dev.index, ring, 1, 0, stream=consumer.cuda_stream) == 0      # queued BEFORE the producer runs; 0 = stream memory operation
         got = torch.zeros((n, cap), dtype=torch.uint8, device="cuda")
         glen = torch.zeros(n, dtype=torch.int64, device="cuda")
 
@@ -206,6 +206,8 @@ def test_delivery_ring_on_one_device(lib):
         assert lib.encode_rgba_batch(imgs.data_ptr(), n, w * h * 4, w, h, HapB200Codec_HapM, 1, k, ring + header, cap, ring + 64,
                                      stream=producer.cuda_stream) == 0
         assert lib.ring_publish(dev.index, ring, 1, stream=producer.cuda_stream) == 0
+        consumer.synchronize()
+        assert lib.ring_wait(dev.index, ring, 1, 5000, stream=consumer.cuda_stream) == 0       # already there: the polling kernel returns at once
         consumer.synchronize()
         assert torch.equal(glen, used)
         for i in range(n):
