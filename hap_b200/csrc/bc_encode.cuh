@@ -14,6 +14,9 @@ namespace hapb200 {
 enum BcKind : int { kBcDxt1 = 0, kBcDxt5 = 1, kBcYCoCg = 2, kBcRgtc1 = 3, kBcYCoCgPlusAlpha = 4 };
 
 constexpr int kBcThreads = 128;
+#ifndef HAPB200_BC_MIN_BLOCKS
+#define HAPB200_BC_MIN_BLOCKS 1      // (a register cap through more resident CTAs was measured: see DESIGN.md section 4)
+#endif
 
 struct BcGeom {
     uint32_t blocks_x, blocks_y;   // width/4, height/4
@@ -26,7 +29,7 @@ struct BcGeom {
 
 // grid = (ceil(blocks/kBcThreads), frames).  REFINE: the chroma endpoint refinement of the YCoCg kinds (bc_block.cuh).
 template <int KIND, bool REFINE = false>
-__global__ void __launch_bounds__(kBcThreads) bc_encode_kernel(const uint8_t *__restrict__ rgba, BcGeom G,
+__global__ void __launch_bounds__(kBcThreads, HAPB200_BC_MIN_BLOCKS) bc_encode_kernel(const uint8_t *__restrict__ rgba, BcGeom G,
                                                                 uint8_t *__restrict__ out)
 {
     const uint32_t nblocks = G.blocks_x * G.blocks_y;

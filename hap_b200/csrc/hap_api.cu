@@ -247,8 +247,9 @@ struct DevBuf {
     explicit DevBuf(cudaStream_t st) : s(st) {}
     bool alloc(size_t n)
     {
-        if (g_call_mem) return cudaMallocFromPoolAsync(&p, n ? n : 16, g_call_mem, s) == cudaSuccess;
-        return cudaMallocAsync(&p, n ? n : 16, s) == cudaSuccess;
+        n = (n + 31) & ~(size_t)15;   // whole 16-byte cells + one: kernels read their inputs in aligned 16-byte cells
+        if (g_call_mem) return cudaMallocFromPoolAsync(&p, n, g_call_mem, s) == cudaSuccess;
+        return cudaMallocAsync(&p, n, s) == cudaSuccess;
     }
     ~DevBuf() { if (p) cudaFreeAsync(p, s); }
     template <class T> T *as() { return reinterpret_cast<T *>(p); }

@@ -256,26 +256,40 @@ __global__ void __launch_bounds__(kPlaceThreads) hap_place_fragments_kernel(
         if (id != 0 && (uint32_t)t < pieces) out[(uint64_t)frame * out_stride + id + t] = frag_entries[(uint64_t)gfrag * kFragEntryStride + t];
         if (id != 0 && (uint32_t)t + kPlaceThreads < pieces) out[(uint64_t)frame * out_stride + id + t + kPlaceThreads] = frag_entries[(uint64_t)gfrag * kFragEntryStride + t + kPlaceThreads];
     }
-    // destination alignment is arbitrary (headers, tables and earlier chunks are byte-sized):
-    // byte-copy to the first 4-byte boundary, then aligned words assembled from two source words
-    uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
+    // destination alignment is arbitrary (headers, tables and earlier chunks are byte-sized): byte-copy to the first 16-byte
+    // boundary of the DESTINATION, then whole 16-byte groups, each assembled from the two aligned 16-byte source cells that
+    // hold its bytes (two LDG.128, four funnel shifts, one STG.128; the shift is the same for the whole fragment), then a
+    // byte tail of at most 31 bytes.
+    uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
     if (head > n) head = n;
     if ((uint32_t)t < head) dst[t] = src[t];
-    const uint32_t nw = (n - head) >> 2;
+    const uint32_t rem = n - head;
     const uint8_t *s2 = src + head;
-    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + head);
-    const uint32_t mis = (uint32_t)((uintptr_t)s2 & 3);
-    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s2 - mis);
-    uint32_t nw_done = nw;
-    if (mis == 0) {
-        for (uint32_t i = t; i < nw; i += kPlaceThreads) d32[i] = s32[i];
-    } else {
-        // the funnel reads word i+1, which for the last word would reach past the source bytes:
-        // stop one word early and leave the rest to the byte tail
-        nw_done = nw ? nw - 1 : 0;
-        for (uint32_t i = t; i < nw_done; i += kPlaceThreads) d32[i] = __funnelshift_r(s32[i], s32[i + 1], 8 * mis);
+    uint4 *d16 = reinterpret_cast<uint4 *>(dst + head);
+    const uint32_t mis = (uint32_t)((uintptr_t)s2 & 15);
+    const uint4 *s16 = reinterpret_cast<const uint4 *>(s2 - mis);   // (s2 - mis >= the buffer's start: buffers are 16-byte aligned)
+    uint32_t ng = rem >> 4;
+    if (mis != 0) {
+        // group i reads cells i and i+1: keep cell i+1 wholly inside the source bytes (a caller's texture buffer may end with them)
+        const uint32_t whole = (mis + rem) >> 4;
+        const uint32_t lim = whole ? whole - 1 : 0;
+        ng = ng < lim ? ng : lim;
     }
-    const uint32_t done = head + (nw_done << 2);
+    if (mis == 0) {
+        for (uint32_t i = t; i < ng; i += kPlaceThreads) d16[i] = s16[i];
+    } else {
+        const uint32_t ws = mis >> 2, bs = 8 * (mis & 3);
+        for (uint32_t i = t; i < ng; i += kPlaceThreads) {
+            const uint4 a = s16[i], b = s16[i + 1];    // group i = bytes mis+16i .. mis+16i+15 of the cells: cell i+1 holds at least one of them
+            uint32_t w0, w1, w2, w3, w4;
+            if (ws == 0) { w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; }
+            else if (ws == 1) { w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; }
+            else if (ws == 2) { w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; }
+            else { w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; }
+            d16[i] = make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
+        }
+    }
+    const uint32_t done = head + (ng << 4);
     if ((uint32_t)t < n - done) dst[done + t] = src[done + t];
 }
 
