@@ -440,6 +440,24 @@ def run_gpu_arm(args, rank, local_rank, world):
 
         FE, T = args.e2e_frames, max(1, args.e2e_threads)
         n_host = min(FE, F, 16)                      # distinct source frames in pinned host memory, cycled
+        # host side of a deployment: the threads that feed a GPU and their pinned buffers sit on the GPU's own NUMA node
+        # (PCIe DMA to the other socket's memory crosses the inter-socket link).  Linux exposes the node's CPUs per PCI device.
+        numa_cpus, all_cpus = None, None
+        if not args.no_numa:
+            try:
+                pr = torch.cuda.get_device_properties(local_rank)
+                path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+                cpus = set()
+                for part in open(path).read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+                all_cpus = os.sched_getaffinity(0)
+                cpus &= all_cpus
+                if cpus and len(cpus) < len(all_cpus):
+                    numa_cpus = cpus
+                    os.sched_setaffinity(0, numa_cpus)      # this thread allocates (first-touches) the pinned buffers below
+            except Exception:
+                numa_cpus = None
         host_rgba = torch.empty((n_host, H, W, 4), dtype=torch.uint8).pin_memory()
         host_rgba.copy_(A.rgba[:n_host])
         # DXT textures of those frames (made by the block encoder once, outside the timed region): what a host
@@ -457,8 +475,13 @@ def run_gpu_arm(args, rank, local_rank, world):
                 function(p, i)
         cb = DECODE_CB(_cb)
 
+        if numa_cpus:
+            os.sched_setaffinity(0, all_cpus)               # (the buffers are placed; the main thread is free again)
+
         def worker_factory(use_rgba):
             def worker(w):
+                if numa_cpus:
+                    os.sched_setaffinity(0, numa_cpus)      # per thread on Linux
                 usedc, fmtc = C.c_ulong(0), C.c_uint(0)
                 h2d = d2h = 0
                 for i in range(w, FE, T):
@@ -502,6 +525,7 @@ def run_gpu_arm(args, rank, local_rank, world):
             t = float(t.item())
             return {"value": world * FE * RGBA_BYTES / t / 1e9, "unit": "GB/s", "h2d_bytes_per_step": world * h2d,
                     "d2h_bytes_per_step": world * d2h, "frames_per_step": world * FE, "fps": world * FE / t, "host_threads": T * world,
+                    "numa": (f"threads and pinned buffers on the GPU's NUMA node ({len(numa_cpus)} of {len(all_cpus)} CPUs)" if numa_cpus else "not bound"),
                     "api": api + f", pinned host buffers, one frame per call, {T} host threads per GPU, all {world} GPU(s) at once"}
 
         e2e = e2e_leg(False, "HapEncode(host DXT texture) + HapDecode(host frame -> host DXT): the reference's own API boundary")
@@ -761,6 +785,7 @@ def main():
     ap.add_argument("--frames", type=int, default=444, help="device-resident frames per GPU per step")
     ap.add_argument("--e2e-frames", type=int, default=64)
     ap.add_argument("--e2e-threads", type=int, default=16)
+    ap.add_argument("--no-numa", action="store_true", help="e2e legs: do not bind host threads / pinned buffers to the GPU's NUMA node")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the per-configuration encode-only / decode-only lines")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: skip the e2e, extra and CPU legs")

@@ -49,7 +49,10 @@ int HapB200GetDevice(void);
  *              HapB200RingPublish(device, ring + flagOffset, value, stream)  -- after everything queued on `stream` so far
  *   consumer:  HapB200RingWait(device, ring + flagOffset, value, timeoutMs, stream)  -- work queued on `stream` afterwards sees
  *              the frames.  timeoutMs 0: wait for ever, as a stream memory operation (cuStreamWaitValue32: no SM is occupied);
- *              timeoutMs > 0: a one-thread polling kernel that gives up after that long (a dead producer cannot hold the GPU)
+ *              timeoutMs > 0: a one-thread polling kernel that gives up after that long (a dead producer cannot hold the GPU).
+ *              Queue a wait BEHIND the work of its own device that it depends on (a producer on the consumer's GPU publishes
+ *              first, then the wait is queued): streams can share a hardware queue, and a wait at its head holds back what
+ *              follows in it.  Producers on other GPUs are independent of the consumer's queues.
  * Layout inside the ring (slots, flags, lengths) is the caller's; flags are 4-byte words, 4-byte aligned, that only grow.
  * Results: HapResult values (hap.h).  Close / Destroy synchronise the device. */
 #define HAPB200_RING_HANDLE_BYTES 64

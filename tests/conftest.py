@@ -25,3 +25,12 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+def pytest_collection_finish(session):
+    # a GPU test that hangs (a wait nobody satisfies) must fail in minutes, not hold a GPU box until the caller's limit:
+    # pytest-timeout's per-test limit, when the plugin is there and no limit was given on the command line
+    if session.config.pluginmanager.hasplugin("timeout") and not session.config.getoption("timeout", None):
+        for it in session.items:
+            if "gpu" in it.keywords and it.get_closest_marker("timeout") is None:
+                it.add_marker(pytest.mark.timeout(900))

@@ -2,11 +2,13 @@
 # Final 1-GPU validation of the round: tests, bench (both arms), block codecs, ncu launch list + full captures, memcheck
 TAG=${1:-r02z}
 mkdir -p gpurun_out
-(time timeout 1700 python -m pytest tests -m gpu -x -q) > gpurun_out/${TAG}_tests.log 2>&1
+(time timeout 900 python -m pytest tests -m gpu -x -q --timeout 300) > gpurun_out/${TAG}_tests.log 2>&1
 tail -4 gpurun_out/${TAG}_tests.log
 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/${TAG}_ref.json 2> gpurun_out/${TAG}_ref.err
 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 python tools/measure_block_codecs.py 32 > gpurun_out/${TAG}_block_codecs.json 2> gpurun_out/${TAG}_block_codecs.err
+python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-threads 32 > gpurun_out/${TAG}_bench_t32.json 2> gpurun_out/${TAG}_bench_t32.err
+python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-numa > gpurun_out/${TAG}_bench_nonuma.json 2> gpurun_out/${TAG}_bench_nonuma.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:hapb200 -c 200 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --profile --steps 2 --warmup 3 > gpurun_out/${TAG}_ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"snappy_encode_fragments|snappy_execute|bc_encode|hap_place" -c 8 \
@@ -20,3 +22,10 @@ tail -3 gpurun_out/${TAG}_memcheck.log
 head -c 400 gpurun_out/${TAG}_bench.json; echo
 head -c 300 gpurun_out/${TAG}_ref.json; echo
 cat gpurun_out/${TAG}_block_codecs.json
+python - <<PY
+import json
+for n in ("bench","bench_t32","bench_nonuma"):
+    try:
+        d=json.load(open("gpurun_out/${TAG}_%s.json"%n)); print(n, d["value"], d["e2e"]["value"], d["e2e"].get("numa"), d["e2e_rgba"]["value"])
+    except Exception as e: print(n, e)
+PY
