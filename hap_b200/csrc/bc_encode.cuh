@@ -15,7 +15,8 @@ enum BcKind : int { kBcDxt1 = 0, kBcDxt5 = 1, kBcYCoCg = 2, kBcRgtc1 = 3, kBcYCo
 
 constexpr int kBcThreads = 128;
 #ifndef HAPB200_BC_MIN_BLOCKS
-#define HAPB200_BC_MIN_BLOCKS 1      // (a register cap through more resident CTAs was measured: see DESIGN.md section 4)
+#define HAPB200_BC_MIN_BLOCKS 1      // resident CTAs asked for (= register cap).  Hap Q: 7 = the 72 registers the kernel needs anyway (without the bound the
+                                     // compiler took 76 and lost a CTA); RGB kinds: 5 (cap 102 of the 113-117 it takes unbounded): 33.2 vs 35.6 us per 4K frame, 6: 33.5
 #endif
 
 struct BcGeom {
@@ -29,7 +30,7 @@ struct BcGeom {
 
 // grid = (ceil(blocks/kBcThreads), frames).  REFINE: the chroma endpoint refinement of the YCoCg kinds (bc_block.cuh).
 template <int KIND, bool REFINE = false>
-__global__ void __launch_bounds__(kBcThreads, HAPB200_BC_MIN_BLOCKS) bc_encode_kernel(const uint8_t *__restrict__ rgba, BcGeom G,
+__global__ void __launch_bounds__(kBcThreads, (KIND == kBcYCoCg && !REFINE) ? 7 : (KIND == kBcDxt1 || KIND == kBcDxt5) ? 5 : HAPB200_BC_MIN_BLOCKS) bc_encode_kernel(const uint8_t *__restrict__ rgba, BcGeom G,
                                                                 uint8_t *__restrict__ out)
 {
     const uint32_t nblocks = G.blocks_x * G.blocks_y;
