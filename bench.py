@@ -662,6 +662,8 @@ def run_gpu_arm(args, rank, local_rank, world):
         except Exception:
             traffic = None
     stage_frac = {k: (alg_bytes[k] / (stage_ms[k] * 1e-3) / 1e9 / peak if stage_ms[k] > 0 else None) for k in stage_ms}
+    if not args.no_index:
+        stage_frac["snappy_index"] = None       # frames carry their index: the kernel is launched on an empty list
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes[dominant], "ms_per_launch": dom_ms,
