@@ -305,6 +305,15 @@ def extra_config_lines(lib, torch, dev, peak):
             enc_ms = time_on_stream(torch, stream, lambda: rt.encode(sp), iters)
             dec_ms = time_on_stream(torch, stream, lambda: rt.decode(sp), iters)
             rt.check()
+            # where one decode call of this batch spends its time (the library's own CUDA-event stage timer; not a bench value)
+            torch.cuda.synchronize(dev)
+            lib.set_stage_timing(True)
+            lib.stage_times()
+            with torch.cuda.stream(stream):
+                rt.decode(sp)
+            st = lib.stage_times()
+            lib.set_stage_timing(False)
+            dec_stages = {k: round(v[0], 4) for k, v in st.items() if v[1] and k in ("parse", "windows", "snappy_index", "snappy_decode", "collect")}
             frame_bytes = rt.mean_frame_bytes()
             tex_total = sum(rt.tex_bytes[: rt.ntex])
             enc_gbs = F * rt.rgba_bytes / enc_ms / 1e6
@@ -313,7 +322,8 @@ def extra_config_lines(lib, torch, dev, peak):
                         "encode": {"ms_per_frame": enc_ms / F, "fps": F / enc_ms * 1e3, "rgba_GBps": enc_gbs,
                                    "roofline_frac_rgba_read": enc_gbs / peak},
                         "decode": {"ms_per_frame": dec_ms / F, "fps": F / dec_ms * 1e3, "rgba_equiv_GBps": F * rt.rgba_bytes / dec_ms / 1e6,
-                                   "traffic_GBps": dec_traffic / dec_ms / 1e6, "roofline_frac_frame_plus_texture": dec_traffic / dec_ms / 1e6 / peak}})
+                                   "traffic_GBps": dec_traffic / dec_ms / 1e6, "roofline_frac_frame_plus_texture": dec_traffic / dec_ms / 1e6 / peak,
+                                   "stage_ms_per_batch": dec_stages}})
             del rt
             torch.cuda.empty_cache()
         except Exception as e:   # a configuration that does not fit must not hide the others
