@@ -580,15 +580,19 @@ def run_gpu_arm(args, rank, local_rank, world):
         HEADER = 4096
         slot_bytes = HEADER + FD * A.cap
         handle = torch.zeros(lib.RING_HANDLE_BYTES, dtype=torch.uint8, device=dev)
-        ring_ptr = 0
+        ring_ptr, ring_up = 0, 1
         if rank == 0:
             rr, ring_ptr, hb = lib.ring_create(local_rank, world * slot_bytes)
-            assert rr == 0, rr
-            handle.copy_(torch.frombuffer(bytearray(hb), dtype=torch.uint8))
+            ring_up = int(rr == 0)
+            if ring_up:
+                handle.copy_(torch.frombuffer(bytearray(hb), dtype=torch.uint8))
         dist.broadcast(handle, 0)
         if rank != 0:
             rr, ring_ptr = lib.ring_open(local_rank, handle.cpu().numpy().tobytes())
-            assert rr == 0, rr
+            ring_up = int(rr == 0 and ring_ptr != 0)
+        agreed = torch.tensor([ring_up], dtype=torch.int32, device=dev)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN)       # every rank takes the same branch below
+        ring_up = int(agreed.item())
         my_slot = ring_ptr + rank * slot_bytes
         consumer = torch.cuda.Stream(device=dev)
         seq = {"n": 0}
@@ -618,8 +622,15 @@ def run_gpu_arm(args, rank, local_rank, world):
                 t = torch.tensor([max(a0.elapsed_time(a1), a0.elapsed_time(c1)) / reps], dtype=torch.float64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
-        ms_ring, ms_local = timed_ms(into_ring), timed_ms(into_local)
-        if rank == 0:
+        if not ring_up:
+            if rank == 0:
+                delivery["ring"] = {"error": "the delivery ring could not be set up on every rank (HapB200RingCreate / HapB200RingOpen: CUDA IPC between these processes)"}
+                if ring_ptr:
+                    lib.ring_destroy(local_rank, ring_ptr)
+            elif ring_ptr:
+                lib.ring_close(local_rank, ring_ptr)
+        ms_ring, ms_local = (timed_ms(into_ring), timed_ms(into_local)) if ring_up else (None, None)
+        if rank == 0 and ring_up:
             class _Ext:
                 def __init__(self, ptr, nb):
                     self.__cuda_array_interface__ = {"shape": (nb,), "typestr": "|u1", "data": (ptr, False), "version": 2}
@@ -633,10 +644,10 @@ def run_gpu_arm(args, rank, local_rank, world):
                                 "frames_per_s": world * FD / (ms_ring * 1e-3), "lengths_equal_nccl_leg": ring_ok}
             del rt
         barrier()
-        if rank != 0:
+        if ring_up and rank != 0:
             assert lib.ring_close(local_rank, ring_ptr) == 0
         barrier()
-        if rank == 0:
+        if ring_up and rank == 0:
             assert lib.ring_destroy(local_rank, ring_ptr) == 0
 
     if rank != 0:
