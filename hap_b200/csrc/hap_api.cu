@@ -368,42 +368,67 @@ uint32_t launch_block_decode(const uint8_t *blocks, const uint8_t *alpha, uint32
 // Everything after the jobs exist (device array): windows, on-the-fly index, execute, repair of chunks whose embedded
 // index did not hold up.  in_bound / out_bound: upper bounds of the jobs' total compressed / decoded bytes (they size the
 // window list; a list that turns out too short makes the affected chunks report Internal_Error, never overruns).
-uint32_t launch_decode_jobs(ChunkJob *jobs, uint32_t njobs, uint64_t in_bound, uint64_t out_bound, cudaStream_t st, bool may_have_index = true)
-{
-    // windows: up to kIdxParts per 16 KiB of stream from the index kernel (twice: a chunk may be indexed again by the repair
-    // pass), one per fragment of an indexed chunk, one per 64 KiB of a verbatim chunk
-    const uint64_t slots64 = 2 * (in_bound / kIdxWin + njobs) + 16;
-    const uint64_t cap64 = kIdxParts * slots64 + out_bound / kIndexFragBytes + 2ull * njobs + 16;
-    if (cap64 >= (1ull << 31)) return HapResult_Bad_Arguments;
-    const uint32_t win_cap = (uint32_t)cap64, entry_slots = (uint32_t)slots64;
-    DevBuf wins(st), entries(st), done(st), ctl(st);
-    if (!wins.alloc((size_t)win_cap * sizeof(DecWin)) || !entries.alloc((size_t)entry_slots * kIdxThreads) || !done.alloc((size_t)win_cap * 4) ||
-        !ctl.alloc(sizeof(DecodeCtl) + 16)) {
-        cudaGetLastError();
-        return HapResult_Internal_Error;
+// The decode of a list of chunk jobs: first pass (windows -> on-the-fly index for chunks without one -> execute) and the repair
+// pass for chunks whose embedded index did not describe their stream (decoded again as if they had none).  Batch calls queue
+// both passes (the second finds nothing to do on honest frames); HapDecode, which reads the statuses on the host anyway, only
+// launches the repair pass when a chunk asks for it.
+struct DecodePasses {
+    DevBuf wins, entries, done, ctl;
+    ChunkJob *jobs = nullptr;
+    uint32_t njobs = 0, win_cap = 0, entry_slots = 0;
+    cudaStream_t st;
+    explicit DecodePasses(cudaStream_t s) : wins(s), entries(s), done(s), ctl(s), st(s) {}
+
+    uint32_t first(ChunkJob *j, uint32_t n, uint64_t in_bound, uint64_t out_bound)
+    {
+        jobs = j; njobs = n;
+        // windows: up to kIdxParts per 16 KiB of stream from the index kernel (twice: a chunk may be indexed again by the repair
+        // pass), one per fragment of an indexed chunk, one per 64 KiB of a verbatim chunk
+        const uint64_t slots64 = 2 * (in_bound / kIdxWin + njobs) + 16;
+        const uint64_t cap64 = kIdxParts * slots64 + out_bound / kIndexFragBytes + 2ull * njobs + 16;
+        if (cap64 >= (1ull << 31)) return HapResult_Bad_Arguments;
+        win_cap = (uint32_t)cap64; entry_slots = (uint32_t)slots64;
+        if (!wins.alloc((size_t)win_cap * sizeof(DecWin)) || !entries.alloc((size_t)entry_slots * kIdxThreads) || !done.alloc((size_t)win_cap * 4) ||
+            !ctl.alloc(sizeof(DecodeCtl) + 16)) {
+            cudaGetLastError();
+            return HapResult_Internal_Error;
+        }
+        if (cudaMemsetAsync(ctl.p, 0, sizeof(DecodeCtl) + 16, st) != cudaSuccess || cudaMemsetAsync(done.p, 0, (size_t)win_cap * 4, st) != cudaSuccess) {
+            cudaGetLastError();
+            return HapResult_Internal_Error;
+        }
+        DecodeCtl *c = ctl.as<DecodeCtl>();
+        const unsigned ex_grid = (unsigned)sm_count() * (unsigned)HAPB200_EX_MIN_BLOCKS;
+        HAP_KLAUNCH(kStWindows, hap_build_windows_kernel, dim3((njobs + 127) / 128), dim3(128), 0, st, jobs, njobs, (uint32_t)g_use_index.load(),
+                    wins.as<DecWin>(), win_cap, c);
+        HAP_KLAUNCH(kStSnappyIndex, snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), st, jobs, (int)njobs, 0u,
+                    wins.as<DecWin>(), win_cap, entries.as<uint8_t>(), entry_slots, c);
+        HAP_KLAUNCH(kStSnappyDecode, snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), st, jobs, njobs, 0u, wins.as<DecWin>(), c,
+                    done.as<uint32_t>());
+        return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
     }
-    if (cudaMemsetAsync(ctl.p, 0, sizeof(DecodeCtl) + 16, st) != cudaSuccess || cudaMemsetAsync(done.p, 0, (size_t)win_cap * 4, st) != cudaSuccess) {
-        cudaGetLastError();
-        return HapResult_Internal_Error;
-    }
-    DecodeCtl *c = ctl.as<DecodeCtl>();
-    uint32_t *any_left = reinterpret_cast<uint32_t *>(ctl.as<uint8_t>() + sizeof(DecodeCtl));
-    const unsigned ex_grid = (unsigned)sm_count() * (unsigned)HAPB200_EX_MIN_BLOCKS;
-    HAP_KLAUNCH(kStWindows, hap_build_windows_kernel, dim3((njobs + 127) / 128), dim3(128), 0, st, jobs, njobs, (uint32_t)g_use_index.load(),
-                wins.as<DecWin>(), win_cap, c);
-    HAP_KLAUNCH(kStSnappyIndex, snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), st, jobs, (int)njobs, 0u,
-                wins.as<DecWin>(), win_cap, entries.as<uint8_t>(), entry_slots, c);
-    HAP_KLAUNCH(kStSnappyDecode, snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), st, jobs, njobs, 0u, wins.as<DecWin>(), c,
-                done.as<uint32_t>());
-    if (g_use_index.load() && may_have_index) {
-        // chunks whose embedded index did not describe their stream: decode them again as if they had none
+
+    // chunks whose embedded index did not describe their stream: decode them again as if they had none
+    uint32_t repair()
+    {
+        DecodeCtl *c = ctl.as<DecodeCtl>();
+        uint32_t *any_left = reinterpret_cast<uint32_t *>(ctl.as<uint8_t>() + sizeof(DecodeCtl));
+        const unsigned ex_grid = (unsigned)sm_count() * (unsigned)HAPB200_EX_MIN_BLOCKS;
         HAP_KLAUNCH(kStWindows, hap_requeue_mismatched_kernel, dim3((njobs + 127) / 128), dim3(128), 0, st, jobs, njobs, any_left);
         HAP_KLAUNCH(kStSnappyIndex, snappy_index_kernel, dim3(njobs), dim3(kIdxThreads), sizeof(IndexSmem), st, jobs, (int)njobs, 1u,
                     wins.as<DecWin>(), win_cap, entries.as<uint8_t>(), entry_slots, c);
         HAP_KLAUNCH(kStSnappyDecode, snappy_execute_kernel, dim3(ex_grid), dim3(kExThreads), sizeof(ExecSmem), st, jobs, njobs, 1u, wins.as<DecWin>(),
                     c, done.as<uint32_t>());
+        return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
     }
-    return cudaGetLastError() == cudaSuccess ? HapResult_No_Error : HapResult_Internal_Error;
+};
+
+uint32_t launch_decode_jobs(ChunkJob *jobs, uint32_t njobs, uint64_t in_bound, uint64_t out_bound, cudaStream_t st, bool may_have_index = true)
+{
+    DecodePasses P(st);
+    uint32_t r = P.first(jobs, njobs, in_bound, out_bound);
+    if (r == HapResult_No_Error && g_use_index.load() && may_have_index) r = P.repair();
+    return r;
 }
 
 // device frames -> texture `index` of each; jobs scratch is allocated here
@@ -1059,7 +1084,8 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
         }
         if (!djobs.alloc(jobs.size() * sizeof(ChunkJob)) ||
             cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(ChunkJob), cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
-        r = launch_decode_jobs(djobs.as<ChunkJob>(), (uint32_t)jobs.size(), in_sum, produced, st, any_index);   // no index in the frame: no repair pass to launch
+        DecodePasses passes(st);
+        r = passes.first(djobs.as<ChunkJob>(), (uint32_t)jobs.size(), in_sum, produced);
         if (r != HapResult_No_Error) return r;
         if (compressor == kHapComplex && jobs.size() > 1) {
             WorkState ws;
@@ -1067,6 +1093,14 @@ unsigned int HapDecode(const void *inputBuffer, unsigned long inputBufferBytes, 
         }
         if (cudaMemcpyAsync(jobs.data(), djobs.p, jobs.size() * sizeof(ChunkJob), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+        bool mismatch = false;     // a chunk whose embedded index failed the execute kernel's checks: the repair pass, then the statuses again
+        for (size_t i = 0; i < jobs.size(); i++) mismatch = mismatch || jobs[i].status == kStatusIndexMismatch;
+        if (mismatch) {
+            r = passes.repair();
+            if (r != HapResult_No_Error) return r;
+            if (cudaMemcpyAsync(jobs.data(), djobs.p, jobs.size() * sizeof(ChunkJob), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return HapResult_Internal_Error; }
+        }
         for (size_t i = 0; i < jobs.size(); i++)
             if (jobs[i].status != HapResult_No_Error) return whole ? (uint32_t)HapResult_Internal_Error : jobs[i].status;  // hap.c:867-875, :899-903
         if (!out_dev && produced) {

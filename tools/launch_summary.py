@@ -16,7 +16,7 @@ def main():
     per = {}
     for r in data:
         name = r[ix["Kernel Name"]]
-        if "hapb200::" not in name:
+        if not any(k in name for k in ("bc_encode_kernel", "bc_decode_kernel", "snappy_", "hap_")):     # (torch's kernels: at::native::...)
             continue
         short = name.split("(")[0].replace("hapb200::", "").replace("void ", "").strip()
         ms = float(r[ix["Metric Value"]]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r[ix["Metric Unit"]], 1e-6)
