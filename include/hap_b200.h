@@ -81,7 +81,7 @@ unsigned int HapB200RingWait(int device, const void *flag, unsigned int value, u
 /* HAPB200_OPTION_CHROMA_REFINE: the scaled-YCoCg block encoders (Hap Q, Hap Q Alpha) score the 5-bit Co' endpoint
  * candidates of blocks with less than one grid cell of Co' extent by their true error (every texel re-assigned) instead of
  * with the clusters of the unquantised fit held fixed.  Closes the encoder's one deficit against the cluster-fit oracle
- * beyond the 0.1 dB bar (slow colour ramps, 1080p: -0.47 dB -> -0.06 dB; video content +0.61 -> +0.65 dB) for +58 % block-encode
+ * beyond the 0.1 dB bar (slow colour ramps, 1080p: -0.47 dB -> -0.06 dB; video content +0.61 -> +0.65 dB) for +60-70 % block-encode
  * time on 4K footage (half of its blocks qualify).  Default 0.  Environment: HAPB200_CHROMA_REFINE. */
 #define HAPB200_OPTION_CHROMA_REFINE 4
 int HapB200SetOption(int option, int value);
