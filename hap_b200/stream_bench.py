@@ -2,14 +2,14 @@
 64 chunks, Snappy), frames sharded round-robin over the GPUs of one box, the ENCODED frames delivered to rank 0 (where a
 muxer would sit) inside the timed region.
 
-One process per GPU (torchrun).  Two ways to deliver, both timed:
+One process per GPU (torchrun).  Two ways to deliver, both timed; `value` is the faster one at the N at hand (`delivery` names it):
 
-  peer (the product path, `value`): rank 0 owns a delivery ring (HapB200RingCreate, CUDA IPC).  Every rank passes an
+  ring: rank 0 owns a delivery ring (HapB200RingCreate, CUDA IPC).  Every rank passes an
       address INSIDE that ring as the output of HapB200EncodeRGBABatch: the kernel that lays a frame out stores it over
       NVLink / NVSwitch straight into rank 0's memory, the frame lengths go to the slot's header the same way, and a
       release store publishes the slot (HapB200RingPublish).  Rank 0's consumer stream waits on the flags
       (HapB200RingWait).  No staging copy, no collective, no host synchronisation inside a step.
-  nccl (the baseline, `nccl_gatherv_baseline`): encode into local memory, all-gather the lengths, grouped
+  nccl (`nccl_gatherv_baseline`): encode into local memory, all-gather the lengths, grouped
       ncclSend/ncclRecv of exactly the encoded bytes (sharding.gatherv_frames_to_root), the delivery of batch i
       overlapping the encode of batch i+1.
 
@@ -248,6 +248,7 @@ def run(args, rank, local_rank, world, emit, ClockSampler, measured_peak_hbm):
                      "unit": "GB/s", "frac": B * rgba_bytes / (ms_enc_step * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
         "clocks": clocks, "gpu_launches": launches,
     }
+    line["delivery"] = "ring"
     if ms_nccl is not None:
         ms_n = ms_nccl / args.steps
         line["nccl_gatherv_baseline"] = {
@@ -255,6 +256,19 @@ def run(args, rank, local_rank, world, emit, ClockSampler, measured_peak_hbm):
                     "batch i overlapping the encode of batch i+1", "ms_per_step": ms_n, "fps": frames_per_step / (ms_n * 1e-3),
             "value": frames_per_step * rgba_bytes / (ms_n * 1e-3) / 1e9, "nvlink_bytes_per_step": moved["bytes"],
             "nvlink_GBps_into_rank0": moved["bytes"] / (ms_n * 1e-3) / 1e9}
+        if ms_n < ms_step:
+            # Measured on this pool: the ring wins at N=2 (1 550 vs 1 380 frames/s); from N=4 on rank 0's NVLink ingress is the
+            # bound (2.9 GB per step at N=8) and a layout kernel that stores remotely holds its SMs while the link is busy, whereas
+            # NCCL's copies run beside the next batch's encode (N=8: 2 690 vs 3 490 frames/s).  The headline is the faster delivery
+            # at this N; both are in the line.
+            b = line["nccl_gatherv_baseline"]
+            line["ring_delivery"] = {"ms_per_step": ms_step, "fps": fps, "value": line["value"], "nvlink_GBps_into_rank0": line["nvlink_GBps_into_rank0"],
+                                     "delivery_share_of_step": line["delivery_share_of_step"]}
+            line.update({"delivery": "nccl_gatherv", "value": b["value"], "fps": b["fps"], "ms_per_step": b["ms_per_step"],
+                         "nvlink_bytes_per_step": b["nvlink_bytes_per_step"], "nvlink_GBps_into_rank0": b["nvlink_GBps_into_rank0"],
+                         "delivery_share_of_step": max(0.0, 1.0 - ms_enc_step / b["ms_per_step"])})
+            line["config"]["parallelism"] = (f"dp{world}: frames encoded into local memory, all-gather of the lengths + grouped ncclSend/ncclRecv to rank 0 overlapping "
+                                             "the next batch's encode (faster than the delivery ring at this N: `ring_delivery`)")
     emit(line)
     assert lib.ring_destroy(local_rank, ring) == 0
     if world > 1:
