@@ -590,28 +590,6 @@ extern "C" {
 const char *HapB200Version(void) { return "hap-b200 0.1 (sm_100a)"; }
 unsigned long long HapB200KernelLaunchCount(void) { return g_launches.load(); }
 
-// Cycle counters of K7's phases (stage window, parse fixpoint, scans, descriptors, execute), summed over
-// CTAs by thread 0 of each; a profiling aid for kernel work, not part of the stable API.
-int HapB200DebugDecodePhaseCycles(unsigned long long *out, int n, int reset)
-{
-#ifndef HAPB200_DECODE_PHASE_CYCLES
-    (void)out; (void)n; (void)reset;
-    return -1;  // built without the counters
-#else
-    unsigned long long h[8] = {0};
-    if (cudaMemcpyFromSymbol(h, g_decode_phase_cycles, sizeof h) != cudaSuccess) { cudaGetLastError(); return -1; }
-    for (int i = 0; i < n && i < 8; i++) out[i] = h[i];
-    if (n >= 16 && cudaMemcpyFromSymbol(h, g_decode_counts, sizeof h) == cudaSuccess)
-        for (int i = 0; i < 8; i++) out[8 + i] = h[i];
-    if (reset) {
-        unsigned long long z[8] = {0};
-        cudaMemcpyToSymbol(g_decode_phase_cycles, z, sizeof z);
-        cudaMemcpyToSymbol(g_decode_counts, z, sizeof z);
-    }
-    return 8;
-#endif
-}
-
 // The device host-pointer calls run on (device-pointer calls run where their buffers live).  -1: forget it; the next
 // host-pointer call takes its thread's current device.
 int HapB200SetDevice(int device)

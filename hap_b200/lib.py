@@ -106,14 +106,6 @@ class HapB200(HapABI):
             "bc_decode": F * (texture_bytes + rgba_bytes),
         }
 
-    def decode_phase_cycles(self, reset=True):
-        out = (C.c_ulonglong * 16)()
-        self.lib.HapB200DebugDecodePhaseCycles(out, 16, 1 if reset else 0)
-        self.last_decode_counts = {"windows": int(out[8]), "elements": int(out[9]), "execute_rounds": int(out[10])}
-        # kernel marks: 0 stage, 5 exit tables, 6 chain hop, 1 walk, 2 scans, 3 descriptors+runs, 7 flatten, 4 execute
-        names = {0: "stage", 5: "exit_tables", 6: "chain_hop", 1: "walk", 2: "scan", 3: "describe", 7: "flatten", 4: "execute"}
-        return {names[i]: int(out[i]) for i in (0, 5, 6, 1, 2, 3, 7, 4)}
-
     def max_encoded_length_rgba(self, w, h, codec, chunks) -> int:
         return int(self.lib.HapB200MaxEncodedLengthRGBA(w, h, codec, chunks))
 
